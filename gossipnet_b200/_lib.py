@@ -1,0 +1,84 @@
+"""ctypes binding of the C ABI in include/gossipnet_b200.h.
+
+There is NO fallback: if the shared library is missing the import of any
+compute entry point raises, and every non-zero return code raises with the
+library's own message.
+"""
+import ctypes
+import os
+
+from gossipnet_b200.build import LIB_PATH
+
+c_int = ctypes.c_int
+c_float = ctypes.c_float
+c_void_p = ctypes.c_void_p
+
+# name -> argtypes; every function returns int unless listed in _RESTYPES
+SIGNATURES = {
+    'gn_last_error': [],
+    'gn_abi_version': [],
+    'gn_sm_count': [],
+    'gn_iou_dense': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                     c_void_p, c_void_p],
+    'gn_neighbor_count': [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_void_p],
+    'gn_exclusive_scan': [c_void_p, c_int, c_void_p, c_void_p],
+    'gn_neighbor_fill': [c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int, c_void_p,
+                         c_void_p, c_void_p, c_void_p, c_void_p],
+    'gn_pair_geometry': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_int, c_int, c_float, c_void_p, c_void_p],
+    'gn_pwfeat_mlp_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    'gn_fc_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
+                  c_int, c_void_p, c_int, c_int, c_void_p],
+    'gn_block_gather_concat': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p, c_int, c_void_p, c_void_p],
+    'gn_segment_max': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    'gn_block_pair_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                          c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                          c_void_p, c_void_p],
+    'gn_detection_matching': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p],
+    'gn_loss_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                    c_void_p, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p,
+                    c_void_p],
+}
+_RESTYPES = {'gn_last_error': ctypes.c_char_p}
+
+_lib = None
+
+
+class GossipnetError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes library; raise if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GossipnetError(
+                'CUDA extension %s is missing: run `python -c "import __graft_entry__ as g; '
+                'g.build()"` (there is no CPU fallback)' % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, c_int)
+        _lib = lib
+    return _lib
+
+
+def call(name, *args):
+    """Call an int-returning entry point; raise on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.gn_last_error()
+        msg = msg.decode() if msg else ''
+        if rc == 1:
+            raise ValueError('%s: %s' % (name, msg))
+        if rc == 3:
+            raise NotImplementedError('%s: %s' % (name, msg))
+        raise GossipnetError('%s failed (%d): %s' % (name, rc, msg))

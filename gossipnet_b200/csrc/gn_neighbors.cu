@@ -1,0 +1,185 @@
+// Neighbor build (A3): ordered compaction of {(c, n) : iou(c, n) >= thresh} into
+// CSR form without materialising the dense N x N matrix.  IoU is recomputed from
+// the boxes with the same rounded arithmetic as gn_iou_dense, so the lists are
+// bit-identical to thresholding the dense matrix (tf.where order: row-major).
+//
+// One warp owns NB_ROWS_PER_WARP consecutive rows; lanes stride over the columns
+// of that image, so each column box is loaded once per warp (coalesced 512 B)
+// and reused from registers for all of the warp's rows.  Order inside a row is
+// kept with ballot + popc prefix counts.
+#include "gn_common.cuh"
+
+namespace gn {
+
+constexpr int NB_THREADS = 256;
+constexpr int NB_ROWS_PER_WARP = 4;
+constexpr int NB_ROWS_PER_CTA = (NB_THREADS / 32) * NB_ROWS_PER_WARP;
+
+template <bool FILL>
+__global__ void __launch_bounds__(NB_THREADS)
+neighbor_kernel(const float* __restrict__ dets, const int32_t* __restrict__ img_off,
+                int num_images, int num_dets, float thresh,
+                const int32_t* __restrict__ row_ptr, int capacity,
+                int32_t* __restrict__ degree, int32_t* __restrict__ pair_c,
+                int32_t* __restrict__ pair_n, float* __restrict__ pair_iou,
+                int32_t* __restrict__ overflow) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * NB_ROWS_PER_CTA + warp * NB_ROWS_PER_WARP;
+  if (row0 >= num_dets) return;
+
+  // The warp's rows may straddle an image boundary: handle each row's own range.
+  Box rb[NB_ROWS_PER_WARP];
+  int lo[NB_ROWS_PER_WARP], hi[NB_ROWS_PER_WARP], cnt[NB_ROWS_PER_WARP], base[NB_ROWS_PER_WARP];
+  int col_lo = 0x7fffffff, col_hi = 0;
+#pragma unroll
+  for (int i = 0; i < NB_ROWS_PER_WARP; ++i) {
+    const int r = row0 + i;
+    cnt[i] = 0;
+    if (r < num_dets) {
+      const int img = find_image(img_off, num_images, r);
+      lo[i] = __ldg(img_off + img);
+      hi[i] = __ldg(img_off + img + 1);
+      rb[i] = make_box(ldg4(dets + (size_t)r * 4));
+      base[i] = FILL ? __ldg(row_ptr + r) : 0;
+      col_lo = min(col_lo, lo[i]);
+      col_hi = max(col_hi, hi[i]);
+    } else {
+      lo[i] = hi[i] = 0;
+      base[i] = 0;
+      rb[i] = Box{0.f, 0.f, 0.f, 0.f, 0.f};
+    }
+  }
+
+  for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
+    const int c = c0 + lane;
+    const bool in_range = c < col_hi;
+    const Box cb = make_box(in_range ? ldg4(dets + (size_t)c * 4) : make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+    for (int i = 0; i < NB_ROWS_PER_WARP; ++i) {
+      const float v = box_iou(rb[i], cb);
+      const bool hit = in_range && c >= lo[i] && c < hi[i] && (v >= thresh);
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (FILL) {
+        if (hit) {
+          const int pos = base[i] + cnt[i] + __popc(mask & ((1u << lane) - 1u));
+          if (pos < capacity) {
+            pair_c[pos] = row0 + i;
+            pair_n[pos] = c;
+            pair_iou[pos] = v;
+          }
+        }
+      }
+      cnt[i] += __popc(mask);
+    }
+  }
+
+  if (!FILL) {
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NB_ROWS_PER_WARP; ++i)
+        if (row0 + i < num_dets) degree[row0 + i] = cnt[i];
+    }
+  } else if (lane == 0 && overflow != nullptr) {
+#pragma unroll
+    for (int i = 0; i < NB_ROWS_PER_WARP; ++i)
+      if (row0 + i < num_dets && base[i] + cnt[i] > capacity) *overflow = 1;
+  }
+}
+
+// Single-CTA exclusive scan with a running carry: out[0..n] (out[n] = total).
+// n is at most a few hundred thousand detections, the scan is latency-bound and
+// a single pass over L2-resident data; one CTA of 1024 threads x 4 items.
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+exclusive_scan_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out) {
+  __shared__ int warp_sums[SCAN_THREADS / 32];
+  __shared__ int carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += SCAN_THREADS * SCAN_ITEMS) {
+    const int i0 = base + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int tsum = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      v[j] = (i0 + j < n) ? in[i0 + j] : 0;
+      tsum += v[j];
+    }
+    int incl = tsum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += t;
+      }
+      warp_sums[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int excl = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + incl - tsum;
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) {
+      if (i0 + j < n) out[i0 + j] = excl;
+      excl += v[j];
+    }
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1) carry_s = carry + warp_sums[SCAN_THREADS / 32 - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry_s;
+}
+
+}  // namespace gn
+
+extern "C" int gn_neighbor_count(const float* dets, const int32_t* img_off, int num_images,
+                                 int num_dets, float thresh, int32_t* degree,
+                                 gn_stream_t stream) {
+  GN_REQUIRE(num_images >= 0 && num_dets >= 0, "gn_neighbor_count: negative size");
+  if (num_dets == 0) return GN_OK;
+  GN_REQUIRE(dets && img_off && degree, "gn_neighbor_count: null pointer");
+  GN_REQUIRE(num_images > 0, "gn_neighbor_count: detections without images");
+  GN_REQUIRE(((uintptr_t)dets & 15) == 0, "gn_neighbor_count: dets must be 16-byte aligned");
+  const int grid = gn::ceil_div(num_dets, gn::NB_ROWS_PER_CTA);
+  gn::neighbor_kernel<false><<<grid, gn::NB_THREADS, 0, (cudaStream_t)stream>>>(
+      dets, img_off, num_images, num_dets, thresh, nullptr, 0, degree, nullptr, nullptr,
+      nullptr, nullptr);
+  GN_CHECK_LAUNCH("gn_neighbor_count");
+  return GN_OK;
+}
+
+extern "C" int gn_exclusive_scan(const int32_t* in, int n, int32_t* out, gn_stream_t stream) {
+  GN_REQUIRE(n >= 0, "gn_exclusive_scan: negative size");
+  GN_REQUIRE(out != nullptr && (in != nullptr || n == 0), "gn_exclusive_scan: null pointer");
+  gn::exclusive_scan_kernel<<<1, gn::SCAN_THREADS, 0, (cudaStream_t)stream>>>(in, n, out);
+  GN_CHECK_LAUNCH("gn_exclusive_scan");
+  return GN_OK;
+}
+
+extern "C" int gn_neighbor_fill(const float* dets, const int32_t* img_off, int num_images,
+                                int num_dets, float thresh, const int32_t* row_ptr,
+                                int capacity, int32_t* pair_c, int32_t* pair_n,
+                                float* pair_iou, int32_t* overflow, gn_stream_t stream) {
+  GN_REQUIRE(num_images >= 0 && num_dets >= 0 && capacity >= 0, "gn_neighbor_fill: negative size");
+  if (num_dets == 0) return GN_OK;
+  GN_REQUIRE(dets && img_off && row_ptr && pair_c && pair_n && pair_iou,
+             "gn_neighbor_fill: null pointer");
+  GN_REQUIRE(num_images > 0, "gn_neighbor_fill: detections without images");
+  const int grid = gn::ceil_div(num_dets, gn::NB_ROWS_PER_CTA);
+  gn::neighbor_kernel<true><<<grid, gn::NB_THREADS, 0, (cudaStream_t)stream>>>(
+      dets, img_off, num_images, num_dets, thresh, row_ptr, capacity, nullptr, pair_c, pair_n,
+      pair_iou, overflow);
+  GN_CHECK_LAUNCH("gn_neighbor_fill");
+  return GN_OK;
+}

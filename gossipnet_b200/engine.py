@@ -1,0 +1,260 @@
+"""Batched Gnet forward on one B200: the host-side sequencing of the C-ABI calls.
+
+One `GnetEngine` owns the flat parameter buffer and a grow-only workspace and
+runs the whole hot path for a BATCH of images whose
+detections are concatenated (`img_off[num_images+1]`): neighbor build ->
+pair-feature MLP -> `num_blocks` blocks -> predict head (-> det/GT IoU ->
+DetectionMatching -> loss when ground truth is given).  Every step is one call
+into libgossipnet_b200.so on torch's current stream; nothing here computes.
+
+The pair count P is data dependent.  It stays on the device (`row_ptr[T]`) and
+every pair kernel reads it there, so a forward never synchronises: buffers are
+sized by a `capacity` the engine learns on its first call (one sync, then
+grow-only with a 25 % margin) and an overflow flag is checked by the caller
+together with the result it reads back anyway (`check_overflow`).  That makes
+`forward` CUDA-graph capturable (bench.py does so).
+
+Reference: nms_net/network.py:148-322 (graph construction order), :344-409
+(block), :257-273 (predict head), :275-314 (loss).
+"""
+import numpy as np
+import torch
+
+from gossipnet_b200 import ops
+from gossipnet_b200 import params as P
+
+
+class CapacityOverflow(RuntimeError):
+    """More neighbor pairs than the workspace was sized for; the engine has
+    grown its capacity, call forward again."""
+
+
+class GnetEngine(object):
+
+    def __init__(self, num_classes, cfg, device='cuda', flat_params=None, seed=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('gossipnet_b200 needs a CUDA device: the hot path has no CPU '
+                               'fallback')
+        ops._lib.load()  # fail loudly now if the extension is not built
+        self.device = torch.device(device)
+        self.num_classes = int(num_classes)
+        self.multiclass = self.num_classes > 1
+        g = cfg.gnet
+        # snapshot of the hyper-parameters the path reads (cfg is a mutable global)
+        self.g = dict((k, g[k]) for k in (
+            'neighbor_thresh', 'shortcut_dim', 'num_blocks', 'reduced_dim', 'pairfeat_dim',
+            'num_block_pw_fc', 'num_block_fc', 'num_predict_fc', 'predict_fc_dim',
+            'neighbor_feats', 'num_pwfeat_fc', 'pwfeat_dim', 'pwfeat_narrow_dim',
+            'pw_feat_multiplyer'))
+        self.normalize_loss = bool(cfg.train.normalize_loss)
+        self.loss_multiplyer = float(cfg.train.loss_multiplyer)
+        self.layout, self.total = P.param_layout(num_classes, cfg)
+        if flat_params is None:
+            flat_params = P.init_flat(self.layout, self.total, cfg, seed=seed)
+        if isinstance(flat_params, np.ndarray):
+            flat_params = torch.from_numpy(np.ascontiguousarray(flat_params, dtype=np.float32))
+        if flat_params.numel() != self.total:
+            raise ValueError('flat parameter buffer has %d elements, layout needs %d'
+                             % (flat_params.numel(), self.total))
+        self.flat = flat_params.to(self.device, torch.float32).contiguous()
+        self.p = P.views(self.layout, self.flat)
+
+        self.raw_width = P.raw_pairfeat_width(num_classes)
+        self.pw_width = g.pwfeat_narrow_dim if g.num_pwfeat_fc > 0 else self.raw_width
+        # the fused kernels are built for the shipped shapes; anything else runs
+        # through the unfused CUDA pieces (same results, more HBM traffic)
+        self.fused_pw = (g.num_pwfeat_fc == 3 and g.pwfeat_dim == 256
+                         and g.pwfeat_narrow_dim == 32)
+        self.fused_block = (self.pw_width == 32 and g.reduced_dim == 32
+                            and g.pairfeat_dim == 64 and g.num_block_pw_fc == 2)
+        self.capacity = 0
+        self._ws = {}
+        self.keep_block_feats = False
+        self.use_fused = True
+
+    # ------------------------------------------------------------------ workspace
+    def _buf(self, name, shape, dtype=torch.float32):
+        n = int(np.prod(shape))
+        t = self._ws.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._ws[name] = t
+        return t[:n].view(*shape)
+
+    def _ensure_capacity(self, num_pairs_dev, num_dets):
+        if self.capacity == 0:
+            p = int(num_pairs_dev.item())  # the one sync of the engine's lifetime
+            self.capacity = max(1024, int(p * 1.25) + 256)
+        return self.capacity
+
+    def check_overflow(self):
+        """Call after reading a result back: raises CapacityOverflow (after
+        growing) if the last forward saw more pairs than it had room for."""
+        p = int(self._last_num_pairs.item())
+        if p > self._last_capacity:
+            self.capacity = int(p * 1.25) + 256
+            raise CapacityOverflow('P=%d > capacity=%d' % (p, self._last_capacity))
+        return p
+
+    # -------------------------------------------------------------------- forward
+    def neighbors(self, dets, img_off):
+        """A3. -> (row_ptr[T+1], num_pairs_dev[1], pair_c, pair_n, pair_iou, capacity)."""
+        T = dets.shape[0]
+        degree = self._buf('degree', (T,), torch.int32)
+        row_ptr = self._buf('row_ptr', (T + 1,), torch.int32)
+        ops.neighbor_count(dets, img_off, self.g['neighbor_thresh'], degree)
+        ops.exclusive_scan(degree, row_ptr)
+        num_pairs = row_ptr[T:T + 1]
+        cap = self._ensure_capacity(num_pairs, T)
+        if not (self.fused_block and self.use_fused):
+            # the unfused pieces index pair rows through row_ptr, so they need
+            # P <= capacity BEFORE going on (not the hot path: one sync is fine)
+            p = int(num_pairs.item())
+            if p > cap:
+                cap = self.capacity = int(p * 1.25) + 256
+        pair_c = self._buf('pair_c', (cap,), torch.int32)
+        pair_n = self._buf('pair_n', (cap,), torch.int32)
+        pair_iou = self._buf('pair_iou', (cap,), torch.float32)
+        ops.neighbor_fill(dets, img_off, self.g['neighbor_thresh'], row_ptr, cap, pair_c, pair_n,
+                          pair_iou, None)
+        self._last_num_pairs, self._last_capacity = num_pairs, cap
+        return row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap
+
+    def _fc(self, x, scope, relu, residual=None, out=None, rows_dev=None):
+        return ops.fc_fwd(x, self.p[scope + '/weights'], self.p[scope + '/biases'], relu,
+                          residual=residual, out=out, rows_dev=rows_dev)
+
+    def pair_features(self, dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, cap):
+        """A4 + A5 -> pw_feats[cap, pw_width] (rows >= P undefined)."""
+        g = self.g
+        cls = classes if self.multiclass else None
+        mult = g['pw_feat_multiplyer']
+        if g['num_pwfeat_fc'] > 0 and self.fused_pw and self.use_fused:
+            s = 'gnet/pw_feats/fc%d/'
+            out = self._buf('pw', (cap, 32))
+            w = [self.p[(s % i) + k] for i in (1, 2, 3) for k in ('weights', 'biases')]
+            return ops.pwfeat_mlp_fwd(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
+                                      self.num_classes, mult, *w, out=out)
+        raw = self._buf('pw_raw', (cap, self.raw_width))
+        ops.pair_geometry(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
+                          self.num_classes, mult, raw)
+        x = raw
+        for i in range(1, g['num_pwfeat_fc'] + 1):
+            width = g['pwfeat_dim'] if i < g['num_pwfeat_fc'] else g['pwfeat_narrow_dim']
+            y = self._buf('pw_fc%d' % (i % 2), (cap, width))
+            x = self._fc(x, 'gnet/pw_feats/fc%d' % i, True, out=y, rows_dev=num_pairs)
+        return x
+
+    def block(self, b, infeats, row_ptr, pair_c, pair_n, num_pairs, cap, pw, out):
+        """A7: nms_net/network.py:344-409."""
+        g = self.g
+        T = infeats.shape[0]
+        s = 'gnet/block%d/' % b
+        red = self._fc(infeats, s + 'reduce_dim', True, out=self._buf('red', (T, g['reduced_dim'])))
+        nred = red
+        if g['neighbor_feats']:
+            nred = self._fc(infeats, s + 'reduce_dim_neighbor', True,
+                            out=self._buf('nred', (T, g['reduced_dim'])))
+        f = g['pairfeat_dim']
+        pooled = self._buf('pooled', (T, f))
+        if self.fused_block and self.use_fused:
+            pooled.zero_()
+            ops.block_pair_fwd(pw, red, nred, pair_c, pair_n, num_pairs, cap,
+                               self.p[s + 'pw_fc1/weights'], self.p[s + 'pw_fc1/biases'],
+                               self.p[s + 'pw_fc2/weights'], self.p[s + 'pw_fc2/biases'], pooled)
+        else:
+            x = ops.block_gather_concat(pw, red, nred, pair_c, pair_n, num_pairs, cap,
+                                        self._buf('pairx', (cap, pw.shape[1] + 2 * g['reduced_dim'])))
+            for i in range(1, g['num_block_pw_fc'] + 1):
+                x = self._fc(x, s + 'pw_fc%d' % i, True, out=self._buf('pairh%d' % (i % 2), (cap, f)),
+                             rows_dev=num_pairs)
+            if g['num_block_pw_fc'] == 0:
+                f = x.shape[1]
+                pooled = self._buf('pooled', (T, f))
+            ops.segment_max(x, row_ptr, T, pooled)
+        x = pooled
+        for i in range(1, g['num_block_fc']):
+            x = self._fc(x, s + 'fc%d' % i, True, out=self._buf('deth%d' % (i % 2), (T, g['pairfeat_dim'])))
+        # last FC has no activation; shortcut: relu(infeats + feats) (:399-408)
+        return self._fc(x, s + 'fc%d' % g['num_block_fc'], True, residual=infeats, out=out)
+
+    def predict(self, feats):
+        """A8: two LINEAR layers then the logit (network.py:257-273)."""
+        g = self.g
+        T = feats.shape[0]
+        x = feats
+        for i in range(1, g['num_predict_fc']):
+            x = self._fc(x, 'gnet/predict/fc%d/fully_connected' % i, False,
+                         out=self._buf('pred%d' % (i % 2), (T, g['predict_fc_dim'])))
+        out = self._fc(x, 'gnet/predict/logits/fully_connected', False,
+                       out=self._buf('logits', (T, 1)))
+        return out.view(-1)
+
+    def forward(self, dets, scores, classes, img_off):
+        """dets[T,4] f32, scores[T] f32, classes[T] i32, img_off[B+1] i32 (all
+        CUDA) -> dict(prediction[T], row_ptr, num_pairs, pair_c, pair_n,
+        pair_iou, pw_feats, feats, [block_feats]).  Returned tensors are views
+        of the engine's workspace: valid until the next forward."""
+        T = dets.shape[0]
+        g = self.g
+        row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = self.neighbors(dets, img_off)
+        pw = self.pair_features(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, cap)
+        d = g['shortcut_dim']
+        feats = self._buf('feats0', (T, d))
+        feats.zero_()  # network.py:241-246
+        block_feats = [feats.clone()] if self.keep_block_feats else None
+        for b in range(1, g['num_blocks'] + 1):
+            out = self._buf('feats%d' % (b % 2), (T, d))
+            feats = self.block(b, feats, row_ptr, pair_c, pair_n, num_pairs, cap, pw, out)
+            if self.keep_block_feats:
+                block_feats.append(feats.clone())
+        prediction = self.predict(feats)
+        res = dict(prediction=prediction, row_ptr=row_ptr, num_pairs=num_pairs, pair_c=pair_c,
+                   pair_n=pair_n, pair_iou=pair_iou, pw_feats=pw, feats=feats, capacity=cap)
+        if self.keep_block_feats:
+            res['block_feats'] = block_feats
+        return res
+
+    # -------------------------------------------------------------- matching, loss
+    def det_anno_iou(self, dets, classes, img_off_host, gt_boxes, gt_crowd, gt_classes,
+                     gt_off_host):
+        """Per-image dense [n_i, g_i] det/GT overlap blocks (network.py:174-187),
+        concatenated; returns (iou_flat, iou_off_host[int64 B+1])."""
+        B = len(img_off_host) - 1
+        off = np.zeros(B + 1, dtype=np.int64)
+        for i in range(B):
+            n = img_off_host[i + 1] - img_off_host[i]
+            gcount = gt_off_host[i + 1] - gt_off_host[i]
+            off[i + 1] = off[i] + int(n) * int(gcount)
+        flat = self._buf('det_anno_iou', (int(off[B]),))
+        for i in range(B):
+            d0, d1 = int(img_off_host[i]), int(img_off_host[i + 1])
+            g0, g1 = int(gt_off_host[i]), int(gt_off_host[i + 1])
+            if d1 == d0 or g1 == g0:
+                continue
+            out = flat[off[i]:off[i + 1]].view(1, d1 - d0, g1 - g0)
+            ops.iou_dense(dets[d0:d1].unsqueeze(0), gt_boxes[g0:g1].unsqueeze(0),
+                          crowd=gt_crowd[g0:g1].unsqueeze(0),
+                          a_cls=classes[d0:d1].unsqueeze(0) if self.multiclass else None,
+                          b_cls=gt_classes[g0:g1].unsqueeze(0) if self.multiclass else None,
+                          out=out)
+        return flat, off
+
+    def matching_and_loss(self, prediction, dets, classes, img_off, img_off_host, gt_boxes,
+                          gt_crowd, gt_classes, gt_off_host, class_weights, want_grad=False):
+        """A9 + A10 (network.py:275-314) for the batch."""
+        dev = self.device
+        iou_flat, iou_off_host = self.det_anno_iou(dets, classes, img_off_host, gt_boxes, gt_crowd,
+                                                   gt_classes, gt_off_host)
+        iou_off = torch.from_numpy(iou_off_host).to(dev)
+        gt_off = torch.from_numpy(np.asarray(gt_off_host, dtype=np.int32)).to(dev)
+        max_gt = int(np.max(np.diff(gt_off_host))) if len(gt_off_host) > 1 else 0
+        labels, weights, assignment = ops.detection_matching_batched(
+            iou_flat, iou_off, prediction, gt_crowd, img_off, gt_off, max_gt)
+        loss_out, dlogit = ops.loss_fwd(prediction, labels, weights, assignment, gt_crowd,
+                                        gt_classes, img_off, gt_off, class_weights,
+                                        self.normalize_loss, self.loss_multiplyer,
+                                        want_grad=want_grad)
+        return dict(labels=labels, weights=weights, det_gt_matching=assignment,
+                    loss_out=loss_out, dlogit=dlogit, det_anno_iou=iou_flat,
+                    det_anno_iou_off=iou_off_host)

@@ -1,0 +1,163 @@
+"""Global configuration `cfg` for the Gnet hot path.
+
+Mirrors the keys, defaults and merge rules of the reference's
+`nms_net/config.py:10-121` (defaults `:10-79`, strict merge `:82-112`,
+`cfg_from_file` `:115-121`) so the shipped `conf.yaml` files load unchanged.
+easydict is not installed in this image, so `AttrDict` is a small attribute
+dictionary with the same behaviour for the operations the reference uses.
+"""
+import os.path
+
+import numpy as np
+import yaml
+
+
+class AttrDict(dict):
+    """dict whose keys are also attributes; nested dicts are converted."""
+
+    def __init__(self, d=None, **kwargs):
+        super().__init__()
+        src = dict(d or {})
+        src.update(kwargs)
+        for k, v in src.items():
+            self[k] = v
+
+    @staticmethod
+    def _wrap(v):
+        if isinstance(v, dict) and not isinstance(v, AttrDict):
+            return AttrDict(v)
+        if isinstance(v, (list, tuple)):
+            return type(v)(AttrDict._wrap(x) for x in v)
+        return v
+
+    def __setitem__(self, k, v):
+        super().__setitem__(k, AttrDict._wrap(v))
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __delattr__(self, k):
+        del self[k]
+
+
+_HERE = os.path.dirname(os.path.realpath(__file__))
+
+_DEFAULTS = {
+    'random_seed': 42,
+    'prefetch_q_size': 20,
+    'log_dir': './log',
+    'ROOT_DIR': os.path.normpath(os.path.join(_HERE, '..', '..')),
+    'resnet_type': '101',
+    'imfeat_crop_width': 7,
+    'imfeat_crop_height': 7,
+    'pixel_mean': [123.68, 116.779, 103.939],
+    # shorter image side is resized to this, longer side capped at the max
+    'image_target_size': 600,
+    'image_max_size': 1000,
+    'train': {
+        'optimizer': 'adam',
+        'model_init': None,
+        'resume': None,
+        'momentum': 0.9,
+        'weight_decay': 0.0005,
+        'num_iter': 100000,
+        'save_iter': 10000,
+        'lr_multi_step': [(10000, 0.001), (80000, 0.0001), (200000, 0.0000001)],
+        'gradient_clipping': -1.0,
+        'detector': 'FRCN_person',
+        'flip': True,
+        'only_class': '',
+        'imdb': 'coco_2014_train',
+        'pos_weight': 0.1,
+        'pretrained_model': '',
+        'display_iter': 20,
+        'det_min_size': 4,
+        'val_imdb': '',
+        'val_iter': 10000,
+        'max_num_detections': -1,
+        'normalize_loss': False,
+        'histograms': False,
+        'loss_multiplyer': 1.0,
+    },
+    'test': {
+        'imdb': 'coco_2014_minival',
+    },
+    'gnet': {
+        'neighbor_thresh': 0.2,
+        'shortcut_dim': 128,
+        'num_blocks': 16,
+        'reduced_dim': 32,
+        'pairfeat_dim': 2 * 32,
+        'gt_match_thresh': 0.5,      # defined but unused, as in the reference
+        'num_block_pw_fc': 2,
+        'num_block_fc': 2,
+        'num_predict_fc': 3,
+        'block_dim': 2 * 32,         # defined but unused, as in the reference
+        'predict_fc_dim': 128,
+        'imfeats': False,
+        'load_imfeats': False,
+        'imfeat_dim': -1,
+        'neighbor_feats': False,
+        'num_pwfeat_fc': 0,
+        'pwfeat_dim': 256,
+        'pwfeat_narrow_dim': 64,
+        'weight_init': 'xavier',
+        'bias_const_init': 0.0,
+        'freeze_n_imfeat_layers': 3,
+        'pw_feat_multiplyer': 1.0,
+    },
+}
+
+cfg = AttrDict(_DEFAULTS)
+
+
+def reset_cfg():
+    """Restore every key to its default (tests switch between experiments)."""
+    for k in list(cfg.keys()):
+        del cfg[k]
+    for k, v in AttrDict(_DEFAULTS).items():
+        cfg[k] = v
+
+
+def _merge_a_into_b(a, b):
+    """Clobber options in b with those in a. Unknown key -> KeyError, type
+    mismatch -> ValueError (reference `config.py:82-112`)."""
+    if type(a) is not AttrDict:
+        return
+    for k, v in a.items():
+        if k not in b:
+            raise KeyError('{} is not a valid config key'.format(k))
+        old_type = type(b[k])
+        if old_type is not type(v):
+            if isinstance(b[k], np.ndarray):
+                v = np.array(v, dtype=b[k].dtype)
+            else:
+                raise ValueError(('Type mismatch ({} vs. {}) '
+                                  'for config key: {}').format(type(b[k]),
+                                                               type(v), k))
+        if type(v) is AttrDict:
+            try:
+                _merge_a_into_b(a[k], b[k])
+            except Exception:
+                print('Error under config key: {}'.format(k))
+                raise
+        else:
+            b[k] = v
+
+
+def cfg_from_file(filename):
+    """Load a YAML config and merge it into the defaults."""
+    with open(filename, 'r') as f:
+        yaml_cfg = AttrDict(yaml.safe_load(f))
+    _merge_a_into_b(yaml_cfg, cfg)
+
+
+def cfg_from_dict(d):
+    """Merge a plain nested dict (same rules as `cfg_from_file`)."""
+    _merge_a_into_b(AttrDict(d), cfg)

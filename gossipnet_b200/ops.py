@@ -1,0 +1,204 @@
+"""Thin torch-tensor front-ends for the C ABI (include/gossipnet_b200.h).
+
+torch is plumbing here: it owns device memory and the stream; every operation
+below is one call into libgossipnet_b200.so on torch's current stream.  Inputs
+must be CUDA tensors; there is no CPU path.
+"""
+import torch
+
+from gossipnet_b200 import _lib
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t, dtype, name, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError('%s: tensor required' % name)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError('%s must be a CUDA tensor (the hot path has no CPU fallback)' % name)
+    if t.dtype != dtype:
+        raise ValueError('%s must have dtype %s, got %s' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError('%s must be contiguous' % name)
+    return t.data_ptr()
+
+
+# --------------------------------------------------------------------------- IoU
+def iou_dense(a, b, crowd=None, a_cls=None, b_cls=None, out=None):
+    """a[B,n,4] or [n,4]; b[B,m,4] or [m,4] -> out[B,n,m] / [n,m]."""
+    squeeze = a.dim() == 2
+    if squeeze:
+        a, b = a.unsqueeze(0), b.unsqueeze(0)
+        crowd = None if crowd is None else crowd.unsqueeze(0)
+        a_cls = None if a_cls is None else a_cls.unsqueeze(0)
+        b_cls = None if b_cls is None else b_cls.unsqueeze(0)
+    if a.dim() != 3 or b.dim() != 3 or a.shape[-1] != 4 or b.shape[-1] != 4 \
+            or a.shape[0] != b.shape[0]:
+        raise ValueError('iou_dense expects a[B,n,4], b[B,m,4]')
+    B, n, m = a.shape[0], a.shape[1], b.shape[1]
+    if crowd is not None:
+        if crowd.dtype == torch.bool:
+            crowd = crowd.to(torch.uint8)
+        if tuple(crowd.shape) != (B, m):
+            raise ValueError('iou_dense: crowd must be [B,m]')
+    if out is None:
+        out = torch.empty((B, n, m), dtype=torch.float32, device=a.device)
+    _lib.call('gn_iou_dense', _chk(a, torch.float32, 'a'), _chk(b, torch.float32, 'b'),
+              _chk(crowd, torch.uint8, 'crowd', True), _chk(a_cls, torch.int32, 'a_cls', True),
+              _chk(b_cls, torch.int32, 'b_cls', True), B, n, m,
+              _chk(out, torch.float32, 'out'), _stream())
+    return out[0] if squeeze else out
+
+
+# --------------------------------------------------------------------- neighbors
+def neighbor_count(dets, img_off, thresh, degree=None):
+    n = dets.shape[0]
+    if degree is None:
+        degree = torch.empty(n, dtype=torch.int32, device=dets.device)
+    _lib.call('gn_neighbor_count', _chk(dets, torch.float32, 'dets'),
+              _chk(img_off, torch.int32, 'img_off'), img_off.numel() - 1, n, float(thresh),
+              _chk(degree, torch.int32, 'degree'), _stream())
+    return degree
+
+
+def exclusive_scan(x, out=None):
+    n = x.numel()
+    if out is None:
+        out = torch.empty(n + 1, dtype=torch.int32, device=x.device)
+    _lib.call('gn_exclusive_scan', _chk(x, torch.int32, 'in'), n,
+              _chk(out, torch.int32, 'out'), _stream())
+    return out
+
+
+def neighbor_fill(dets, img_off, thresh, row_ptr, capacity, pair_c, pair_n, pair_iou, overflow):
+    _lib.call('gn_neighbor_fill', _chk(dets, torch.float32, 'dets'),
+              _chk(img_off, torch.int32, 'img_off'), img_off.numel() - 1, dets.shape[0],
+              float(thresh), _chk(row_ptr, torch.int32, 'row_ptr'), int(capacity),
+              _chk(pair_c, torch.int32, 'pair_c'), _chk(pair_n, torch.int32, 'pair_n'),
+              _chk(pair_iou, torch.float32, 'pair_iou'),
+              _chk(overflow, torch.int32, 'overflow', True), _stream())
+
+
+# ------------------------------------------------------------------ pair features
+def pair_geometry(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
+                  num_classes, multiplier, out=None):
+    width = 9 if num_classes <= 1 else 2 * num_classes + 7
+    if out is None:
+        out = torch.empty((capacity, width), dtype=torch.float32, device=dets.device)
+    _lib.call('gn_pair_geometry', _chk(dets, torch.float32, 'dets'),
+              _chk(scores, torch.float32, 'scores'), _chk(classes, torch.int32, 'classes', True),
+              _chk(pair_c, torch.int32, 'pair_c'), _chk(pair_n, torch.int32, 'pair_n'),
+              _chk(pair_iou, torch.float32, 'pair_iou'), _chk(num_pairs, torch.int32, 'num_pairs'),
+              int(capacity), int(num_classes), float(multiplier),
+              _chk(out, torch.float32, 'out'), _stream())
+    return out
+
+
+def pwfeat_mlp_fwd(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
+                   num_classes, multiplier, w1, b1, w2, b2, w3, b3, out=None):
+    hidden, out_dim = w2.shape[1], w3.shape[1]
+    if out is None:
+        out = torch.empty((capacity, out_dim), dtype=torch.float32, device=dets.device)
+    f32 = torch.float32
+    _lib.call('gn_pwfeat_mlp_fwd', _chk(dets, f32, 'dets'), _chk(scores, f32, 'scores'),
+              _chk(classes, torch.int32, 'classes', True), _chk(pair_c, torch.int32, 'pair_c'),
+              _chk(pair_n, torch.int32, 'pair_n'), _chk(pair_iou, f32, 'pair_iou'),
+              _chk(num_pairs, torch.int32, 'num_pairs'), int(capacity), int(num_classes),
+              float(multiplier), _chk(w1, f32, 'w1'), _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2'),
+              _chk(b2, f32, 'b2'), _chk(w3, f32, 'w3'), _chk(b3, f32, 'b3'), int(hidden),
+              int(out_dim), _chk(out, f32, 'pw_out'), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------- FC
+def fc_fwd(x, w, b, relu, residual=None, out=None, rows_dev=None):
+    """y = act(residual + x @ w + b); x[rows,k] (row stride may exceed k)."""
+    if x.dim() != 2 or w.dim() != 2 or x.shape[1] != w.shape[0] or b.numel() != w.shape[1]:
+        raise ValueError('fc_fwd: shape mismatch x%s w%s b%s' % (tuple(x.shape), tuple(w.shape),
+                                                                 tuple(b.shape)))
+    rows, k = x.shape
+    n = w.shape[1]
+    if out is None:
+        out = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+    f32 = torch.float32
+    _lib.call('gn_fc_fwd', _chk(x, f32, 'x'), x.stride(0), _chk(w, f32, 'w'), _chk(b, f32, 'b'),
+              _chk(residual, f32, 'residual', True),
+              0 if residual is None else residual.stride(0), 1 if relu else 0,
+              _chk(out, f32, 'y'), out.stride(0), rows,
+              _chk(rows_dev, torch.int32, 'rows_dev', True), k, n, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------ blocks
+def block_gather_concat(pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, out=None):
+    w, r = pw.shape[1], feats.shape[1]
+    if out is None:
+        out = torch.empty((capacity, w + 2 * r), dtype=torch.float32, device=pw.device)
+    f32 = torch.float32
+    _lib.call('gn_block_gather_concat', _chk(pw, f32, 'pw'), w, _chk(feats, f32, 'feats'),
+              _chk(nfeats, f32, 'nfeats'), r, _chk(pair_c, torch.int32, 'pair_c'),
+              _chk(pair_n, torch.int32, 'pair_n'), _chk(num_pairs, torch.int32, 'num_pairs'),
+              int(capacity), _chk(out, f32, 'x'), _stream())
+    return out
+
+
+def segment_max(x, row_ptr, num_dets, out=None):
+    f = x.shape[1]
+    if out is None:
+        out = torch.empty((num_dets, f), dtype=torch.float32, device=x.device)
+    _lib.call('gn_segment_max', _chk(x, torch.float32, 'x'), f,
+              _chk(row_ptr, torch.int32, 'row_ptr'), int(num_dets),
+              _chk(out, torch.float32, 'out'), _stream())
+    return out
+
+
+def block_pair_fwd(pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2,
+                   pooled):
+    """pooled[num_dets,f] must be zero-filled; it is max-accumulated in place."""
+    f32 = torch.float32
+    _lib.call('gn_block_pair_fwd', _chk(pw, f32, 'pw'), pw.shape[1], _chk(feats, f32, 'feats'),
+              _chk(nfeats, f32, 'nfeats'), feats.shape[1], _chk(pair_c, torch.int32, 'pair_c'),
+              _chk(pair_n, torch.int32, 'pair_n'), _chk(num_pairs, torch.int32, 'num_pairs'),
+              int(capacity), _chk(w1, f32, 'w1'), _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2'),
+              _chk(b2, f32, 'b2'), w2.shape[1], _chk(pooled, f32, 'pooled'), _stream())
+    return pooled
+
+
+# ---------------------------------------------------------------- matching, loss
+def detection_matching_batched(iou, iou_off, score, ignore, img_off, gt_off, max_gt):
+    n = score.numel()
+    dev = score.device
+    labels = torch.empty(n, dtype=torch.float32, device=dev)
+    weights = torch.empty(n, dtype=torch.float32, device=dev)
+    assignment = torch.empty(n, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    _lib.call('gn_detection_matching', _chk(iou, torch.float32, 'iou'),
+              _chk(iou_off, torch.int64, 'iou_off'), _chk(score, torch.float32, 'score'),
+              _chk(ignore, torch.uint8, 'ignore'), _chk(img_off, torch.int32, 'img_off'),
+              _chk(gt_off, torch.int32, 'gt_off'), img_off.numel() - 1, n, int(max_gt),
+              _chk(labels, torch.float32, 'labels'), _chk(weights, torch.float32, 'weights'),
+              _chk(assignment, torch.int32, 'assignment'), _chk(ws, torch.int32, 'workspace'),
+              _stream())
+    return labels, weights, assignment
+
+
+def loss_fwd(prediction, labels, weights, assignment, gt_crowd, gt_classes, img_off, gt_off,
+             class_weights, normalize, loss_multiplier, want_grad=False):
+    """Updates `weights` in place; returns (loss_out[num_images,3], dlogit|None)."""
+    num_images = img_off.numel() - 1
+    dev = prediction.device
+    loss_out = torch.empty((num_images, 3), dtype=torch.float32, device=dev)
+    dlogit = torch.empty_like(prediction) if want_grad else None
+    f32 = torch.float32
+    _lib.call('gn_loss_fwd', _chk(prediction, f32, 'prediction'), _chk(labels, f32, 'labels'),
+              _chk(weights, f32, 'weights'), _chk(assignment, torch.int32, 'assignment'),
+              _chk(gt_crowd, torch.uint8, 'gt_crowd'), _chk(gt_classes, torch.int32, 'gt_classes'),
+              _chk(img_off, torch.int32, 'img_off'), _chk(gt_off, torch.int32, 'gt_off'),
+              num_images, prediction.numel(), _chk(class_weights, f32, 'class_weights'),
+              1 if normalize else 0, float(loss_multiplier), _chk(loss_out, f32, 'loss_out'),
+              _chk(dlogit, f32, 'dlogit', True), _stream())
+    return loss_out, dlogit

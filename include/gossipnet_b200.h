@@ -1,0 +1,182 @@
+/*
+ * gossipnet_b200 C ABI: the drop-in boundary of the B200-native GossipNet hot path.
+ *
+ * One shared library (gossipnet_b200/csrc/libgossipnet_b200.so), plain C linkage,
+ * plain pointers and sizes, no torch / TensorFlow types.  The reference has no
+ * C ABI of its own: its boundary is a TF-0.12 Python graph plus two
+ * tf.load_op_library() objects.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference repository root).
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless the
+ *     name ends in _host; the caller owns and pre-allocates every buffer
+ *     (outputs and workspace); nothing is allocated or freed inside;
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and never
+ *     synchronises; data-dependent sizes (the pair count P) stay on the device
+ *     in an int32 counter the later calls read, so a whole forward pass is
+ *     CUDA-graph capturable;
+ *   - return value 0 = launched; non-zero = rejected before launch (argument
+ *     validation, mirrors the reference ops' InvalidArgument checks) or a CUDA
+ *     launch error; gn_last_error() returns a thread-local message;
+ *   - re-entrant and thread-safe: no global mutable state besides the
+ *     thread-local error string (the reference's DetectionMatchingOp keeps
+ *     scratch vectors as kernel members, det_matching.cc:39-40, and is not);
+ *   - detections of a batch of images are concatenated: dets[num_dets,4] with
+ *     img_off[num_images+1] giving each image's [begin,end) rows.  All pair /
+ *     neighbor indices are GLOBAL row numbers into that concatenation, so the
+ *     block kernels never need to know about image boundaries.
+ */
+#ifndef GOSSIPNET_B200_H_
+#define GOSSIPNET_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* gn_stream_t; /* cudaStream_t */
+
+#define GN_OK 0
+#define GN_ERR_INVALID_ARGUMENT 1
+#define GN_ERR_CUDA 2
+#define GN_ERR_UNSUPPORTED 3
+
+const char* gn_last_error(void);
+int gn_abi_version(void);
+/* Number of SMs of the current device (grid sizing for persistent kernels). */
+int gn_sm_count(void);
+
+/* ---- A1 + A2: box IoU ------------------------------------------------------
+ * Replaces Gnet._xyxy_to_boxdata / _intersection / _iou
+ * (nms_net/network.py:462-472, :490-511, :474-488) and the multi-class
+ * det<->GT mask (:177-187).
+ *   a[batch,n,4], b[batch,m,4]  xyxy float32
+ *   crowd[batch,m] (uint8, nullable): column j uses inter / area(a_i)
+ *   a_cls[batch,n], b_cls[batch,m] (int32, both nullable): out=0 where classes differ
+ *   out[batch,n,m] float32; bit-exact with the float32 reference arithmetic
+ *   (no FMA contraction, IEEE division). */
+int gn_iou_dense(const float* a, const float* b, const uint8_t* crowd,
+                 const int32_t* a_cls, const int32_t* b_cls,
+                 int batch, int n, int m, float* out, gn_stream_t stream);
+
+/* ---- A3: neighbor build ----------------------------------------------------
+ * Replaces tf.where(det_det_iou >= cfg.gnet.neighbor_thresh)
+ * (nms_net/network.py:192-195).  IoU is recomputed from the boxes (same
+ * arithmetic as gn_iou_dense), the dense N x N matrix is never materialised.
+ * Pairs come out in the reference's row-major order: c ascending, then n
+ * ascending; self pairs included.
+ *
+ *   gn_neighbor_count : degree[num_dets]  (pairs per row)
+ *   gn_exclusive_scan : row_ptr[num_dets+1] from degree (row_ptr[num_dets] = P)
+ *   gn_neighbor_fill  : pair_c[P], pair_n[P] (global rows, int32), pair_iou[P]
+ *                       for pairs that fit `capacity`; *overflow is set to 1
+ *                       (else left untouched) when P > capacity.
+ * num_pairs for later calls is row_ptr + num_dets (device int32). */
+int gn_neighbor_count(const float* dets, const int32_t* img_off, int num_images,
+                      int num_dets, float thresh, int32_t* degree,
+                      gn_stream_t stream);
+int gn_exclusive_scan(const int32_t* in, int n, int32_t* out, gn_stream_t stream);
+int gn_neighbor_fill(const float* dets, const int32_t* img_off, int num_images,
+                     int num_dets, float thresh, const int32_t* row_ptr,
+                     int capacity, int32_t* pair_c, int32_t* pair_n,
+                     float* pair_iou, int32_t* overflow, gn_stream_t stream);
+
+/* ---- A4: hand-crafted pair features ------------------------------------------
+ * Replaces Gnet._geometry_feats (nms_net/network.py:411-454) times
+ * cfg.gnet.pw_feat_multiplyer (:199-200).  out[capacity, width] with
+ * width = 9 (num_classes<=1) or 2*num_classes+7; columns
+ * [c_score | n_score | iou, x_dist, y_dist, l2_dist, w_diff, h_diff, aspect_diff].
+ * Rows >= *num_pairs are not written. */
+int gn_pair_geometry(const float* dets, const float* scores, const int32_t* classes,
+                     const int32_t* pair_c, const int32_t* pair_n,
+                     const float* pair_iou, const int32_t* num_pairs, int capacity,
+                     int num_classes, float multiplier, float* out,
+                     gn_stream_t stream);
+
+/* ---- A5: pair-feature MLP, fused with A4 ------------------------------------
+ * Replaces Gnet._pw_feats_fc (nms_net/network.py:324-342) applied to the
+ * geometry features for the shipped shape num_pwfeat_fc=3:
+ * width -> hidden -> hidden -> out_dim, ReLU after every layer.
+ * w1[width,hidden] b1[hidden] w2[hidden,hidden] b2 w3[hidden,out_dim] b3;
+ * pw_out[capacity,out_dim].  hidden must be 256 and out_dim 32 (the fused
+ * kernel's shape); other shapes go through gn_pair_geometry + gn_fc_fwd. */
+int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const int32_t* classes,
+                      const int32_t* pair_c, const int32_t* pair_n,
+                      const float* pair_iou, const int32_t* num_pairs, int capacity,
+                      int num_classes, float multiplier,
+                      const float* w1, const float* b1, const float* w2,
+                      const float* b2, const float* w3, const float* b3,
+                      int hidden, int out_dim, float* pw_out, gn_stream_t stream);
+
+/* ---- generic fully connected layer -----------------------------------------
+ * tf.contrib.layers.fully_connected as the reference uses it everywhere:
+ * y = act(x @ W[k,n] + b) (+ optional residual before the activation:
+ * y = act(res + x @ W + b), the block shortcut network.py:407-408).
+ * rows_dev (nullable) overrides `rows` with a device-side count (<= rows). */
+int gn_fc_fwd(const float* x, int ldx, const float* w, const float* b,
+              const float* residual, int ld_res, int relu, float* y, int ldy,
+              int rows, const int32_t* rows_dev, int k, int n, gn_stream_t stream);
+
+/* ---- A7: one Gnet block -----------------------------------------------------
+ * Unfused pieces (reference formulation, nms_net/network.py:367-388):
+ *   gn_block_gather_concat: x[P, w + 2r] = [pw | feats[pair_c] | nfeats[pair_n]],
+ *                           n-part zeroed on self pairs (:368-376)
+ *   gn_segment_max:         out[num_dets, f] = max over each row's pairs
+ *                           (tf.segment_max, :387-388)
+ * Fused hot path:
+ *   gn_block_pair_fwd: gather + concat + pw_fc1 + pw_fc2 (+ReLU) + segment max
+ *                      in one kernel; pooled[num_dets, f] must be zero-filled
+ *                      by the caller (post-ReLU values are >= 0 and every row
+ *                      has its self pair, so an integer atomicMax is exact). */
+int gn_block_gather_concat(const float* pw, int w, const float* feats,
+                           const float* nfeats, int r, const int32_t* pair_c,
+                           const int32_t* pair_n, const int32_t* num_pairs,
+                           int capacity, float* x, gn_stream_t stream);
+int gn_segment_max(const float* x, int f, const int32_t* row_ptr, int num_dets,
+                   float* out, gn_stream_t stream);
+int gn_block_pair_fwd(const float* pw, int w, const float* feats,
+                      const float* nfeats, int r, const int32_t* pair_c,
+                      const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                      const float* w1, const float* b1, const float* w2,
+                      const float* b2, int f, float* pooled, gn_stream_t stream);
+
+/* ---- A9: DetectionMatching ---------------------------------------------------
+ * Replaces the DetectionMatching TF op (nms_net/matching_module/det_matching.cc:
+ * 16-33 op def, :72-160 Compute; python name matching_module.detection_matching,
+ * __init__.py:13).  Batched over images: iou rows of image i are
+ * [img_off[i], img_off[i+1]) and its GT columns [gt_off[i], gt_off[i+1]);
+ * iou is stored per image as a dense [n_i, g_i] block at iou_off[i] (int64
+ * element offsets).  Outputs are [num_dets].  Visiting orders reproduce the
+ * reference's std::sort (+reverse) permutations exactly, including the order
+ * among tied scores / equal ignore flags (libstdc++ introsort decision
+ * sequence, gn_introsort.cuh), so results are bit-identical to a g++ build of
+ * det_matching.cc for any non-NaN input.
+ * max_gt: largest g_i of the batch (host-known; sizes the shared-memory GT
+ * tables).  workspace: int32[num_dets] (visiting order). */
+int gn_detection_matching(const float* iou, const int64_t* iou_off,
+                          const float* score, const uint8_t* ignore,
+                          const int32_t* img_off, const int32_t* gt_off,
+                          int num_images, int num_dets, int max_gt,
+                          float* labels, float* weights, int32_t* assignment,
+                          int32_t* workspace, gn_stream_t stream);
+
+/* ---- A10: loss ---------------------------------------------------------------
+ * Replaces nms_net/network.py:281-313: class weighting of the matching
+ * weights, sigmoid cross entropy, sum and mean.  gt_crowd / gt_classes are
+ * concatenated like gt_off says; class_weights[num_classes+1].
+ * weights_io is updated in place (weights * class_weights[det_class]);
+ * loss_out[3*num_images] = per image (unnormed sum, normed mean, loss);
+ * dlogit (nullable) [num_dets] = d loss / d prediction. */
+int gn_loss_fwd(const float* prediction, const float* labels, float* weights_io,
+                const int32_t* assignment, const uint8_t* gt_crowd,
+                const int32_t* gt_classes, const int32_t* img_off,
+                const int32_t* gt_off, int num_images, int num_dets,
+                const float* class_weights, int normalize, float loss_multiplier,
+                float* loss_out, float* dlogit, gn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOSSIPNET_B200_H_ */
