@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py: detections/s of the Gnet forward (N=1000 detections/image, 16 blocks,
+coco_person hyper-parameters = BASELINE.json configs[1]) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one forward of the hot path (neighbor build -> pair-feature MLP ->
+16 blocks -> predict head) over a batch of `--images` synthetic images per GPU.
+Images shard across ranks with no data-path collective (weak scaling).
+
+Printed JSON (one line, rank 0): `value` = whole-job detections/s with inputs
+resident in HBM (CUDA-graph replay, CUDA events, L2 flushed between steps, max
+over ranks); `e2e` = the same metric through the host-buffer session
+(gossipnet_b200.session.InferenceSession.run: pinned H2D of the step's inputs
+and D2H of its logits inside the timed region); `roofline` = the dominant
+kernel (block pair stage) timed live with CUDA events; `roofline_iou` = the
+dense N x N IoU kernel (BASELINE metric "IoU HBM GB/s"); `cpu_baseline` = the
+numpy restatement of the reference (oracle/, TensorFlow is not installable)
+timed on this box's host cores on a bounded sample.
+
+`--impl reference` times that CPU restatement alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'detections/sec Gnet fwd (N=1000, 16 blocks)'
+UNIT = 'detections/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--images', type=int, default=64, help='images per GPU per step')
+    ap.add_argument('--n-dets', type=int, default=1000)
+    ap.add_argument('--blocks', type=int, default=16)
+    ap.add_argument('--cpu-seconds', type=float, default=12.0,
+                    help='budget of the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true')
+    return ap.parse_args()
+
+
+def setup_cfg(blocks):
+    from gossipnet_b200.nms_net.config import cfg, cfg_from_file, reset_cfg
+    reset_cfg()
+    cfg_from_file(os.path.join(ROOT, 'experiments', 'coco_person', 'conf.yaml'))
+    cfg.gnet.num_blocks = blocks
+    return cfg
+
+
+def make_inputs(n_images, n_dets, first_index):
+    from gossipnet_b200 import synthetic
+    imgs = [synthetic.make_image(n_dets, 1, seed=42, image_index=first_index + i)
+            for i in range(n_images)]
+    dets = np.concatenate([im['dets'] for im in imgs]).astype(np.float32)
+    scores = np.concatenate([im['det_scores'] for im in imgs]).astype(np.float32)
+    classes = np.concatenate([im['det_classes'] for im in imgs]).astype(np.int32)
+    img_off = (np.arange(n_images + 1) * n_dets).astype(np.int32)
+    return imgs, dets, scores, classes, img_off
+
+
+# ------------------------------------------------------------------ CPU baseline
+def cpu_forward_rate(cfg, n_dets, seconds, max_images=64, first_index=0):
+    """Reference formulation on the host cores, one image per call like
+    test.py:63-71 (numpy float32 restatement, BLAS threads = all cores)."""
+    from gossipnet_b200 import params as P
+    from gossipnet_b200 import synthetic
+    from oracle import gnet_oracle
+    layout, total = P.param_layout(1, cfg)
+    pv = P.views(layout, P.init_flat(layout, total, cfg, seed=1))
+    keys = ('dets', 'det_scores', 'det_classes')
+    img = synthetic.make_image(n_dets, 1, image_index=first_index)
+    gnet_oracle.gnet_forward({k: img[k] for k in keys}, pv, cfg, 1, keep_intermediates=False)
+    done, t0 = 0, time.perf_counter()
+    while done < max_images:
+        img = synthetic.make_image(n_dets, 1, image_index=first_index + done)
+        gnet_oracle.gnet_forward({k: img[k] for k in keys}, pv, cfg, 1, keep_intermediates=False)
+        done += 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    return done * n_dets / dt, done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cfg = setup_cfg(args.blocks)
+    cores = os.cpu_count()
+    per_step = 2  # images per step: a bounded sample of the workload
+    for _ in range(args.warmup):
+        cpu_forward_rate(cfg, args.n_dets, 1e9, max_images=1)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_forward_rate(cfg, args.n_dets, 1e9, max_images=per_step, first_index=s * per_step)
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step * args.n_dets / dt
+    sample = '%d images x N=%d per step, one image per call' % (per_step, args.n_dets)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'coco_person N=%d dets/image, %d blocks, d=128, fp32' % (
+            args.n_dets, args.blocks), 'images_per_step': per_step},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': sample + '; numpy float32 restatement of the reference '
+                         '(oracle/gnet_oracle.py; TensorFlow 0.12 is not installable here)'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ------------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                 '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[2:6]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(mx)),
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------- B200
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from gossipnet_b200 import _lib, ops
+    from gossipnet_b200.nms_net.network import Gnet
+    from gossipnet_b200.session import InferenceSession
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    cfg = setup_cfg(args.blocks)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    bf16_peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
+    peak_src = 'measured' if peaks else 'fallback'
+
+    B, N = args.images, args.n_dets
+    imgs, dets, scores, classes, img_off = make_inputs(B, N, first_index=rank * B)
+    net = Gnet(1)
+    eng = net.engine
+    sess = InferenceSession(net, use_graph=not args.no_graph)
+    T = dets.shape[0]
+
+    # ---- e2e warm-up doubles as graph capture ------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        pred = sess.run(dets, scores, classes, img_off)
+    P = int(sess.h_np[0])
+    launches = sess.launches_per_forward
+    stream = sess.stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def replay():
+        if sess._graph:
+            sess._graph.replay()
+        else:
+            sess._forward()
+
+    # ---- value: inputs resident, device time, L2 flushed between steps ----------
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            replay()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        with torch.cuda.stream(stream):
+            for s in range(args.steps):
+                flush.zero_()
+                ev[s][0].record(stream)
+                replay()
+                ev[s][1].record(stream)
+        barrier()
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        # ---- e2e: host buffers in, host logits out ------------------------------
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            pred = sess.run(dets, scores, classes, img_off)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+    clk = clocks.summary()
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    total_dets = world * B * N * args.steps
+    value = total_dets / (dev_ms * 1e-3)
+    e2e_value = total_dets / (e2e_ms * 1e-3)
+
+    # ---- roofline: the dominant kernel, timed live (un-graphed, events per launch)
+    roof = roof_iou = None
+    if rank == 0:
+        with torch.cuda.stream(stream):
+            res = eng.forward(sess.d_dets, sess.d_scores, sess.d_cls, sess.d_off)
+            red = eng._buf('red', (T, 32))
+            pooled = eng._buf('pooled', (T, 64))
+            s1 = 'gnet/block1/'
+            times = []
+            for rep in range(8):
+                flush.zero_()
+                pooled.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                ops.block_pair_fwd(res['pw_feats'], red, red, res['pair_c'], res['pair_n'],
+                                   res['num_pairs'], res['capacity'],
+                                   eng.p[s1 + 'pw_fc1/weights'], eng.p[s1 + 'pw_fc1/biases'],
+                                   eng.p[s1 + 'pw_fc2/weights'], eng.p[s1 + 'pw_fc2/biases'], pooled)
+                b.record(stream)
+                stream.synchronize()
+                times.append(a.elapsed_time(b))
+            k_ms = float(np.median(times[2:]))
+        flops = 20480.0 * P  # 2*(96*64 + 64*64) per pair
+        tf32_peak = bf16_peak / 2.0
+        roof = {'kernel': 'block_pair_fwd_kernel', 'bound': 'tensor',
+                'achieved': flops / (k_ms * 1e-3) / 1e12, 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                'frac': flops / (k_ms * 1e-3) / 1e12 / tf32_peak, 'traffic': None,
+                'ms_per_launch': k_ms, 'launches_per_step': args.blocks,
+                'algorithmic_flops_per_launch': flops,
+                'peak_source': '%s bf16 sustained %.1f TF/s / 2 (tf32 nominal ratio; the kernel '
+                               'computes in fp32)' % (peak_src, bf16_peak)}
+        # dense IoU kernel at the stress size (N=10000 -> 400 MB written, > L2)
+        with torch.cuda.stream(stream):
+            n_iou = 10000
+            from gossipnet_b200 import synthetic
+            big = torch.from_numpy(synthetic.make_image(n_iou, 1)['dets']).cuda()
+            out = torch.empty((1, n_iou, n_iou), device='cuda')
+            times = []
+            for rep in range(8):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                ops.iou_dense(big.unsqueeze(0), big.unsqueeze(0), out=out)
+                b.record(stream)
+                stream.synchronize()
+                times.append(a.elapsed_time(b))
+            i_ms = float(np.median(times[2:]))
+            del out
+        iou_bytes = 4.0 * n_iou * n_iou + 16.0 * 2 * n_iou
+        roof_iou = {'kernel': 'iou_dense_kernel', 'bound': 'hbm',
+                    'achieved': iou_bytes / (i_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': iou_bytes / (i_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
+                    'ms_per_launch': i_ms, 'workload': 'N=M=%d, one image' % n_iou,
+                    'peak_source': peak_src}
+
+    # ---- CPU baseline on this box's cores (rank 0, N=1) ---------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, n_img, dt = cpu_forward_rate(cfg, N, args.cpu_seconds)
+        cpu = {'value': rate, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': '%d images x N=%d, one image per call, %.1f s; numpy float32 restatement '
+                         'of the reference (oracle/gnet_oracle.py)' % (n_img, N, dt)}
+
+    if rank == 0:
+        print(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'coco_person N=%d dets/image, %d blocks, d=128, fp32 '
+                                   '(BASELINE configs[1])' % (N, args.blocks),
+                       'images_per_gpu_per_step': B, 'pairs_per_step_rank0': P,
+                       'parallelism': 'images sharded over %d GPU(s), no data-path collective'
+                                      % world,
+                       'l2': 'flushed between timed steps (256 MiB memset); working set also '
+                             '> 126 MB L2',
+                       'cuda_graph': bool(sess._graph)},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': sess.h2d_bytes,
+                    'd2h_bytes_per_step': sess.d2h_bytes, 'ms_per_step': e2e_ms / args.steps,
+                    'api': 'gossipnet_b200.session.InferenceSession.run (numpy in/out)'},
+            'gpu_launches': launches * args.steps,
+            'clocks': clk, 'roofline': roof, 'roofline_iou': roof_iou, 'cpu_baseline': cpu,
+            'logit_checksum': float(np.sum(pred, dtype=np.float64)),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

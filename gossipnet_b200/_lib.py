@@ -47,6 +47,9 @@ SIGNATURES = {
 _RESTYPES = {'gn_last_error': ctypes.c_char_p}
 
 _lib = None
+# number of C-ABI compute calls made so far (each is one kernel launch of this
+# library); bench.py reports the count inside its timed region
+CALLS = [0]
 
 
 class GossipnetError(RuntimeError):
@@ -74,6 +77,7 @@ def call(name, *args):
     """Call an int-returning entry point; raise on a non-zero status."""
     lib = load()
     rc = getattr(lib, name)(*args)
+    CALLS[0] += 1
     if rc != 0:
         msg = lib.gn_last_error()
         msg = msg.decode() if msg else ''

@@ -204,7 +204,8 @@ class Gnet(object):
             self.gt_boxdata = self._xyxy_to_boxdata(self.gt_boxes)
             self.labels, self.weights = res['labels'], res['weights']
             self.det_gt_matching = res['det_gt_matching']
-            self.det_anno_iou = res['det_anno_iou'].view(self.num_dets, -1).clone()
+            self.det_anno_iou = res['det_anno_iou'].reshape(
+                self.num_dets, int(res['gt_boxes'].shape[0])).clone()
             lo = res['loss_out'][0]
             self.loss_unnormed, self.loss_normed, self.loss = lo[0], lo[1], lo[2]
         return self.prediction

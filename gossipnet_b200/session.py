@@ -1,0 +1,108 @@
+"""Host-buffer inference sessions: the batched equivalent of the reference's
+test loop (test.py:63-71: feed numpy arrays -> sess.run(net.prediction) -> numpy
+scores), with the host<->device copies done from pinned staging buffers and the
+whole forward replayed as ONE CUDA graph per batch shape.
+
+    sess = InferenceSession(net)
+    new_scores = sess.run(dets, det_scores, det_classes, img_off)   # numpy in, numpy out
+
+`run` is the call bench.py times for the end-to-end number: it includes the
+host->device copy of the step's inputs and the device->host read of its
+logits.
+"""
+import numpy as np
+import torch
+
+from gossipnet_b200 import _lib
+from gossipnet_b200.engine import CapacityOverflow
+
+
+class InferenceSession(object):
+
+    def __init__(self, net, use_graph=True):
+        self.net = net
+        self.engine = net.engine
+        self.device = net.device
+        self.use_graph = use_graph
+        self._shape = None
+        self._graph = None
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.launches_per_forward = None
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self, T, B):
+        dev = self.device
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
+        self.h_dets, self.d_dets = pin((T, 4), torch.float32), torch.empty((T, 4), device=dev)
+        self.h_scores, self.d_scores = pin((T,), torch.float32), torch.empty(T, device=dev)
+        self.h_cls = pin((T,), torch.int32)
+        self.d_cls = torch.empty(T, dtype=torch.int32, device=dev)
+        self.h_off = pin((B + 1,), torch.int32)
+        self.d_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        self.h_pred = pin((T,), torch.float32)
+        self.h_np = pin((1,), torch.int32)
+        self.h2d_bytes = T * (16 + 4 + 4) + (B + 1) * 4
+        self.d2h_bytes = T * 4 + 4
+        self._shape = (T, B)
+        self._graph = None
+
+    def _forward(self):
+        res = self.engine.forward(self.d_dets, self.d_scores, self.d_cls, self.d_off)
+        self._pred, self._num_pairs, self._cap = res['prediction'], res['num_pairs'], res['capacity']
+
+    def _prepare(self):
+        """Warm up (learns the pair capacity, sets kernel attributes) and capture."""
+        with torch.cuda.stream(self.stream):
+            for _ in range(2):
+                while True:
+                    self._forward()
+                    try:
+                        self.engine.check_overflow()
+                        break
+                    except CapacityOverflow:
+                        continue
+            n0 = _lib.CALLS[0]
+            self._forward()
+            self.launches_per_forward = _lib.CALLS[0] - n0
+            self.stream.synchronize()
+            if self.use_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._forward()
+                self._graph = g
+            else:
+                self._graph = False
+
+    # ---------------------------------------------------------------------- run
+    def run(self, dets, det_scores, det_classes, img_off):
+        """numpy: dets[T,4] f32, det_scores[T] f32, det_classes[T] i32,
+        img_off[B+1] i32 -> new scores (logits) [T] f32 (a view of the pinned
+        result buffer, valid until the next run)."""
+        T, B = int(dets.shape[0]), int(img_off.shape[0]) - 1
+        if self._shape != (T, B):
+            self._alloc(T, B)
+        self.h_dets.numpy()[...] = dets
+        self.h_scores.numpy()[...] = det_scores
+        self.h_cls.numpy()[...] = det_classes
+        self.h_off.numpy()[...] = img_off
+        for attempt in range(3):
+            with torch.cuda.stream(self.stream):
+                self.d_dets.copy_(self.h_dets, non_blocking=True)
+                self.d_scores.copy_(self.h_scores, non_blocking=True)
+                self.d_cls.copy_(self.h_cls, non_blocking=True)
+                self.d_off.copy_(self.h_off, non_blocking=True)
+                if self._graph is None:
+                    self._prepare()
+                if self._graph:
+                    self._graph.replay()
+                else:
+                    self._forward()
+                self.h_pred.copy_(self._pred, non_blocking=True)
+                self.h_np.copy_(self._num_pairs, non_blocking=True)
+            self.stream.synchronize()
+            if int(self.h_np[0]) <= self._cap:
+                return self.h_pred.numpy()
+            # denser batch than the workspace was sized for: grow, re-capture, redo
+            self.engine.capacity = int(int(self.h_np[0]) * 1.25) + 256
+            self._graph = None
+        raise RuntimeError('pair capacity did not converge')

@@ -1,0 +1,128 @@
+"""GPU: whole Gnet forward (+ matching + loss) through the nms_net surface vs
+(a) the golden vectors made by executing the reference's own code and (b) the
+oracle on fresh synthetic inputs.  Index outputs bit-exact; logits within the
+1e-4 relative tolerance BASELINE.json states (max|d| / max|ref|)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gossipnet_b200 import params as P
+from gossipnet_b200 import synthetic
+from gossipnet_b200.nms_net.config import cfg
+from gossipnet_b200.nms_net.network import Gnet
+from oracle import det_matching_oracle, gnet_oracle
+from tests.helpers import GOLDEN, load_experiment, rel_err
+from tests.test_oracle_golden import CASES, setup_case
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-4
+
+
+def check_against(net, ref, with_loss=True):
+    assert np.array_equal(net.neighbor_pair_idxs.cpu().numpy(), ref['neighbor_pair_idxs'])
+    assert net.neighbor_pair_idxs.dtype == torch.int64
+    pred = net.prediction.cpu().numpy()
+    assert rel_err(pred, ref['prediction']) < LOGIT_TOL
+    if with_loss:
+        assert np.array_equal(net.det_anno_iou.cpu().numpy(), ref['det_anno_iou'])
+        # matching consumes the GPU logits: identical decisions unless two logits
+        # are closer than the logit tolerance (not the case for these inputs)
+        assert np.array_equal(net.det_gt_matching.cpu().numpy(), ref['det_gt_matching'])
+        assert np.array_equal(net.labels.cpu().numpy(), ref['labels'])
+        assert np.allclose(net.weights.cpu().numpy(), ref['weights'], rtol=1e-6)
+        for k in ('loss', 'loss_normed', 'loss_unnormed'):
+            assert abs(float(getattr(net, k)) - float(ref[k])) <= 2e-4 * max(1.0, abs(float(ref[k])))
+
+
+@pytest.mark.parametrize('name', CASES)
+@pytest.mark.parametrize('fused', [True, False])
+def test_forward_matches_reference_golden(name, fused):
+    g, num_classes, layout, flat, img = setup_case(name)
+    net = Gnet(num_classes, class_weights=g['class_weights'], params=flat)
+    net.engine.use_fused = fused
+    net(img)
+    check_against(net, g)
+    if 'pw_feats' in g:
+        assert rel_err(net.pw_feats.cpu().numpy(), g['pw_feats']) < 2e-5
+        assert rel_err(net.block_feats[1].cpu().numpy(), g['block1_feats']) < 2e-5
+        assert rel_err(net.block_feats[-1].cpu().numpy(), g['last_feats']) < LOGIT_TOL
+        assert np.array_equal(net.det_det_iou.cpu().numpy(), g['det_det_iou'])
+
+
+@pytest.mark.parametrize('n,blocks,exp,C', [(300, 2, 'coco_person', 1),       # BASELINE configs[0]
+                                            (1000, 16, 'coco_person', 1),     # configs[1]
+                                            (2000, 16, 'coco_multiclass', 80)])  # configs[2] (fp32)
+def test_forward_matches_oracle_at_baseline_configs(n, blocks, exp, C, oracle_built):
+    load_experiment(exp, num_blocks=blocks)
+    layout, total = P.param_layout(C, cfg)
+    flat = P.init_flat(layout, total, cfg, seed=11)
+    img = synthetic.make_image(n, C, image_index=0)
+    ref = gnet_oracle.gnet_forward(img, P.views(layout, flat), cfg, C,
+                                   matching_fn=det_matching_oracle.detection_matching)
+    net = Gnet(C, params=flat)
+    net(img)
+    check_against(net, ref)
+
+
+def test_batched_forward_equals_per_image():
+    load_experiment('coco_person', num_blocks=4)
+    net = Gnet(1)
+    sizes = [300, 1, 1000, 57, 640]
+    imgs = [synthetic.make_image(n, 1, image_index=i) for i, n in enumerate(sizes)]
+    res = net.run_batch(imgs)
+    off = res['img_off_host']
+    batched = res['prediction'].cpu().numpy().copy()
+    assign = res['det_gt_matching'].cpu().numpy().copy()
+    for i, img in enumerate(imgs):
+        single = net(img).cpu().numpy()
+        assert np.array_equal(batched[off[i]:off[i + 1]], single)   # same kernels, same order
+        assert np.array_equal(assign[off[i]:off[i + 1]], net.det_gt_matching.cpu().numpy())
+
+
+def test_capacity_regrows_on_denser_batch():
+    load_experiment('coco_person', num_blocks=2)
+    net = Gnet(1)
+    small = synthetic.make_image(100, 1)
+    net(small)
+    cap0 = net.engine.capacity
+    big = synthetic.make_image(2000, 1)
+    pred = net(big).cpu().numpy()
+    assert net.engine.capacity > cap0
+    layout, total = P.param_layout(1, cfg)
+    ref = gnet_oracle.gnet_forward({k: v for k, v in big.items() if not k.startswith('gt_')},
+                                   P.views(layout, net.engine.flat.cpu().numpy()), cfg, 1)
+    assert rel_err(pred, ref['prediction']) < LOGIT_TOL
+
+
+def test_inference_without_ground_truth_and_reuse():
+    load_experiment('coco_person', num_blocks=2)
+    net = Gnet(1)
+    img = synthetic.make_image(64, 1)
+    test_batch = {k: img[k] for k in Gnet.get_batch_spec(1, is_training=False)}
+    pred = net(test_batch)
+    assert pred.shape == (64,) and net.labels is None and net.loss is None
+    val = Gnet(1, reuse=True)
+    assert val.engine is net.engine
+    assert torch.equal(val(test_batch), pred)
+    names = [v.name for v in net.trainable_variables]
+    assert 'gnet/block1/pw_fc1/weights:0' in names and len(names) == len(net.engine.layout)
+
+
+def test_static_block_matches_oracle():
+    load_experiment('coco_person', num_blocks=2)
+    net = Gnet(1)
+    img = synthetic.make_image(200, 1)
+    net(img)
+    pairs = net.neighbor_pair_idxs
+    infeats = net.block_feats[1]
+    out = Gnet._block(2, infeats, None, None, pairs[:, 0], pairs[:, 1], net.pw_feats, None)
+    assert rel_err(out.cpu().numpy(), net.block_feats[2].cpu().numpy()) < 1e-6
+
+
+def test_imfeats_is_rejected_loudly():
+    cfg.gnet.imfeats = True
+    with pytest.raises(NotImplementedError):
+        Gnet(1)

@@ -1,0 +1,93 @@
+"""CPU: host-side logic that mirrors the reference's Python surface."""
+import numpy as np
+import pytest
+
+from gossipnet_b200 import params as P
+from gossipnet_b200 import synthetic
+from gossipnet_b200.nms_net import config as C
+from gossipnet_b200.nms_net.config import cfg
+from tests.helpers import load_experiment
+
+
+def test_cfg_defaults_match_reference_keys():
+    assert cfg.gnet.neighbor_thresh == 0.2 and cfg.gnet.num_blocks == 16
+    assert cfg.gnet.shortcut_dim == 128 and cfg.gnet.reduced_dim == 32
+    assert cfg.gnet.pairfeat_dim == 64 and cfg.gnet.num_pwfeat_fc == 0
+    assert cfg.train.normalize_loss is False and cfg.train.loss_multiplyer == 1.0
+
+
+def test_cfg_merge_rules():
+    with pytest.raises(KeyError):
+        C.cfg_from_dict({'gnet': {'no_such_key': 1}})
+    with pytest.raises(ValueError):
+        C.cfg_from_dict({'gnet': {'num_blocks': '16'}})
+    C.cfg_from_dict({'gnet': {'num_blocks': 4}})
+    assert cfg.gnet.num_blocks == 4
+
+
+def test_shipped_experiments_load():
+    load_experiment('coco_person')
+    assert cfg.gnet.num_blocks == 1 and cfg.gnet.num_pwfeat_fc == 3
+    assert cfg.gnet.pwfeat_narrow_dim == 32 and cfg.gnet.bias_const_init == 0.1
+    C.reset_cfg()
+    load_experiment('coco_multiclass')
+    assert cfg.gnet.num_blocks == 16 and cfg.gnet.bias_const_init == 0.01
+
+
+def test_param_counts_match_survey():
+    load_experiment('coco_person', num_blocks=16)
+    layout, total = P.param_layout(1, cfg)
+    assert P.num_params(layout) == 541345
+    C.reset_cfg()
+    load_experiment('coco_multiclass')
+    layout, total = P.param_layout(80, cfg)
+    assert P.num_params(layout) == 581793
+    names = list(layout)
+    assert 'gnet/pw_feats/fc1/weights' in names and 'gnet/block16/fc2/biases' in names
+    assert 'gnet/predict/logits/fully_connected/weights' in names
+    assert layout['gnet/block3/pw_fc1/weights'].shape == (96, 64)
+    assert not layout['gnet/predict/fc1/fully_connected/weights'].regularized
+    assert layout['gnet/block1/fc1/weights'].regularized
+    assert not layout['gnet/block1/fc1/biases'].regularized
+    assert all(e.offset % 4 == 0 for e in layout.values())
+
+
+def test_synthetic_boxes_are_valid():
+    img = synthetic.make_image(1000, 1)
+    d = img['dets']
+    assert d.dtype == np.float32 and d.shape == (1000, 4)
+    assert np.all(d[:, 2] >= d[:, 0] + 4) and np.all(d[:, 3] >= d[:, 1] + 4)
+    assert np.all(d >= 0) and np.all(d[:, 2] <= 1000) and np.all(d[:, 3] <= 600)
+    img2 = synthetic.make_image(1000, 1)
+    assert np.array_equal(d, img2['dets'])
+
+
+def test_class_equal_weights():
+    from gossipnet_b200.nms_net.class_weights import class_equal_weights_from_counts
+    cfg.train.pos_weight = 0.1
+    w = class_equal_weights_from_counts([900, 50, 50])
+    assert np.allclose(w, [1000 * 0.9 / 900, 1000 * 0.05 / 50, 1000 * 0.05 / 50])
+
+
+def test_nms_net_alias_package_is_the_implementation():
+    import nms_net
+    from nms_net import cfg as cfg2, matching_module
+    from nms_net.network import Gnet
+    import gossipnet_b200.nms_net.network as impl
+    assert cfg2 is cfg and Gnet is impl.Gnet
+    assert hasattr(matching_module, 'detection_matching')
+    spec = Gnet.get_batch_spec(1, is_training=False)
+    assert sorted(spec) == ['det_classes', 'det_scores', 'dets']
+    assert sorted(Gnet.get_batch_spec(80)) == ['det_classes', 'det_scores', 'dets', 'gt_boxes',
+                                               'gt_classes', 'gt_crowd']
+    assert nms_net.cfg is cfg
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    from tests.helpers import ROOT
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'gossipnet_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'import oracle' not in text and 'from oracle' not in text, f
