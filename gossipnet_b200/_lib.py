@@ -43,6 +43,7 @@ SIGNATURES = {
     'gn_loss_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                     c_void_p, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p,
                     c_void_p],
+    'gn_selftest_umma': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
 }
 _RESTYPES = {'gn_last_error': ctypes.c_char_p}
 

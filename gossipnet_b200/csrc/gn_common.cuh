@@ -64,7 +64,11 @@ __device__ __forceinline__ float box_intersection(const Box& a, const Box& b) {
 __device__ __forceinline__ float box_iou(const Box& a, const Box& b) {
   const float inter = box_intersection(a, b);
   const float uni = __fsub_rn(__fadd_rn(a.area, b.area), inter);
-  return __fdiv_rn(inter, uni);
+  // 0 / positive is +0 exactly; a zero numerator would leave div.rn's fast path,
+  // and most pairs are disjoint.  Everything else takes the exact IEEE division.
+  const bool zero = (inter == 0.0f) && (uni > 0.0f);
+  const float q = __fdiv_rn(zero ? uni : inter, uni);
+  return zero ? 0.0f : q;
 }
 
 // index of the image that owns detection row `row`: largest i with off[i] <= row

@@ -1,67 +1,101 @@
 // Dense box IoU / IoA (A1 + A2).  HBM-store bound: 4 bytes out per pair, the
-// 16-byte boxes are reused from registers / L1.
+// 16-byte boxes are reused from registers / shared memory.
 //
-// Layout: a[batch,n,4], b[batch,m,4] -> out[batch,n,m].  One CTA owns a strip
-// of ROWS_PER_CTA rows and all m columns of one image; each thread keeps the
-// boxes of 4 consecutive columns in registers, walks the strip's rows (row box
-// is a warp-uniform broadcast load) and emits one 16-byte streaming store per
-// row, so a warp writes 512 contiguous bytes per instruction.
+// Layout: a[batch,n,4], b[batch,m,4] -> out[batch,n,m].  A CTA owns a tile of
+// IOU_ROWS rows x (IOU_THREADS*4) columns of one image: the row boxes (+areas)
+// are staged in shared memory once, each thread keeps the boxes of 4
+// consecutive columns in registers, walks the rows and emits one 16-byte
+// streaming store per row, so a warp writes 512 contiguous bytes per
+// instruction.  The grid is (column tiles, row tiles, images): thousands of
+// small CTAs, so the 148 SMs stay evenly loaded at any N.
+//
+// Division: most pairs are disjoint (inter == 0).  IEEE division with a zero
+// numerator leaves the fast path of div.rn.f32, so for inter == 0 and a
+// positive union the quotient (+0) is produced by a select instead; every other
+// case (including zero / NaN unions of degenerate boxes) goes through the exact
+// __fdiv_rn, so results stay bit-identical to the reference arithmetic.
 #include "gn_common.cuh"
 
 namespace gn {
 
-constexpr int IOU_THREADS = 256;
-constexpr int IOU_ROWS_PER_CTA = 16;
+constexpr int IOU_THREADS = 128;
+constexpr int IOU_ROWS = 32;
+constexpr int IOU_COLS = IOU_THREADS * 4;
 
-template <bool VEC4>
+template <bool CROWD, bool CLS, bool VEC4>
 __global__ void __launch_bounds__(IOU_THREADS)
 iou_dense_kernel(const float* __restrict__ a, const float* __restrict__ b,
                  const uint8_t* __restrict__ crowd, const int32_t* __restrict__ a_cls,
-                 const int32_t* __restrict__ b_cls, int n, int m, int strips_per_image,
-                 float* __restrict__ out) {
-  const int img = blockIdx.x / strips_per_image;
-  const int strip = blockIdx.x - img * strips_per_image;
-  const int row0 = strip * IOU_ROWS_PER_CTA;
-  const int row1 = min(row0 + IOU_ROWS_PER_CTA, n);
+                 const int32_t* __restrict__ b_cls, int n, int m, float* __restrict__ out) {
+  __shared__ float4 row_box[IOU_ROWS];
+  __shared__ float row_area[IOU_ROWS];
+  __shared__ int row_cls[IOU_ROWS];
+  const int img = blockIdx.z;
+  const int row0 = blockIdx.y * IOU_ROWS;
+  const int nrows = min(IOU_ROWS, n - row0);
   const float* ai = a + (size_t)img * n * 4;
   const float* bi = b + (size_t)img * m * 4;
   float* oi = out + (size_t)img * n * m;
 
-  for (int c0 = threadIdx.x * 4; c0 < m; c0 += IOU_THREADS * 4) {
-    Box cb[4];
-    bool cr[4];
-    int cc[4];
+  if (threadIdx.x < nrows) {
+    const float4 v = ldg4(ai + (size_t)(row0 + threadIdx.x) * 4);
+    row_box[threadIdx.x] = v;
+    row_area[threadIdx.x] = __fmul_rn(__fsub_rn(v.z, v.x), __fsub_rn(v.w, v.y));
+    if (CLS) row_cls[threadIdx.x] = a_cls[(size_t)img * n + row0 + threadIdx.x];
+  }
+  __syncthreads();
+
+  const int c0 = blockIdx.x * IOU_COLS + threadIdx.x * 4;
+  if (c0 >= m) return;
+  Box cb[4];
+  bool cr[4];
+  int cc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = min(c0 + j, m - 1);
+    cb[j] = make_box(ldg4(bi + (size_t)c * 4));
+    cr[j] = CROWD ? (crowd[(size_t)img * m + c] != 0) : false;
+    cc[j] = CLS ? b_cls[(size_t)img * m + c] : 0;
+  }
+  float* dst = oi + (size_t)row0 * m + c0;
+#pragma unroll 2
+  for (int r = 0; r < nrows; ++r, dst += m) {
+    const float4 rv = row_box[r];
+    const float ra = row_area[r];
+    float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = min(c0 + j, m - 1);
-      cb[j] = make_box(ldg4(bi + (size_t)c * 4));
-      cr[j] = crowd ? (crowd[(size_t)img * m + c] != 0) : false;
-      cc[j] = b_cls ? b_cls[(size_t)img * m + c] : 0;
+      const float w = fmaxf(0.0f, __fsub_rn(fminf(rv.z, cb[j].x2), fmaxf(rv.x, cb[j].x1)));
+      const float h = fmaxf(0.0f, __fsub_rn(fminf(rv.w, cb[j].y2), fmaxf(rv.y, cb[j].y1)));
+      const float inter = __fmul_rn(w, h);
+      const float uni = __fsub_rn(__fadd_rn(ra, cb[j].area), inter);
+      // crowd column: intersection over the DETECTION's area (network.py:485-488)
+      const float den = (CROWD && cr[j]) ? ra : uni;
+      const bool zero = (inter == 0.0f) && (den > 0.0f);   // 0 / positive = +0, exactly
+      float q = __fdiv_rn(zero ? den : inter, den);
+      q = zero ? 0.0f : q;
+      if (CLS && row_cls[r] != cc[j]) q = 0.0f;  // network.py:177-187
+      v[j] = q;
     }
-    for (int r = row0; r < row1; ++r) {
-      const Box rb = make_box(ldg4(ai + (size_t)r * 4));
-      const int rc = a_cls ? a_cls[(size_t)img * n + r] : 0;
-      float v[4];
+    if (VEC4) {
+      __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float inter = box_intersection(rb, cb[j]);
-        const float uni = __fsub_rn(__fadd_rn(rb.area, cb[j].area), inter);
-        // crowd column: intersection over the DETECTION's area (network.py:485-488)
-        const float den = cr[j] ? rb.area : uni;
-        float q = __fdiv_rn(inter, den);
-        if (a_cls && rc != cc[j]) q = 0.0f;  // network.py:177-187
-        v[j] = q;
-      }
-      float* dst = oi + (size_t)r * m + c0;
-      if (VEC4) {
-        __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c0 + j < m) __stcs(dst + j, v[j]);
-      }
+      for (int j = 0; j < 4; ++j)
+        if (c0 + j < m) __stcs(dst + j, v[j]);
     }
   }
+}
+
+template <bool CROWD, bool CLS>
+static void launch_iou(const float* a, const float* b, const uint8_t* crowd, const int32_t* a_cls,
+                       const int32_t* b_cls, int batch, int n, int m, float* out, bool vec,
+                       cudaStream_t s) {
+  dim3 grid(ceil_div(m, IOU_COLS), ceil_div(n, IOU_ROWS), batch);
+  if (vec)
+    iou_dense_kernel<CROWD, CLS, true><<<grid, IOU_THREADS, 0, s>>>(a, b, crowd, a_cls, b_cls, n, m, out);
+  else
+    iou_dense_kernel<CROWD, CLS, false><<<grid, IOU_THREADS, 0, s>>>(a, b, crowd, a_cls, b_cls, n, m, out);
 }
 
 }  // namespace gn
@@ -76,17 +110,15 @@ extern "C" int gn_iou_dense(const float* a, const float* b, const uint8_t* crowd
   GN_REQUIRE(a && b && out, "gn_iou_dense: null pointer");
   GN_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0,
              "gn_iou_dense: box arrays must be 16-byte aligned");
-  const int strips = gn::ceil_div(n, gn::IOU_ROWS_PER_CTA);
-  const int64_t grid = (int64_t)strips * batch;
-  GN_REQUIRE(grid < (1ll << 31), "gn_iou_dense: problem too large for one launch");
+  GN_REQUIRE(batch <= 65535 && gn::ceil_div(n, gn::IOU_ROWS) <= 65535,
+             "gn_iou_dense: problem too large for one launch");
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (m % 4 == 0) && (((uintptr_t)out & 15) == 0);
-  if (vec)
-    gn::iou_dense_kernel<true><<<(unsigned)grid, gn::IOU_THREADS, 0, s>>>(
-        a, b, crowd, a_cls, b_cls, n, m, strips, out);
-  else
-    gn::iou_dense_kernel<false><<<(unsigned)grid, gn::IOU_THREADS, 0, s>>>(
-        a, b, crowd, a_cls, b_cls, n, m, strips, out);
+  const bool has_crowd = crowd != nullptr, has_cls = a_cls != nullptr;
+  if (has_crowd && has_cls) gn::launch_iou<true, true>(a, b, crowd, a_cls, b_cls, batch, n, m, out, vec, s);
+  else if (has_crowd) gn::launch_iou<true, false>(a, b, crowd, a_cls, b_cls, batch, n, m, out, vec, s);
+  else if (has_cls) gn::launch_iou<false, true>(a, b, crowd, a_cls, b_cls, batch, n, m, out, vec, s);
+  else gn::launch_iou<false, false>(a, b, crowd, a_cls, b_cls, batch, n, m, out, vec, s);
   GN_CHECK_LAUNCH("gn_iou_dense");
   return GN_OK;
 }

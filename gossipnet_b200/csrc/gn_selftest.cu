@@ -1,0 +1,114 @@
+// Diagnostic entry point: one 128 x 64 x K product on the tensor cores with the
+// exact building blocks the FC kernels use (bf16x3 split operands in the
+// no-swizzle K-major shared-memory layout, tcgen05.mma into TMEM, tcgen05.ld
+// epilogue).  tests/test_gpu_umma.py checks it against a float64 product, so a
+// wrong descriptor / layout assumption shows up here and not inside a fused kernel.
+#include "gn_common.cuh"
+#include "gn_umma.cuh"
+
+namespace gn {
+
+constexpr int ST_M = 128, ST_N = 64, ST_KMAX = 256;
+
+// c[128,64] = a[128,k] @ w[k,64]
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                     float* __restrict__ c, int k) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int t = threadIdx.x, warp = t >> 5;
+  const int chunks = k / 8;
+  // [chunk][row][8 bf16]
+  uint4* a_hi = reinterpret_cast<uint4*>(smem);
+  uint4* a_lo = a_hi + chunks * ST_M;
+  uint4* b_hi = a_lo + chunks * ST_M;
+  uint4* b_lo = b_hi + chunks * ST_N;
+
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 64);
+  if (t == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_barrier_init();
+  }
+  // A: thread t owns row t
+  for (int j = 0; j < chunks; ++j) {
+    const float4 v0 = ldg4(a + (size_t)t * k + j * 8), v1 = ldg4(a + (size_t)t * k + j * 8 + 4);
+    uint4 h, l;
+    umma::split_bf16x2(v0.x, v0.y, h.x, l.x);
+    umma::split_bf16x2(v0.z, v0.w, h.y, l.y);
+    umma::split_bf16x2(v1.x, v1.y, h.z, l.z);
+    umma::split_bf16x2(v1.z, v1.w, h.w, l.w);
+    a_hi[j * ST_M + t] = h;
+    a_lo[j * ST_M + t] = l;
+  }
+  // B[n][kk] = w[kk][n]: thread handles n = t % 64, chunks of parity t / 64
+  for (int j = t >> 6; j < chunks; j += 2) {
+    const int n = t & 63;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = __ldg(w + (size_t)(j * 8 + e) * ST_N + n);
+    uint4 h, l;
+    umma::split_bf16x2(x[0], x[1], h.x, l.x);
+    umma::split_bf16x2(x[2], x[3], h.y, l.y);
+    umma::split_bf16x2(x[4], x[5], h.z, l.z);
+    umma::split_bf16x2(x[6], x[7], h.w, l.w);
+    b_hi[j * ST_N + n] = h;
+    b_lo[j * ST_N + n] = l;
+  }
+  umma::fence_smem_to_async();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = tmem_base;
+
+  if (t == 0) {
+    const uint32_t idesc = umma::idesc_bf16_f32(ST_M, ST_N);
+    const uint32_t lbo_a = ST_M * 16, lbo_b = ST_N * 16, sbo = 128;
+    uint32_t acc = 0;
+    for (int ks = 0; ks < k / 16; ++ks) {
+      const uint64_t dah = umma::smem_desc(umma::smem_u32(a_hi) + ks * 2 * lbo_a, lbo_a, sbo);
+      const uint64_t dal = umma::smem_desc(umma::smem_u32(a_lo) + ks * 2 * lbo_a, lbo_a, sbo);
+      const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ks * 2 * lbo_b, lbo_b, sbo);
+      const uint64_t dbl = umma::smem_desc(umma::smem_u32(b_lo) + ks * 2 * lbo_b, lbo_b, sbo);
+      umma::mma_bf16_ss(tmem, dal, dbh, idesc, acc);
+      umma::mma_bf16_ss(tmem, dah, dbl, idesc, 1);
+      umma::mma_bf16_ss(tmem, dah, dbh, idesc, 1);
+      acc = 1;
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after();
+
+#pragma unroll
+  for (int c0 = 0; c0 < ST_N; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[(size_t)t * ST_N + c0 + i] = v[i];
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 64);
+}
+
+}  // namespace gn
+
+extern "C" int gn_selftest_umma(const float* a, const float* w, float* c, int k,
+                                gn_stream_t stream) {
+  GN_REQUIRE(a && w && c, "gn_selftest_umma: null pointer");
+  GN_REQUIRE(k >= 16 && k % 16 == 0 && k <= gn::ST_KMAX, "gn_selftest_umma: k=%d must be a "
+             "multiple of 16 in [16, %d]", k, gn::ST_KMAX);
+  GN_REQUIRE((((uintptr_t)a | (uintptr_t)w) & 15) == 0, "gn_selftest_umma: unaligned pointer");
+  const int smem = (k / 8) * (gn::ST_M + gn::ST_N) * 16 * 2;
+  cudaError_t e = cudaFuncSetAttribute(gn::umma_selftest_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    gn::set_error("gn_selftest_umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
+  gn::umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, w, c, k);
+  GN_CHECK_LAUNCH("gn_selftest_umma");
+  return GN_OK;
+}

@@ -1,0 +1,144 @@
+// Blackwell (sm_100a) tensor-core plumbing used by the FC kernels: tcgen05.mma
+// with shared-memory operands and TMEM accumulators, TMEM allocation and loads,
+// mbarrier completion tracking.  Hand-written PTX wrappers; no library code.
+//
+// Numerics: the reference computes its FCs in float32.  bf16 tensor-core
+// operands carry 8 significant bits, so every fp32 operand x is split into
+// hi = bf16(x) and lo = bf16(x - hi) (|x - hi - lo| <= 2^-17 |x|) and a product
+// is evaluated as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  with fp32 accumulation in
+// TMEM ("bf16x3").  The dropped a_lo*b_lo term and the split residuals are
+// ~2^-16 relative per product, which keeps the logits inside the 1e-4 relative
+// budget of BASELINE.json (measured: tests/test_gpu_forward.py).
+//
+// Shared-memory operand layout (both A[M,K] and B[N,K], K-major, no swizzle =
+// the "interleaved" canonical layout): 16-byte chunks of 8 bf16 along K; a core
+// matrix is 8 rows x 16 B stored contiguously (128 B); chunk j of row r lives at
+//     base + j * LBO + (r / 8) * SBO + (r % 8) * 16
+// One tcgen05.mma consumes K = 16 (two chunks); advancing K by 16 moves the
+// descriptor start address by 2 * LBO.
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace gn {
+namespace umma {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier -----------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done != 0;
+}
+// Bounded wait: a malformed descriptor must end as a reported launch failure
+// (trap), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+    if (spin > (1u << 26)) __trap();
+}
+
+// ---- TMEM ---------------------------------------------------------------------
+// One full warp allocates `ncols` (power of two >= 32) columns; the base address
+// is written to *dst_smem.
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+               ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// generic-proxy smem writes -> visible to the tensor core (async proxy)
+__device__ __forceinline__ void fence_smem_to_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// TMEM address: lane in bits [16,32), column in bits [0,16).  A warp may only
+// touch lanes 32*(warp%4) .. +31.  32x32b.x16: thread i of the warp receives 16
+// consecutive fp32 columns of lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---- descriptors ----------------------------------------------------------------
+// Shared-memory matrix descriptor, K-major, no swizzle (layout_type 0), version 1.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;
+}
+// Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
+  return (1u << 4)                      // D format: F32
+         | (1u << 7)                    // A format: BF16
+         | (1u << 10)                   // B format: BF16
+         | ((uint32_t)(n >> 3) << 17)   // N / 8
+         | ((uint32_t)(m >> 4) << 24);  // M / 16
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T.  Issued by ONE thread.
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Arrive on `bar` when every MMA issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- fp32 -> (hi, lo) bf16 split --------------------------------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+// two values -> packed hi pair and lo pair (element 0 in the low half)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+}  // namespace umma
+}  // namespace gn

@@ -202,3 +202,14 @@ def loss_fwd(prediction, labels, weights, assignment, gt_crowd, gt_classes, img_
               1 if normalize else 0, float(loss_multiplier), _chk(loss_out, f32, 'loss_out'),
               _chk(dlogit, f32, 'dlogit', True), _stream())
     return loss_out, dlogit
+
+
+# -------------------------------------------------------------------- diagnostics
+def selftest_umma(a, w):
+    """c[128,64] = a[128,k] @ w[k,64] through tcgen05 (see gn_selftest.cu)."""
+    if tuple(a.shape)[0] != 128 or tuple(w.shape) != (a.shape[1], 64):
+        raise ValueError('selftest_umma expects a[128,k], w[k,64]')
+    c = torch.empty((128, 64), dtype=torch.float32, device=a.device)
+    _lib.call('gn_selftest_umma', _chk(a, torch.float32, 'a'), _chk(w, torch.float32, 'w'),
+              _chk(c, torch.float32, 'c'), int(a.shape[1]), _stream())
+    return c

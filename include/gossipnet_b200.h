@@ -176,6 +176,13 @@ int gn_loss_fwd(const float* prediction, const float* labels, float* weights_io,
                 const float* class_weights, int normalize, float loss_multiplier,
                 float* loss_out, float* dlogit, gn_stream_t stream);
 
+/* ---- diagnostics ---------------------------------------------------------------
+ * c[128,64] = a[128,k] @ w[k,64] on the tensor cores with the building blocks of
+ * the FC kernels (bf16x3 split operands, tcgen05.mma into TMEM, tcgen05.ld).
+ * k: multiple of 16, <= 256.  No reference counterpart; used by the tests to pin
+ * the descriptor / layout conventions independently of the fused kernels. */
+int gn_selftest_umma(const float* a, const float* w, float* c, int k, gn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
