@@ -37,6 +37,9 @@ SIGNATURES = {
     'gn_block_pair_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                           c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_void_p],
+    'gn_block_pair_fwd_ffma': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                               c_void_p, c_void_p],
     'gn_detection_matching': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p],

@@ -2,7 +2,8 @@
 //
 // Unfused pieces in the reference's formulation (parity cross-check and the
 // path for non-shipped shapes): gather+concat, segment max.
-// Fused hot path (CUDA-core FFMA engine): a persistent CTA takes tiles of 128
+// Fused CUDA-core (FFMA) variant, kept as gn_block_pair_fwd_ffma: the fp32
+// cross-check of the tensor-core kernel in gn_block_tc.cu.  A persistent CTA takes tiles of 128
 // consecutive pairs; pw_feats rows and the gathered detection features are
 // cp.async'd straight into a pair-major [128][96] shared tile (self-pair
 // neighbour halves and rows past P are zero-filled by the copy itself), both
@@ -241,30 +242,30 @@ extern "C" int gn_segment_max(const float* x, int f, const int32_t* row_ptr, int
   return GN_OK;
 }
 
-extern "C" int gn_block_pair_fwd(const float* pw, int w, const float* feats,
+extern "C" int gn_block_pair_fwd_ffma(const float* pw, int w, const float* feats,
                                  const float* nfeats, int r, const int32_t* pair_c,
                                  const int32_t* pair_n, const int32_t* num_pairs, int capacity,
                                  const float* w1, const float* b1, const float* w2,
                                  const float* b2, int f, float* pooled, gn_stream_t stream) {
-  GN_REQUIRE(capacity >= 0, "gn_block_pair_fwd: negative capacity");
+  GN_REQUIRE(capacity >= 0, "gn_block_pair_fwd_ffma: negative capacity");
   if (w != gn::BP_W || r != gn::BP_R || f != gn::BP_F) {
-    gn::set_error("gn_block_pair_fwd: fused kernel is built for w=%d r=%d f=%d (got %d, %d, %d)",
+    gn::set_error("gn_block_pair_fwd_ffma: fused kernel is built for w=%d r=%d f=%d (got %d, %d, %d)",
                   gn::BP_W, gn::BP_R, gn::BP_F, w, r, f);
     return GN_ERR_UNSUPPORTED;
   }
   if (capacity == 0) return GN_OK;
   GN_REQUIRE(pw && feats && nfeats && pair_c && pair_n && num_pairs && w1 && b1 && w2 && b2 &&
                  pooled,
-             "gn_block_pair_fwd: null pointer");
+             "gn_block_pair_fwd_ffma: null pointer");
   GN_REQUIRE((((uintptr_t)pw | (uintptr_t)feats | (uintptr_t)nfeats | (uintptr_t)w1 |
                (uintptr_t)b1 | (uintptr_t)w2 | (uintptr_t)b2) & 15) == 0,
-             "gn_block_pair_fwd: pointers must be 16-byte aligned");
+             "gn_block_pair_fwd_ffma: pointers must be 16-byte aligned");
   static_assert(sizeof(gn::BpSmem) <= 227 * 1024, "block tile exceeds shared memory");
   const int smem = (int)sizeof(gn::BpSmem);
   cudaError_t e = cudaFuncSetAttribute(gn::block_pair_fwd_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
-    gn::set_error("gn_block_pair_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    gn::set_error("gn_block_pair_fwd_ffma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return GN_ERR_CUDA;
   }
   int grid = gn::ceil_div(capacity, gn::BP_TILE);
@@ -272,6 +273,6 @@ extern "C" int gn_block_pair_fwd(const float* pw, int w, const float* feats,
   if (grid > sms) grid = sms;
   gn::block_pair_fwd_kernel<<<grid, gn::BP_THREADS, smem, (cudaStream_t)stream>>>(
       pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2, pooled);
-  GN_CHECK_LAUNCH("gn_block_pair_fwd");
+  GN_CHECK_LAUNCH("gn_block_pair_fwd_ffma");
   return GN_OK;
 }

@@ -1,0 +1,317 @@
+// One Gnet block's pair stage on the tensor cores (A7a + pw_fc1 + pw_fc2 + A7b),
+// shipped shape w = 32, r = 32, f = 64:
+//
+//   x[p]   = [pw_feats[p] | feats[pair_c[p]] | nfeats[pair_n[p]] (0 if c == n)]   (96)
+//   h1     = relu(x  @ W1 + b1)                                                    (64)
+//   h2     = relu(h1 @ W2 + b2)                                                    (64)
+//   pooled[c] = max over the pairs of c of h2                     (network.py:367-388)
+//
+// Tile = 128 consecutive pairs = the M dimension of one tcgen05.mma.  Per tile:
+//   1. fill   : 256 threads gather the 96 fp32 inputs of each pair (coalesced
+//               8-row x 128-byte warp requests), split every value into bf16
+//               hi + lo and store both into K-major operand tiles in shared memory;
+//   2. FC1    : one thread issues 6 k-steps x 3 (lo*hi, hi*lo, hi*hi) UMMAs,
+//               M=128 N=64 K=16, fp32 accumulation in TMEM columns [0,64);
+//   3. epi 1  : 8 warps read the accumulator (tcgen05.ld), add b1, ReLU, split to
+//               bf16 hi/lo and store h1 as the A operand of FC2;
+//   4. FC2    : 4 k-steps x 3 UMMAs into TMEM columns [64,128);
+//   5. epi 2  : + b2, ReLU, fp32 tile to shared memory;
+//   6. pool   : per column, runs of equal c are max-reduced and merged into
+//               pooled[] with one integer atomicMax per (segment, tile, column):
+//               activations are >= 0 and every detection owns its self pair, so
+//               the result is exact and order independent.
+// W1^T / W2^T (hi and lo) stay resident in shared memory for the CTA's lifetime.
+// The phases of one CTA are sequential; two CTAs are resident per SM (92 KB smem,
+// 128 TMEM columns each) so one CTA's UMMAs overlap the other's CUDA-core phases.
+#include "gn_common.cuh"
+#include "gn_umma.cuh"
+
+namespace gn {
+
+constexpr int TC_TILE = 128;
+constexpr int TC_THREADS = 256;
+constexpr int TC_W = 32, TC_R = 32, TC_F = 64;
+constexpr int TC_K1 = TC_W + 2 * TC_R;          // 96
+constexpr int TC_CH1 = TC_K1 / 8;               // 12 chunks of 8 bf16
+constexpr int TC_CH2 = TC_F / 8;                // 8
+constexpr uint32_t TC_SBO = 128;                // 8 rows x 16 B
+// A-side chunk pitch: 128 rows x 16 B + 32 B skew, so that the fill's
+// (2 rows x 4 chunks) quarter-warp store hits 8 distinct 16-byte bank groups
+constexpr uint32_t TC_LBO_A = TC_TILE * 16 + 32;
+constexpr uint32_t TC_LBO_B = TC_F * 16;        // 64 rows x 16 B
+constexpr int TC_LDH2 = TC_F + 4;               // fp32 h2 tile row pitch (floats)
+
+constexpr uint32_t TC_OFF_B1H = 0;
+constexpr uint32_t TC_OFF_B1L = TC_OFF_B1H + TC_CH1 * TC_LBO_B;
+constexpr uint32_t TC_OFF_B2H = TC_OFF_B1L + TC_CH1 * TC_LBO_B;
+constexpr uint32_t TC_OFF_B2L = TC_OFF_B2H + TC_CH2 * TC_LBO_B;
+constexpr uint32_t TC_OFF_A = TC_OFF_B2L + TC_CH2 * TC_LBO_B;           // 40960
+constexpr uint32_t TC_A_BYTES = 2 * TC_CH1 * TC_LBO_A;                   // hi + lo, 49920
+constexpr uint32_t TC_OFF_IDX = TC_OFF_A + TC_A_BYTES;                   // c[128], n[128]
+constexpr uint32_t TC_OFF_BIAS = TC_OFF_IDX + 2 * TC_TILE * 4;          // b1[64], b2[64]
+constexpr uint32_t TC_OFF_BAR = TC_OFF_BIAS + 2 * TC_F * 4;
+constexpr uint32_t TC_SMEM = TC_OFF_BAR + 16;
+static_assert(2 * TC_CH2 * TC_LBO_A <= TC_A_BYTES, "h1 operand tile must fit the A region");
+static_assert(TC_TILE * TC_LDH2 * 4 <= TC_A_BYTES, "h2 tile must fit the A region");
+static_assert(2 * TC_SMEM <= 227 * 1024, "two CTAs per SM");
+
+// transpose + split a [k_total, 64] fp32 weight into K-major hi / lo operand tiles
+__device__ __forceinline__ void stage_weight(const float* __restrict__ w, int chunks,
+                                             unsigned char* hi, unsigned char* lo, int t) {
+  for (int u = t; u < chunks * TC_F; u += TC_THREADS) {
+    const int n = u & (TC_F - 1), j = u >> 6;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = __ldg(w + (size_t)(j * 8 + e) * TC_F + n);
+    uint4 h, l;
+    umma::split_bf16x2(x[0], x[1], h.x, l.x);
+    umma::split_bf16x2(x[2], x[3], h.y, l.y);
+    umma::split_bf16x2(x[4], x[5], h.z, l.z);
+    umma::split_bf16x2(x[6], x[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + j * TC_LBO_B + n * 16) = h;
+    *reinterpret_cast<uint4*>(lo + j * TC_LBO_B + n * 16) = l;
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ feats,
+                     const float* __restrict__ nfeats, const int32_t* __restrict__ pair_c,
+                     const int32_t* __restrict__ pair_n, const int32_t* __restrict__ num_pairs,
+                     int capacity, const float* __restrict__ w1, const float* __restrict__ b1,
+                     const float* __restrict__ w2, const float* __restrict__ b2,
+                     float* __restrict__ pooled) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int P = min(__ldg(num_pairs), capacity);
+  const int num_tiles = (P + TC_TILE - 1) / TC_TILE;
+  if ((int)blockIdx.x >= num_tiles) return;  // uniform per CTA: before any allocation
+
+  unsigned char* a_hi = smem + TC_OFF_A;
+  unsigned char* a_lo = a_hi + TC_CH1 * TC_LBO_A;
+  unsigned char* h_hi = smem + TC_OFF_A;                       // aliases A (dead after FC1)
+  unsigned char* h_lo = h_hi + TC_CH2 * TC_LBO_A;
+  float* h2 = reinterpret_cast<float*>(smem + TC_OFF_A);        // aliases h1 (dead after FC2)
+  int* c_idx = reinterpret_cast<int*>(smem + TC_OFF_IDX);
+  int* n_idx = c_idx + TC_TILE;
+  float* bias1 = reinterpret_cast<float*>(smem + TC_OFF_BIAS);
+  float* bias2 = bias1 + TC_F;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 128);
+  if (t == 0) {
+    umma::mbar_init(bar, 1);
+    umma::fence_barrier_init();
+  }
+  stage_weight(w1, TC_CH1, smem + TC_OFF_B1H, smem + TC_OFF_B1L, t);
+  stage_weight(w2, TC_CH2, smem + TC_OFF_B2H, smem + TC_OFF_B2L, t);
+  if (t < TC_F) {
+    bias1[t] = __ldg(b1 + t);
+    bias2[t] = __ldg(b2 + t);
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + TC_F;
+  const uint32_t idesc = umma::idesc_bf16_f32(TC_TILE, TC_F);
+  const uint32_t sa_hi = umma::smem_u32(a_hi), sa_lo = umma::smem_u32(a_lo);
+  const uint32_t sh_hi = umma::smem_u32(h_hi), sh_lo = umma::smem_u32(h_lo);
+  const uint32_t sb1h = umma::smem_u32(smem + TC_OFF_B1H), sb1l = umma::smem_u32(smem + TC_OFF_B1L);
+  const uint32_t sb2h = umma::smem_u32(smem + TC_OFF_B2H), sb2l = umma::smem_u32(smem + TC_OFF_B2L);
+
+  // epilogue mapping: TMEM lane quadrant = warp % 4, column half = warp / 4
+  const int erow = (warp & 3) * 32 + lane;
+  const int ecol0 = (warp >> 2) * 32;
+  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int p0 = tile * TC_TILE;
+
+    // ---- 0. pair indices of the tile ---------------------------------------------
+    if (t < TC_TILE) {
+      const int p = p0 + t;
+      c_idx[t] = p < P ? __ldg(pair_c + p) : -1;
+    } else {
+      const int p = p0 + t - TC_TILE;
+      n_idx[t - TC_TILE] = p < P ? __ldg(pair_n + p) : -1;
+    }
+    __syncthreads();
+
+    // ---- 1. fill A (hi / lo) -------------------------------------------------------
+    // warp task = 8 rows x one 128-byte part (pw | c | n); lane = (row % 8) * 4 + piece
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+      const int task = it * 8 + warp;        // 0..47
+      const int part = task >> 4;            // 0 pw, 1 c, 2 n   (warp uniform)
+      const int row = (task & 15) * 8 + (lane >> 2);
+      const int q = lane & 3;
+      const int c = c_idx[row];
+      const float* src = nullptr;
+      if (c >= 0) {
+        if (part == 0) src = pw + (size_t)(p0 + row) * TC_W;
+        else if (part == 1) src = feats + (size_t)c * TC_R;
+        else {
+          const int n = n_idx[row];
+          if (n != c) src = nfeats + (size_t)n * TC_R;   // self pair: zeros (network.py:372-374)
+        }
+      }
+      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      if (src != nullptr) {
+        v0 = ldg4(src + q * 8);
+        v1 = ldg4(src + q * 8 + 4);
+      }
+      uint4 h, l;
+      umma::split_bf16x2(v0.x, v0.y, h.x, l.x);
+      umma::split_bf16x2(v0.z, v0.w, h.y, l.y);
+      umma::split_bf16x2(v1.x, v1.y, h.z, l.z);
+      umma::split_bf16x2(v1.z, v1.w, h.w, l.w);
+      const uint32_t off = (uint32_t)(part * 4 + q) * TC_LBO_A + (uint32_t)row * 16;
+      *reinterpret_cast<uint4*>(a_hi + off) = h;
+      *reinterpret_cast<uint4*>(a_lo + off) = l;
+    }
+    umma::fence_smem_to_async();
+    umma::tc_fence_before();
+    __syncthreads();
+
+    // ---- 2. FC1 on the tensor core -------------------------------------------------
+    if (t == 0) {
+      umma::tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < TC_K1 / 16; ++ks) {
+        const uint64_t dah = umma::smem_desc(sa_hi + ks * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+        const uint64_t dal = umma::smem_desc(sa_lo + ks * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+        const uint64_t dbh = umma::smem_desc(sb1h + ks * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
+        const uint64_t dbl = umma::smem_desc(sb1l + ks * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
+        umma::mma_bf16_ss(tmem_d1, dal, dbh, idesc, ks > 0);
+        umma::mma_bf16_ss(tmem_d1, dah, dbl, idesc, 1);
+        umma::mma_bf16_ss(tmem_d1, dah, dbh, idesc, 1);
+      }
+      umma::mma_commit(bar);
+    }
+    umma::mbar_wait(bar, 0);
+    umma::tc_fence_after();
+
+    // ---- 3. epilogue 1: h1 = relu(acc + b1) -> bf16 hi / lo operand tile -----------
+#pragma unroll
+    for (int cc = 0; cc < 32; cc += 16) {
+      float v[16];
+      umma::tmem_ld16(tmem_d1 + tlane + ecol0 + cc, v);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int col = ecol0 + cc + g * 8;
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = fmaxf(v[g * 8 + e] + bias1[col + e], 0.f);
+        uint4 h, l;
+        umma::split_bf16x2(x[0], x[1], h.x, l.x);
+        umma::split_bf16x2(x[2], x[3], h.y, l.y);
+        umma::split_bf16x2(x[4], x[5], h.z, l.z);
+        umma::split_bf16x2(x[6], x[7], h.w, l.w);
+        const uint32_t off = (uint32_t)(col >> 3) * TC_LBO_A + (uint32_t)erow * 16;
+        *reinterpret_cast<uint4*>(h_hi + off) = h;
+        *reinterpret_cast<uint4*>(h_lo + off) = l;
+      }
+    }
+    umma::fence_smem_to_async();
+    umma::tc_fence_before();
+    __syncthreads();
+
+    // ---- 4. FC2 ---------------------------------------------------------------------
+    if (t == 0) {
+      umma::tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < TC_F / 16; ++ks) {
+        const uint64_t dah = umma::smem_desc(sh_hi + ks * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+        const uint64_t dal = umma::smem_desc(sh_lo + ks * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
+        const uint64_t dbh = umma::smem_desc(sb2h + ks * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
+        const uint64_t dbl = umma::smem_desc(sb2l + ks * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
+        umma::mma_bf16_ss(tmem_d2, dal, dbh, idesc, ks > 0);
+        umma::mma_bf16_ss(tmem_d2, dah, dbl, idesc, 1);
+        umma::mma_bf16_ss(tmem_d2, dah, dbh, idesc, 1);
+      }
+      umma::mma_commit(bar);
+    }
+    umma::mbar_wait(bar, 1);
+    umma::tc_fence_after();
+
+    // ---- 5. epilogue 2: h2 = relu(acc + b2) -> fp32 tile ---------------------------
+#pragma unroll
+    for (int cc = 0; cc < 32; cc += 16) {
+      float v[16];
+      umma::tmem_ld16(tmem_d2 + tlane + ecol0 + cc, v);
+      umma::tmem_ld_wait();
+      float* dst = h2 + erow * TC_LDH2 + ecol0 + cc;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = ecol0 + cc + g * 4;
+        *reinterpret_cast<float4*>(dst + g * 4) =
+            make_float4(fmaxf(v[g * 4 + 0] + bias2[col + 0], 0.f), fmaxf(v[g * 4 + 1] + bias2[col + 1], 0.f),
+                        fmaxf(v[g * 4 + 2] + bias2[col + 2], 0.f), fmaxf(v[g * 4 + 3] + bias2[col + 3], 0.f));
+      }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+
+    // ---- 6. segmented max over the tile's rows ---------------------------------------
+    {
+      const int j = t & 63;            // column
+      const int r0 = (t >> 6) * 32;    // 32-row slice
+      int cur_c = -1;
+      float cur = 0.f;
+      for (int r = r0; r < r0 + 32; ++r) {
+        const int c = c_idx[r];
+        if (c < 0) break;  // rows past P
+        if (c != cur_c) {
+          if (cur_c >= 0)
+            atomicMax(reinterpret_cast<int*>(pooled + (size_t)cur_c * TC_F + j), __float_as_int(cur));
+          cur_c = c;
+          cur = 0.f;
+        }
+        cur = fmaxf(cur, h2[r * TC_LDH2 + j]);
+      }
+      if (cur_c >= 0)
+        atomicMax(reinterpret_cast<int*>(pooled + (size_t)cur_c * TC_F + j), __float_as_int(cur));
+    }
+    __syncthreads();  // tile buffers free for the next fill
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+}
+
+}  // namespace gn
+
+extern "C" int gn_block_pair_fwd(const float* pw, int w, const float* feats,
+                                 const float* nfeats, int r, const int32_t* pair_c,
+                                 const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                                 const float* w1, const float* b1, const float* w2,
+                                 const float* b2, int f, float* pooled, gn_stream_t stream) {
+  GN_REQUIRE(capacity >= 0, "gn_block_pair_fwd: negative capacity");
+  if (w != gn::TC_W || r != gn::TC_R || f != gn::TC_F) {
+    gn::set_error("gn_block_pair_fwd: fused kernel is built for w=%d r=%d f=%d (got %d, %d, %d)",
+                  gn::TC_W, gn::TC_R, gn::TC_F, w, r, f);
+    return GN_ERR_UNSUPPORTED;
+  }
+  if (capacity == 0) return GN_OK;
+  GN_REQUIRE(pw && feats && nfeats && pair_c && pair_n && num_pairs && w1 && b1 && w2 && b2 &&
+                 pooled,
+             "gn_block_pair_fwd: null pointer");
+  GN_REQUIRE((((uintptr_t)pw | (uintptr_t)feats | (uintptr_t)nfeats) & 15) == 0,
+             "gn_block_pair_fwd: pointers must be 16-byte aligned");
+  cudaError_t e = cudaFuncSetAttribute(gn::block_pair_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn::TC_SMEM);
+  if (e != cudaSuccess) {
+    gn::set_error("gn_block_pair_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
+  int grid = gn::ceil_div(capacity, gn::TC_TILE);
+  const int cap = 2 * gn::sm_count();
+  if (grid > cap) grid = cap;
+  gn::block_pair_tc_kernel<<<grid, gn::TC_THREADS, gn::TC_SMEM, (cudaStream_t)stream>>>(
+      pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2, pooled);
+  GN_CHECK_LAUNCH("gn_block_pair_fwd");
+  return GN_OK;
+}

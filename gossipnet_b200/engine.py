@@ -71,6 +71,7 @@ class GnetEngine(object):
         self._ws = {}
         self.keep_block_feats = False
         self.use_fused = True
+        self.use_tensor_cores = True   # False: fp32 FFMA variants of the fused kernels
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name, shape, dtype=torch.float32):
@@ -161,7 +162,8 @@ class GnetEngine(object):
             pooled.zero_()
             ops.block_pair_fwd(pw, red, nred, pair_c, pair_n, num_pairs, cap,
                                self.p[s + 'pw_fc1/weights'], self.p[s + 'pw_fc1/biases'],
-                               self.p[s + 'pw_fc2/weights'], self.p[s + 'pw_fc2/biases'], pooled)
+                               self.p[s + 'pw_fc2/weights'], self.p[s + 'pw_fc2/biases'], pooled,
+                               ffma=not self.use_tensor_cores)
         else:
             x = ops.block_gather_concat(pw, red, nred, pair_c, pair_n, num_pairs, cap,
                                         self._buf('pairx', (cap, pw.shape[1] + 2 * g['reduced_dim'])))

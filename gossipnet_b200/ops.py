@@ -157,10 +157,11 @@ def segment_max(x, row_ptr, num_dets, out=None):
 
 
 def block_pair_fwd(pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2,
-                   pooled):
-    """pooled[num_dets,f] must be zero-filled; it is max-accumulated in place."""
+                   pooled, ffma=False):
+    """pooled[num_dets,f] must be zero-filled; it is max-accumulated in place.
+    ffma=True runs the fp32 CUDA-core variant instead of the tensor-core kernel."""
     f32 = torch.float32
-    _lib.call('gn_block_pair_fwd', _chk(pw, f32, 'pw'), pw.shape[1], _chk(feats, f32, 'feats'),
+    _lib.call('gn_block_pair_fwd_ffma' if ffma else 'gn_block_pair_fwd', _chk(pw, f32, 'pw'), pw.shape[1], _chk(feats, f32, 'feats'),
               _chk(nfeats, f32, 'nfeats'), feats.shape[1], _chk(pair_c, torch.int32, 'pair_c'),
               _chk(pair_n, torch.int32, 'pair_n'), _chk(num_pairs, torch.int32, 'num_pairs'),
               int(capacity), _chk(w1, f32, 'w1'), _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2'),

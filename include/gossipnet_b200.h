@@ -127,7 +127,9 @@ int gn_fc_fwd(const float* x, int ldx, const float* w, const float* b,
  *                           (tf.segment_max, :387-388)
  * Fused hot path:
  *   gn_block_pair_fwd: gather + concat + pw_fc1 + pw_fc2 (+ReLU) + segment max
- *                      in one kernel; pooled[num_dets, f] must be zero-filled
+ *                      in one kernel, the two FCs on the tensor cores (tcgen05,
+ *                      bf16 hi/lo split operands, fp32 accumulation in TMEM);
+ *                      pooled[num_dets, f] must be zero-filled
  *                      by the caller (post-ReLU values are >= 0 and every row
  *                      has its self pair, so an integer atomicMax is exact). */
 int gn_block_gather_concat(const float* pw, int w, const float* feats,
@@ -141,6 +143,13 @@ int gn_block_pair_fwd(const float* pw, int w, const float* feats,
                       const int32_t* pair_n, const int32_t* num_pairs, int capacity,
                       const float* w1, const float* b1, const float* w2,
                       const float* b2, int f, float* pooled, gn_stream_t stream);
+/* Same contract, evaluated with fp32 FFMA on the CUDA cores (no tensor cores):
+ * the in-library cross-check of gn_block_pair_fwd's bf16x3 tensor-core product. */
+int gn_block_pair_fwd_ffma(const float* pw, int w, const float* feats,
+                           const float* nfeats, int r, const int32_t* pair_c,
+                           const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                           const float* w1, const float* b1, const float* w2,
+                           const float* b2, int f, float* pooled, gn_stream_t stream);
 
 /* ---- A9: DetectionMatching ---------------------------------------------------
  * Replaces the DetectionMatching TF op (nms_net/matching_module/det_matching.cc:
