@@ -26,9 +26,13 @@ SIGNATURES = {
                          c_void_p, c_void_p, c_void_p, c_void_p],
     'gn_pair_geometry': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_int, c_int, c_float, c_void_p, c_void_p],
+    'gn_pwfeat_prep_bytes': [],
     'gn_pwfeat_mlp_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
-                          c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
+                          c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    'gn_pwfeat_mlp_fwd_ffma': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p],
     'gn_fc_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int,
                   c_int, c_void_p, c_int, c_int, c_void_p],
     'gn_block_gather_concat': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
@@ -48,7 +52,7 @@ SIGNATURES = {
                     c_void_p],
     'gn_selftest_umma': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
 }
-_RESTYPES = {'gn_last_error': ctypes.c_char_p}
+_RESTYPES = {'gn_last_error': ctypes.c_char_p, 'gn_pwfeat_prep_bytes': ctypes.c_int64}
 
 _lib = None
 # number of C-ABI compute calls made so far (each is one kernel launch of this

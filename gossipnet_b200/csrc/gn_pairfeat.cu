@@ -1,6 +1,8 @@
 // Pair features: raw geometry (A4) and the fused geometry + 3-layer MLP (A5).
 //
-// Fused kernel (CUDA-core FFMA engine): a persistent CTA takes tiles of 64 pairs;
+// Fused CUDA-core (FFMA) variant, kept as gn_pwfeat_mlp_fwd_ffma: the fp32
+// cross-check of the tensor-core kernel in gn_pairfeat_tc.cu.  A persistent CTA
+// takes tiles of 64 pairs;
 // the geometry of the tile is computed in registers, layer 1 (K = 9 effective
 // inputs: with one-hot class scores the 2C+7 wide first layer degenerates to two
 // weight-row gathers scaled by the scores plus 7 geometry rows) is evaluated
@@ -283,33 +285,33 @@ extern "C" int gn_pair_geometry(const float* dets, const float* scores, const in
   return GN_OK;
 }
 
-extern "C" int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const int32_t* classes,
+extern "C" int gn_pwfeat_mlp_fwd_ffma(const float* dets, const float* scores, const int32_t* classes,
                                  const int32_t* pair_c, const int32_t* pair_n,
                                  const float* pair_iou, const int32_t* num_pairs, int capacity,
                                  int num_classes, float multiplier, const float* w1,
                                  const float* b1, const float* w2, const float* b2,
                                  const float* w3, const float* b3, int hidden, int out_dim,
                                  float* pw_out, gn_stream_t stream) {
-  GN_REQUIRE(capacity >= 0 && num_classes >= 1, "gn_pwfeat_mlp_fwd: bad sizes");
+  GN_REQUIRE(capacity >= 0 && num_classes >= 1, "gn_pwfeat_mlp_fwd_ffma: bad sizes");
   if (hidden != gn::PW_H || out_dim != gn::PW_O) {
-    gn::set_error("gn_pwfeat_mlp_fwd: fused kernel is built for hidden=%d out=%d (got %d, %d)",
+    gn::set_error("gn_pwfeat_mlp_fwd_ffma: fused kernel is built for hidden=%d out=%d (got %d, %d)",
                   gn::PW_H, gn::PW_O, hidden, out_dim);
     return GN_ERR_UNSUPPORTED;
   }
   if (capacity == 0) return GN_OK;
   GN_REQUIRE(dets && scores && pair_c && pair_n && pair_iou && num_pairs && pw_out && w1 && b1 &&
                  w2 && b2 && w3 && b3,
-             "gn_pwfeat_mlp_fwd: null pointer");
-  GN_REQUIRE(num_classes == 1 || classes != nullptr, "gn_pwfeat_mlp_fwd: classes required");
+             "gn_pwfeat_mlp_fwd_ffma: null pointer");
+  GN_REQUIRE(num_classes == 1 || classes != nullptr, "gn_pwfeat_mlp_fwd_ffma: classes required");
   GN_REQUIRE((((uintptr_t)w1 | (uintptr_t)b1 | (uintptr_t)w2 | (uintptr_t)b2 | (uintptr_t)w3 |
                (uintptr_t)b3 | (uintptr_t)pw_out | (uintptr_t)dets) & 15) == 0,
-             "gn_pwfeat_mlp_fwd: pointers must be 16-byte aligned");
+             "gn_pwfeat_mlp_fwd_ffma: pointers must be 16-byte aligned");
   static_assert(sizeof(gn::PwSmem) <= 227 * 1024, "pair MLP tile exceeds shared memory");
   const int smem = (int)sizeof(gn::PwSmem);
   cudaError_t e = cudaFuncSetAttribute(gn::pwfeat_mlp_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) {
-    gn::set_error("gn_pwfeat_mlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    gn::set_error("gn_pwfeat_mlp_fwd_ffma: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return GN_ERR_CUDA;
   }
   int grid = gn::ceil_div(capacity, gn::PW_TILE);
@@ -318,6 +320,6 @@ extern "C" int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const i
   gn::pwfeat_mlp_kernel<<<grid, gn::PW_THREADS, smem, (cudaStream_t)stream>>>(
       dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,
       multiplier, w1, b1, w2, b2, w3, b3, pw_out);
-  GN_CHECK_LAUNCH("gn_pwfeat_mlp_fwd");
+  GN_CHECK_LAUNCH("gn_pwfeat_mlp_fwd_ffma");
   return GN_OK;
 }

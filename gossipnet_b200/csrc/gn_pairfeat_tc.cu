@@ -1,0 +1,442 @@
+// Pair features on the tensor cores: geometry (A4) + the 3-layer pair-feature
+// MLP (A5) width -> 256 -> 256 -> 32 with ReLU after every layer, fused.
+//
+// Tile = 128 pairs (the M of one tcgen05.mma), one persistent CTA per SM.
+//   geometry : one thread per pair computes the 9 hand-crafted features in fp32
+//              (pair_geometry, same rounding as the reference) and writes a K=16
+//              bf16 hi/lo operand row;
+//   layer 1  : [128 x 16] x [16 x 256]  (1 k-step x 3 UMMAs, N = 256) -> TMEM [0,256)
+//              single class: K rows = [c_score, n_score, 7 geometry]; multi class:
+//              the one-hot score block degenerates to two weight-row gathers that
+//              the epilogue adds in fp32 (K rows = 7 geometry only);
+//   layer 2  : [128 x 256] x [256 x 256] (16 k-steps x 3 UMMAs) -> TMEM [256,512).
+//              W2 (256 KB as bf16 hi+lo) does not fit next to the activations, so it
+//              is streamed per k-step (16 KB) from a pre-split operand image in
+//              global memory (L2 resident) through a 4-stage cp.async.bulk ring
+//              (mbarrier complete_tx / tcgen05.commit) that runs ahead of the UMMAs
+//              across the epilogue phases;
+//   layer 3  : [128 x 256] x [256 x 32] -> TMEM [0,32) (layer-1 columns are dead).
+// The activation operand tile holds 128 of the 256 K columns at a time, so each of
+// layers 2 and 3 runs as two (epilogue-half, 8 k-step) rounds.  Only pw_out[P,32]
+// goes back to HBM; the [P,256] activations never leave the SM.
+// bf16x3: every fp32 operand is split into bf16 hi + lo and each product is
+// a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation (gn_umma.cuh).
+#include "gn_pairfeat.cuh"
+#include "gn_umma.cuh"
+
+namespace gn {
+
+constexpr int PT_TILE = 128;
+constexpr int PT_THREADS = 256;
+constexpr int PT_H = 256, PT_O = 32;
+constexpr int PT_RING = 4;
+constexpr uint32_t PT_SBO = 128;
+constexpr uint32_t PT_LBO_A = PT_TILE * 16;      // activation / A1 chunk pitch (2048)
+constexpr uint32_t PT_LBO_W = PT_H * 16;         // 256-row weight chunk pitch (4096)
+constexpr uint32_t PT_LBO_W3 = PT_O * 16;        // 32-row weight chunk pitch (512)
+constexpr uint32_t PT_STAGE = 2 * 2 * PT_LBO_W;  // one W2 k-step: (hi, lo) x 2 chunks = 16 KB
+
+// prepared weight image (global workspace), bytes
+constexpr uint32_t PT_IMG_W2 = 0;                            // 16 k-steps x 16 KB
+constexpr uint32_t PT_IMG_B1 = PT_IMG_W2 + 16 * PT_STAGE;    // hi 8 KB, lo 8 KB
+constexpr uint32_t PT_IMG_B3 = PT_IMG_B1 + 2 * 2 * PT_LBO_W; // hi 16 KB, lo 16 KB
+constexpr uint32_t PT_IMG_BYTES = PT_IMG_B3 + 2 * 32 * PT_LBO_W3;
+
+// shared memory map
+constexpr uint32_t PS_RING = 0;                                   // 4 x 16 KB
+constexpr uint32_t PS_H = PS_RING + PT_RING * PT_STAGE;           // hi 32 KB + lo 32 KB
+constexpr uint32_t PS_B1 = PS_H + 2 * 16 * PT_LBO_A;              // 16 KB
+constexpr uint32_t PS_B3 = PS_B1 + 2 * 2 * PT_LBO_W;              // 32 KB
+constexpr uint32_t PS_A1 = PS_B3 + 2 * 32 * PT_LBO_W3;            // hi 4 KB + lo 4 KB
+constexpr uint32_t PS_BIAS = PS_A1 + 2 * 2 * PT_LBO_A;            // b1[256] b2[256] b3[32]
+constexpr uint32_t PS_ROW = PS_BIAS + (2 * PT_H + PT_O) * 4;      // sc[128] sn[128] rc[128] rn[128]
+constexpr uint32_t PS_BAR = PS_ROW + 4 * PT_TILE * 4;             // full[4] empty[4] done
+constexpr uint32_t PS_BYTES = PS_BAR + 16 * 8;
+static_assert(PS_BYTES <= 227 * 1024, "pair MLP tile exceeds shared memory");
+
+// ---------------------------------------------------------------------------------
+// weight preparation: fp32 [in,out] -> bf16 hi/lo K-major operand images
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void put_split(unsigned char* hi_base, unsigned char* lo_base,
+                                          uint32_t off, int e, float x) {
+  __nv_bfloat16 h, l;
+  umma::split_bf16(x, h, l);
+  reinterpret_cast<__nv_bfloat16*>(hi_base + off)[e] = h;
+  reinterpret_cast<__nv_bfloat16*>(lo_base + off)[e] = l;
+}
+
+__global__ void pwfeat_prepare_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
+                                      const float* __restrict__ w3, int num_classes,
+                                      unsigned char* __restrict__ img) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  // W2: k-step ks, chunk c (8 k), row n
+  for (int i = tid; i < PT_H * PT_H; i += nth) {
+    const int k = i / PT_H, n = i - k * PT_H;
+    const int ks = k >> 4, c = (k >> 3) & 1, e = k & 7;
+    unsigned char* st = img + PT_IMG_W2 + ks * PT_STAGE;
+    put_split(st, st + 2 * PT_LBO_W, c * PT_LBO_W + n * 16, e, __ldg(w2 + i));
+  }
+  // B1: 16 K rows selected from W1 (zero padded)
+  const bool multi = num_classes > 1;
+  const int gbase = multi ? 2 * num_classes : 2;
+  for (int i = tid; i < 16 * PT_H; i += nth) {
+    const int k = i / PT_H, n = i - k * PT_H;
+    int src_row;
+    if (multi) src_row = k < 7 ? gbase + k : -1;      // geometry only
+    else src_row = k < 9 ? k : -1;                     // c_score, n_score, geometry
+    const float x = src_row >= 0 ? __ldg(w1 + (size_t)src_row * PT_H + n) : 0.f;
+    unsigned char* st = img + PT_IMG_B1;
+    put_split(st, st + 2 * PT_LBO_W, (k >> 3) * PT_LBO_W + n * 16, k & 7, x);
+  }
+  // B3: W3^T, 32 chunks x 32 rows
+  for (int i = tid; i < PT_H * PT_O; i += nth) {
+    const int k = i / PT_O, n = i - k * PT_O;
+    unsigned char* st = img + PT_IMG_B3;
+    put_split(st, st + 32 * PT_LBO_W3, (k >> 3) * PT_LBO_W3 + n * 16, k & 7, __ldg(w3 + i));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
+}
+
+struct PtRing {
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t ring_smem;
+  const unsigned char* w2img;
+  uint32_t loads_issued, total_loads;
+
+  // issue every W2 k-step load up to (exclusive) index `upto`
+  __device__ __forceinline__ void fill(uint32_t upto) {
+    while (loads_issued < upto && loads_issued < total_loads) {
+      const uint32_t i = loads_issued, s = i % PT_RING;
+      if (i >= PT_RING) umma::mbar_wait(&empty[s], ((i / PT_RING) - 1) & 1);
+      bulk_g2s(ring_smem + s * PT_STAGE, w2img + (size_t)(i & 15) * PT_STAGE, PT_STAGE, &full[s]);
+      ++loads_issued;
+    }
+  }
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(PT_THREADS, 1)
+pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ scores,
+                 const int32_t* __restrict__ classes, const int32_t* __restrict__ pair_c,
+                 const int32_t* __restrict__ pair_n, const float* __restrict__ pair_iou,
+                 const int32_t* __restrict__ num_pairs, int capacity, int num_classes, float mult,
+                 const float* __restrict__ w1, const float* __restrict__ b1,
+                 const float* __restrict__ b2, const float* __restrict__ b3,
+                 const unsigned char* __restrict__ img, float* __restrict__ pw_out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int P = min(__ldg(num_pairs), capacity);
+  const int num_tiles = (P + PT_TILE - 1) / PT_TILE;
+  if ((int)blockIdx.x >= num_tiles) return;
+  const int my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  unsigned char* h_hi = smem + PS_H;
+  unsigned char* h_lo = h_hi + 16 * PT_LBO_A;
+  unsigned char* a1_hi = smem + PS_A1;
+  unsigned char* a1_lo = a1_hi + 2 * PT_LBO_A;
+  float* bias1 = reinterpret_cast<float*>(smem + PS_BIAS);
+  float* bias2 = bias1 + PT_H;
+  float* bias3 = bias2 + PT_H;
+  float* row_sc = reinterpret_cast<float*>(smem + PS_ROW);
+  float* row_sn = row_sc + PT_TILE;
+  int* row_rc = reinterpret_cast<int*>(row_sn + PT_TILE);
+  int* row_rn = row_rc + PT_TILE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PS_BAR);
+  uint64_t* empty = full + PT_RING;
+  uint64_t* done = empty + PT_RING;
+
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
+  if (t == 0) {
+    for (int s = 0; s < PT_RING; ++s) {
+      umma::mbar_init(&full[s], 1);
+      umma::mbar_init(&empty[s], 1);
+    }
+    umma::mbar_init(done, 1);
+    umma::fence_barrier_init();
+  }
+  // resident operands: B1, B3 (already split, copied verbatim), biases
+  for (int i = t; i < (int)(2 * 2 * PT_LBO_W) / 16; i += PT_THREADS)
+    reinterpret_cast<uint4*>(smem + PS_B1)[i] = __ldg(reinterpret_cast<const uint4*>(img + PT_IMG_B1) + i);
+  for (int i = t; i < (int)(2 * 32 * PT_LBO_W3) / 16; i += PT_THREADS)
+    reinterpret_cast<uint4*>(smem + PS_B3)[i] = __ldg(reinterpret_cast<const uint4*>(img + PT_IMG_B3) + i);
+  for (int i = t; i < PT_H; i += PT_THREADS) {
+    bias1[i] = __ldg(b1 + i);
+    bias2[i] = __ldg(b2 + i);
+  }
+  if (t < PT_O) bias3[t] = __ldg(b3 + t);
+  umma::fence_smem_to_async();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tm_l1 = tmem, tm_l2 = tmem + PT_H, tm_l3 = tmem;
+  const uint32_t idesc256 = umma::idesc_bf16_f32(PT_TILE, PT_H);
+  const uint32_t idesc32 = umma::idesc_bf16_f32(PT_TILE, PT_O);
+  const uint32_t s_ring = umma::smem_u32(smem + PS_RING);
+  const uint32_t s_hh = umma::smem_u32(h_hi), s_hl = umma::smem_u32(h_lo);
+  const uint32_t s_a1h = umma::smem_u32(a1_hi), s_a1l = umma::smem_u32(a1_lo);
+  const uint32_t s_b1h = umma::smem_u32(smem + PS_B1), s_b1l = s_b1h + 2 * PT_LBO_W;
+  const uint32_t s_b3h = umma::smem_u32(smem + PS_B3), s_b3l = s_b3h + 32 * PT_LBO_W3;
+
+  PtRing ring{full, empty, s_ring, img + PT_IMG_W2, 0u, (uint32_t)my_tiles * 16u};
+  uint32_t mma_k = 0;     // W2 k-steps consumed so far (thread 0 only)
+  uint32_t done_par = 0;  // parity of the next `done` completion (all threads)
+  if (t == 0) ring.fill(PT_RING - 1);
+
+  // epilogue mapping: TMEM lane quadrant = warp % 4; within a 128-column half the
+  // warp owns columns [64 * (warp / 4), +64)
+  const int erow = (warp & 3) * 32 + lane;
+  const int ecol = (warp >> 2) * 64;
+  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+  // one half-epilogue: relu(acc[:, half*128 + ecol ..+64] + bias (+ score rows)) -> h tile
+  auto epilogue_to_h = [&](uint32_t tm_src, const float* bias, int half, bool add_scores) {
+    const int col_base = half * 128 + ecol;
+#pragma unroll 1
+    for (int cc = 0; cc < 64; cc += 16) {
+      float v[16];
+      umma::tmem_ld16(tm_src + tlane + col_base + cc, v);
+      umma::tmem_ld_wait();
+      const int col = col_base + cc;
+      if (MULTI && add_scores) {
+        const float sc = row_sc[erow], sn = row_sn[erow];
+        const float* wc = w1 + (size_t)row_rc[erow] * PT_H + col;
+        const float* wn = w1 + (size_t)row_rn[erow] * PT_H + col;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float4 a = ldg4(wc + g * 4), b = ldg4(wn + g * 4);
+          v[g * 4 + 0] += sc * a.x + sn * b.x;
+          v[g * 4 + 1] += sc * a.y + sn * b.y;
+          v[g * 4 + 2] += sc * a.z + sn * b.z;
+          v[g * 4 + 3] += sc * a.w + sn * b.w;
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        float x[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = fmaxf(v[g * 8 + e] + bias[col + g * 8 + e], 0.f);
+        uint4 h, l;
+        umma::split_bf16x2(x[0], x[1], h.x, l.x);
+        umma::split_bf16x2(x[2], x[3], h.y, l.y);
+        umma::split_bf16x2(x[4], x[5], h.z, l.z);
+        umma::split_bf16x2(x[6], x[7], h.w, l.w);
+        // chunk index inside the 128-column half
+        const uint32_t off = (uint32_t)((ecol + cc + g * 8) >> 3) * PT_LBO_A + (uint32_t)erow * 16;
+        *reinterpret_cast<uint4*>(h_hi + off) = h;
+        *reinterpret_cast<uint4*>(h_lo + off) = l;
+      }
+    }
+    umma::fence_smem_to_async();
+    umma::tc_fence_before();
+    __syncthreads();
+  };
+  auto wait_done = [&]() {
+    umma::mbar_wait(done, done_par);
+    done_par ^= 1;
+    umma::tc_fence_after();
+  };
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int p0 = tile * PT_TILE;
+
+    // ---- geometry -> A1 (K = 16) ------------------------------------------------
+    if (t < PT_TILE) {
+      const int p = p0 + t;
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = 0.f;
+      float sc = 0.f, sn = 0.f;
+      int rc = 0, rn = 0;
+      if (p < P) {
+        const int c = __ldg(pair_c + p), n = __ldg(pair_n + p);
+        float g[7];
+        pair_geometry(ldg4(dets + (size_t)c * 4), ldg4(dets + (size_t)n * 4),
+                      __ldg(pair_iou + p), mult, g);
+        sc = __fmul_rn(__ldg(scores + c), mult);
+        sn = __fmul_rn(__ldg(scores + n), mult);
+        if (MULTI) {
+          rc = __ldg(classes + c) - 1;                 // one-based classes (network.py:413-419)
+          rn = num_classes + __ldg(classes + n) - 1;
+#pragma unroll
+          for (int i = 0; i < 7; ++i) f[i] = g[i];
+        } else {
+          f[0] = sc;
+          f[1] = sn;
+#pragma unroll
+          for (int i = 0; i < 7; ++i) f[2 + i] = g[i];
+        }
+      }
+      if (MULTI) {
+        row_sc[t] = sc; row_sn[t] = sn; row_rc[t] = rc; row_rn[t] = rn;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        uint4 h, l;
+        umma::split_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1], h.x, l.x);
+        umma::split_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3], h.y, l.y);
+        umma::split_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5], h.z, l.z);
+        umma::split_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7], h.w, l.w);
+        *reinterpret_cast<uint4*>(a1_hi + ch * PT_LBO_A + t * 16) = h;
+        *reinterpret_cast<uint4*>(a1_lo + ch * PT_LBO_A + t * 16) = l;
+      }
+    }
+    umma::fence_smem_to_async();
+    umma::tc_fence_before();
+    __syncthreads();
+
+    // ---- layer 1 ------------------------------------------------------------------
+    if (t == 0) {
+      umma::tc_fence_after();
+      const uint64_t dah = umma::smem_desc(s_a1h, PT_LBO_A, PT_SBO), dal = umma::smem_desc(s_a1l, PT_LBO_A, PT_SBO);
+      const uint64_t dbh = umma::smem_desc(s_b1h, PT_LBO_W, PT_SBO), dbl = umma::smem_desc(s_b1l, PT_LBO_W, PT_SBO);
+      umma::mma_bf16_ss(tm_l1, dal, dbh, idesc256, 0);
+      umma::mma_bf16_ss(tm_l1, dah, dbl, idesc256, 1);
+      umma::mma_bf16_ss(tm_l1, dah, dbh, idesc256, 1);
+      umma::mma_commit(done);
+    }
+    wait_done();
+
+    // ---- layer 2, two K halves ------------------------------------------------------
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      epilogue_to_h(tm_l1, bias1, half, true);
+      if (t == 0) {
+        umma::tc_fence_after();
+#pragma unroll 1
+        for (int ksl = 0; ksl < 8; ++ksl) {
+          const uint32_t g = mma_k++, s = g % PT_RING;
+          umma::mbar_wait(&full[s], (g / PT_RING) & 1);
+          umma::tc_fence_after();
+          const uint32_t sb = s_ring + s * PT_STAGE;
+          const uint64_t dah = umma::smem_desc(s_hh + ksl * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
+          const uint64_t dal = umma::smem_desc(s_hl + ksl * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
+          const uint64_t dbh = umma::smem_desc(sb, PT_LBO_W, PT_SBO);
+          const uint64_t dbl = umma::smem_desc(sb + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
+          const uint32_t acc = (half | ksl) != 0;
+          umma::mma_bf16_ss(tm_l2, dal, dbh, idesc256, acc);
+          umma::mma_bf16_ss(tm_l2, dah, dbl, idesc256, 1);
+          umma::mma_bf16_ss(tm_l2, dah, dbh, idesc256, 1);
+          umma::mma_commit(&empty[s]);
+          ring.fill(g + PT_RING);   // keep RING-1 k-steps in flight behind the running one
+        }
+        umma::mma_commit(done);
+      }
+      wait_done();
+    }
+
+    // ---- layer 3, two K halves ------------------------------------------------------
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      epilogue_to_h(tm_l2, bias2, half, false);
+      if (t == 0) {
+        umma::tc_fence_after();
+#pragma unroll
+        for (int ksl = 0; ksl < 8; ++ksl) {
+          const int kc = (half * 8 + ksl) * 2;   // chunk index into W3^T
+          const uint64_t dah = umma::smem_desc(s_hh + ksl * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
+          const uint64_t dal = umma::smem_desc(s_hl + ksl * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
+          const uint64_t dbh = umma::smem_desc(s_b3h + kc * PT_LBO_W3, PT_LBO_W3, PT_SBO);
+          const uint64_t dbl = umma::smem_desc(s_b3l + kc * PT_LBO_W3, PT_LBO_W3, PT_SBO);
+          const uint32_t acc = (half | ksl) != 0;
+          umma::mma_bf16_ss(tm_l3, dal, dbh, idesc32, acc);
+          umma::mma_bf16_ss(tm_l3, dah, dbl, idesc32, 1);
+          umma::mma_bf16_ss(tm_l3, dah, dbh, idesc32, 1);
+        }
+        umma::mma_commit(done);
+      }
+      wait_done();
+    }
+
+    // ---- output: relu(acc + b3) -> pw_out[p, 32] ---------------------------------------
+    if (warp < 4) {
+      const int p = p0 + erow;
+#pragma unroll
+      for (int cc = 0; cc < PT_O; cc += 16) {
+        float v[16];
+        umma::tmem_ld16(tm_l3 + tlane + cc, v);
+        umma::tmem_ld_wait();
+        if (p < P) {
+          float* dst = pw_out + (size_t)p * PT_O + cc;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(dst + g * 4) = make_float4(
+                fmaxf(v[g * 4 + 0] + bias3[cc + g * 4 + 0], 0.f), fmaxf(v[g * 4 + 1] + bias3[cc + g * 4 + 1], 0.f),
+                fmaxf(v[g * 4 + 2] + bias3[cc + g * 4 + 2], 0.f), fmaxf(v[g * 4 + 3] + bias3[cc + g * 4 + 3], 0.f));
+        }
+      }
+    }
+    umma::tc_fence_before();
+    __syncthreads();   // TMEM [0,32) and the row tables are free for the next tile
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace gn
+
+extern "C" int64_t gn_pwfeat_prep_bytes(void) { return (int64_t)gn::PT_IMG_BYTES; }
+
+extern "C" int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const int32_t* classes,
+                                 const int32_t* pair_c, const int32_t* pair_n,
+                                 const float* pair_iou, const int32_t* num_pairs, int capacity,
+                                 int num_classes, float multiplier, const float* w1,
+                                 const float* b1, const float* w2, const float* b2,
+                                 const float* w3, const float* b3, int hidden, int out_dim,
+                                 void* wprep, float* pw_out, gn_stream_t stream) {
+  GN_REQUIRE(capacity >= 0 && num_classes >= 1, "gn_pwfeat_mlp_fwd: bad sizes");
+  if (hidden != gn::PT_H || out_dim != gn::PT_O) {
+    gn::set_error("gn_pwfeat_mlp_fwd: fused kernel is built for hidden=%d out=%d (got %d, %d)",
+                  gn::PT_H, gn::PT_O, hidden, out_dim);
+    return GN_ERR_UNSUPPORTED;
+  }
+  if (capacity == 0) return GN_OK;
+  GN_REQUIRE(dets && scores && pair_c && pair_n && pair_iou && num_pairs && pw_out && w1 && b1 &&
+                 w2 && b2 && w3 && b3 && wprep,
+             "gn_pwfeat_mlp_fwd: null pointer");
+  GN_REQUIRE(num_classes == 1 || classes != nullptr, "gn_pwfeat_mlp_fwd: classes required");
+  GN_REQUIRE((((uintptr_t)w1 | (uintptr_t)pw_out | (uintptr_t)dets | (uintptr_t)wprep) & 15) == 0,
+             "gn_pwfeat_mlp_fwd: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  unsigned char* img = static_cast<unsigned char*>(wprep);
+  gn::pwfeat_prepare_kernel<<<64, 256, 0, s>>>(w1, w2, w3, num_classes, img);
+  GN_CHECK_LAUNCH("gn_pwfeat_mlp_fwd(prepare)");
+  int grid = gn::ceil_div(capacity, gn::PT_TILE);
+  const int sms = gn::sm_count();
+  if (grid > sms) grid = sms;
+  cudaError_t e;
+  if (num_classes > 1) {
+    e = cudaFuncSetAttribute(gn::pwfeat_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gn::PS_BYTES);
+    if (e == cudaSuccess)
+      gn::pwfeat_tc_kernel<true><<<grid, gn::PT_THREADS, gn::PS_BYTES, s>>>(
+          dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,
+          multiplier, w1, b1, b2, b3, img, pw_out);
+  } else {
+    e = cudaFuncSetAttribute(gn::pwfeat_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gn::PS_BYTES);
+    if (e == cudaSuccess)
+      gn::pwfeat_tc_kernel<false><<<grid, gn::PT_THREADS, gn::PS_BYTES, s>>>(
+          dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,
+          multiplier, w1, b1, b2, b3, img, pw_out);
+  }
+  if (e != cudaSuccess) {
+    gn::set_error("gn_pwfeat_mlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
+  GN_CHECK_LAUNCH("gn_pwfeat_mlp_fwd");
+  return GN_OK;
+}

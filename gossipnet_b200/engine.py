@@ -134,8 +134,12 @@ class GnetEngine(object):
             s = 'gnet/pw_feats/fc%d/'
             out = self._buf('pw', (cap, 32))
             w = [self.p[(s % i) + k] for i in (1, 2, 3) for k in ('weights', 'biases')]
+            if 'wprep' not in self._ws:
+                self._ws['wprep'] = torch.empty(int(ops._lib.load().gn_pwfeat_prep_bytes()),
+                                                dtype=torch.uint8, device=self.device)
             return ops.pwfeat_mlp_fwd(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
-                                      self.num_classes, mult, *w, out=out)
+                                      self.num_classes, mult, *w, out=out,
+                                      ffma=not self.use_tensor_cores, wprep=self._ws['wprep'])
         raw = self._buf('pw_raw', (cap, self.raw_width))
         ops.pair_geometry(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
                           self.num_classes, mult, raw)

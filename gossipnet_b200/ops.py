@@ -98,19 +98,37 @@ def pair_geometry(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, ca
     return out
 
 
+_PREP = {}
+
+
 def pwfeat_mlp_fwd(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
-                   num_classes, multiplier, w1, b1, w2, b2, w3, b3, out=None):
+                   num_classes, multiplier, w1, b1, w2, b2, w3, b3, out=None, ffma=False,
+                   wprep=None):
+    """Fused geometry + 3-layer pair-feature MLP.  Tensor-core kernel by default
+    (needs the `wprep` weight-image workspace; one per device is kept here when
+    the caller does not pass its own); ffma=True runs the fp32 CUDA-core variant."""
     hidden, out_dim = w2.shape[1], w3.shape[1]
     if out is None:
         out = torch.empty((capacity, out_dim), dtype=torch.float32, device=dets.device)
     f32 = torch.float32
-    _lib.call('gn_pwfeat_mlp_fwd', _chk(dets, f32, 'dets'), _chk(scores, f32, 'scores'),
-              _chk(classes, torch.int32, 'classes', True), _chk(pair_c, torch.int32, 'pair_c'),
-              _chk(pair_n, torch.int32, 'pair_n'), _chk(pair_iou, f32, 'pair_iou'),
-              _chk(num_pairs, torch.int32, 'num_pairs'), int(capacity), int(num_classes),
-              float(multiplier), _chk(w1, f32, 'w1'), _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2'),
-              _chk(b2, f32, 'b2'), _chk(w3, f32, 'w3'), _chk(b3, f32, 'b3'), int(hidden),
-              int(out_dim), _chk(out, f32, 'pw_out'), _stream())
+    args = [_chk(dets, f32, 'dets'), _chk(scores, f32, 'scores'),
+            _chk(classes, torch.int32, 'classes', True), _chk(pair_c, torch.int32, 'pair_c'),
+            _chk(pair_n, torch.int32, 'pair_n'), _chk(pair_iou, f32, 'pair_iou'),
+            _chk(num_pairs, torch.int32, 'num_pairs'), int(capacity), int(num_classes),
+            float(multiplier), _chk(w1, f32, 'w1'), _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2'),
+            _chk(b2, f32, 'b2'), _chk(w3, f32, 'w3'), _chk(b3, f32, 'b3'), int(hidden),
+            int(out_dim)]
+    if ffma:
+        _lib.call('gn_pwfeat_mlp_fwd_ffma', *(args + [_chk(out, f32, 'pw_out'), _stream()]))
+        return out
+    if wprep is None:
+        key = dets.device.index
+        if key not in _PREP:
+            _PREP[key] = torch.empty(int(_lib.load().gn_pwfeat_prep_bytes()), dtype=torch.uint8,
+                                     device=dets.device)
+        wprep = _PREP[key]
+    _lib.call('gn_pwfeat_mlp_fwd', *(args + [_chk(wprep, torch.uint8, 'wprep'),
+                                             _chk(out, f32, 'pw_out'), _stream()]))
     return out
 
 

@@ -101,14 +101,29 @@ int gn_pair_geometry(const float* dets, const float* scores, const int32_t* clas
  * width -> hidden -> hidden -> out_dim, ReLU after every layer.
  * w1[width,hidden] b1[hidden] w2[hidden,hidden] b2 w3[hidden,out_dim] b3;
  * pw_out[capacity,out_dim].  hidden must be 256 and out_dim 32 (the fused
- * kernel's shape); other shapes go through gn_pair_geometry + gn_fc_fwd. */
+ * kernel's shape); other shapes go through gn_pair_geometry + gn_fc_fwd.
+ * The three layers run on the tensor cores (tcgen05, bf16 hi/lo split operands,
+ * fp32 accumulation in TMEM).  wprep: caller-owned device workspace of
+ * gn_pwfeat_prep_bytes() bytes (16-byte aligned) that receives the pre-split
+ * operand image of the weights; it is rewritten by every call.
+ * gn_pwfeat_mlp_fwd_ffma: same contract on the CUDA cores in fp32 (no wprep),
+ * the in-library cross-check. */
+int64_t gn_pwfeat_prep_bytes(void);
 int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const int32_t* classes,
                       const int32_t* pair_c, const int32_t* pair_n,
                       const float* pair_iou, const int32_t* num_pairs, int capacity,
                       int num_classes, float multiplier,
                       const float* w1, const float* b1, const float* w2,
                       const float* b2, const float* w3, const float* b3,
-                      int hidden, int out_dim, float* pw_out, gn_stream_t stream);
+                      int hidden, int out_dim, void* wprep, float* pw_out,
+                      gn_stream_t stream);
+int gn_pwfeat_mlp_fwd_ffma(const float* dets, const float* scores, const int32_t* classes,
+                           const int32_t* pair_c, const int32_t* pair_n,
+                           const float* pair_iou, const int32_t* num_pairs, int capacity,
+                           int num_classes, float multiplier,
+                           const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3,
+                           int hidden, int out_dim, float* pw_out, gn_stream_t stream);
 
 /* ---- generic fully connected layer -----------------------------------------
  * tf.contrib.layers.fully_connected as the reference uses it everywhere:
