@@ -93,7 +93,6 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   unsigned char* h_lo = h_hi + TC_CH2 * TC_LBO_A;
   float* h2 = reinterpret_cast<float*>(smem + TC_OFF_A);        // aliases h1 (dead after FC2)
   int* c_idx = reinterpret_cast<int*>(smem + TC_OFF_IDX);
-  int* n_idx = c_idx + TC_TILE;
   float* bias1 = reinterpret_cast<float*>(smem + TC_OFF_BIAS);
   float* bias2 = bias1 + TC_F;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
@@ -125,42 +124,60 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   const int ecol0 = (warp >> 2) * 32;
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
 
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int p0 = tile * TC_TILE;
-
-    // ---- 0. pair indices of the tile ---------------------------------------------
-    if (t < TC_TILE) {
-      const int p = p0 + t;
-      c_idx[t] = p < P ? __ldg(pair_c + p) : -1;
-    } else {
-      const int p = p0 + t - TC_TILE;
-      n_idx[t - TC_TILE] = p < P ? __ldg(pair_n + p) : -1;
-    }
-    __syncthreads();
-
-    // ---- 1. fill A (hi / lo) -------------------------------------------------------
-    // warp task = 8 rows x one 128-byte part (pw | c | n); lane = (row % 8) * 4 + piece
+  // The 96 inputs of a pair row are fetched one tile ahead into registers (6 units
+  // of 8 floats per thread), so the L2 gather latency of tile i+1 hides behind the
+  // UMMA / epilogue phases of tile i.  Warp task = 8 rows x one 128-byte part
+  // (pw | c | n); lane = (row % 8) * 4 + piece: every warp request covers 8 rows x
+  // 128 contiguous bytes.
+  float4 pre[6][2];
+  auto prefetch = [&](int tile_) {
+    const int q0 = tile_ * TC_TILE;
 #pragma unroll
     for (int it = 0; it < 6; ++it) {
       const int task = it * 8 + warp;        // 0..47
       const int part = task >> 4;            // 0 pw, 1 c, 2 n   (warp uniform)
       const int row = (task & 15) * 8 + (lane >> 2);
       const int q = lane & 3;
-      const int c = c_idx[row];
+      const int p = q0 + row;
       const float* src = nullptr;
-      if (c >= 0) {
-        if (part == 0) src = pw + (size_t)(p0 + row) * TC_W;
-        else if (part == 1) src = feats + (size_t)c * TC_R;
+      if (tile_ < num_tiles && p < P) {
+        if (part == 0) src = pw + (size_t)p * TC_W;
         else {
-          const int n = n_idx[row];
-          if (n != c) src = nfeats + (size_t)n * TC_R;   // self pair: zeros (network.py:372-374)
+          const int c = __ldg(pair_c + p);
+          if (part == 1) src = feats + (size_t)c * TC_R;
+          else {
+            const int n = __ldg(pair_n + p);
+            if (n != c) src = nfeats + (size_t)n * TC_R;   // self pair: zeros (network.py:372-374)
+          }
         }
       }
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+      pre[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pre[it][1] = pre[it][0];
       if (src != nullptr) {
-        v0 = ldg4(src + q * 8);
-        v1 = ldg4(src + q * 8 + 4);
+        pre[it][0] = ldg4(src + q * 8);
+        pre[it][1] = ldg4(src + q * 8 + 4);
       }
+    }
+  };
+  prefetch(blockIdx.x);
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int p0 = tile * TC_TILE;
+
+    // ---- 0. segment ids of the tile (for the pooling phase) --------------------------
+    if (t < TC_TILE) {
+      const int p = p0 + t;
+      c_idx[t] = p < P ? __ldg(pair_c + p) : -1;
+    }
+
+    // ---- 1. fill A (hi / lo) from the prefetched registers ---------------------------
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+      const int task = it * 8 + warp;
+      const int part = task >> 4;
+      const int row = (task & 15) * 8 + (lane >> 2);
+      const int q = lane & 3;
+      const float4 v0 = pre[it][0], v1 = pre[it][1];
       uint4 h, l;
       umma::split_bf16x2(v0.x, v0.y, h.x, l.x);
       umma::split_bf16x2(v0.z, v0.w, h.y, l.y);
@@ -189,6 +206,7 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
       }
       umma::mma_commit(bar);
     }
+    prefetch(tile + gridDim.x);   // in flight during the UMMA / epilogue phases
     umma::mbar_wait(bar, 0);
     umma::tc_fence_after();
 
