@@ -50,6 +50,19 @@ SIGNATURES = {
     'gn_loss_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                     c_void_p, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_void_p,
                     c_void_p],
+    'gn_relu_mask': [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    'gn_add_inplace': [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    'gn_transpose': [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    'gn_fc_bwd_weight': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                         c_int, c_int, c_void_p],
+    'gn_segment_max_bwd': [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                           c_void_p],
+    'gn_gather_concat_bwd': [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'gn_adam_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_float,
+                     c_float, c_float, c_float, ctypes.c_int64, c_float, c_void_p],
+    'gn_momentum_step': [c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_int64, c_float,
+                         c_float, c_float, c_void_p],
     'gn_selftest_umma': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
 }
 _RESTYPES = {'gn_last_error': ctypes.c_char_p, 'gn_pwfeat_prep_bytes': ctypes.c_int64}

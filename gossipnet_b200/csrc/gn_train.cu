@@ -1,0 +1,325 @@
+// Training-side kernels (A10/A11): the backward pieces of the reference graph
+// that TF autodiff generates for nms_net/network.py (MatMul / BiasAdd / Relu
+// grads, SegmentMax grad, Gather grad) and the optimizer update of
+// train.py:64-77 (tf.train.AdamOptimizer / MomentumOptimizer + the slim L2
+// regulariser of train.py:231).  fp32 on the CUDA cores; the training forward
+// keeps the per-pair activations (h1, h2) it needs, so nothing is recomputed.
+#include "gn_common.cuh"
+
+namespace gn {
+
+// ---------------------------------------------------------------------------
+// elementwise
+// ---------------------------------------------------------------------------
+__global__ void relu_mask_kernel(float* __restrict__ dy, const float* __restrict__ y, int64_t n,
+                                 const int32_t* __restrict__ rows_dev, int width) {
+  if (rows_dev != nullptr) n = min(n, (int64_t)__ldg(rows_dev) * width);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    if (!(y[i] > 0.f)) dy[i] = 0.f;   // tf.nn.relu grad: passes where the output is > 0
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src,
+                                   int64_t n, const int32_t* __restrict__ rows_dev, int width) {
+  if (rows_dev != nullptr) n = min(n, (int64_t)__ldg(rows_dev) * width);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+
+__global__ void transpose_kernel(const float* __restrict__ w, int k, int n, float* __restrict__ wt) {
+  __shared__ float tile[32][33];
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = by + j, c = bx + threadIdx.x;
+    tile[j][threadIdx.x] = (r < k && c < n) ? w[(size_t)r * n + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int r = bx + j, c = by + threadIdx.x;   // wt[n,k]
+    if (r < n && c < k) wt[(size_t)r * k + c] = tile[threadIdx.x][j];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// dW[k,n] += x[rows,k]^T @ dy[rows,n];  db[n] += column sums of dy
+// grid (k tiles of 64, n tiles of 64, row chunks); 4x4 outputs per thread,
+// partial products reduced into dW with atomicAdd.
+// ---------------------------------------------------------------------------
+constexpr int WG_T = 64, WG_RK = 16, WG_THREADS = 256, WG_ROWS_PER_CTA = 2048;
+
+__global__ void __launch_bounds__(WG_THREADS)
+fc_bwd_weight_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int ldy,
+                     float* __restrict__ dw, float* __restrict__ db, int rows_host,
+                     const int32_t* __restrict__ rows_dev, int k, int n) {
+  __shared__ __align__(16) float Xs[WG_RK][WG_T + 4];
+  __shared__ __align__(16) float Ds[WG_RK][WG_T + 4];
+  int rows = rows_host;
+  if (rows_dev != nullptr) rows = min(rows, __ldg(rows_dev));
+  const int k0 = blockIdx.x * WG_T, n0 = blockIdx.y * WG_T;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;   // threads 0..63 of k-tile 0 accumulate db
+
+  for (int chunk = blockIdx.z; (int64_t)chunk * WG_ROWS_PER_CTA < rows; chunk += gridDim.z) {
+    const int r_begin = chunk * WG_ROWS_PER_CTA;
+    const int r_end = min(rows, r_begin + WG_ROWS_PER_CTA);
+    for (int r0 = r_begin; r0 < r_end; r0 += WG_RK) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = (t >> 6) + 4 * i, c = t & 63;
+        const int gr = r0 + rr;
+        Xs[rr][c] = (gr < r_end && k0 + c < k) ? __ldg(x + (size_t)gr * ldx + k0 + c) : 0.f;
+        Ds[rr][c] = (gr < r_end && n0 + c < n) ? __ldg(dy + (size_t)gr * ldy + n0 + c) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < WG_RK; ++rr) {
+        const float4 a = *reinterpret_cast<const float4*>(&Xs[rr][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Ds[rr][tx * 4]);
+        const float a4[4] = {a.x, a.y, a.z, a.w}, b4[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+      }
+      if (blockIdx.x == 0 && t < WG_T) {
+#pragma unroll
+        for (int rr = 0; rr < WG_RK; ++rr) bsum += Ds[rr][t];
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gk = k0 + ty * 4 + i, gn = n0 + tx * 4 + j;
+      if (gk < k && gn < n && acc[i][j] != 0.f) atomicAdd(dw + (size_t)gk * n + gn, acc[i][j]);
+    }
+  if (db != nullptr && blockIdx.x == 0 && t < WG_T && n0 + t < n && bsum != 0.f)
+    atomicAdd(db + n0 + t, bsum);
+}
+
+// ---------------------------------------------------------------------------
+// tf.segment_max gradient (math_grad.py _SegmentMinOrMaxGrad): rows equal to the
+// segment max receive grad / (number of such rows); everything else 0.
+// ---------------------------------------------------------------------------
+__global__ void segment_max_bwd_kernel(const float* __restrict__ h, const float* __restrict__ pooled,
+                                       const float* __restrict__ dpooled, int f,
+                                       const int32_t* __restrict__ row_ptr, int num_dets,
+                                       float* __restrict__ dh) {
+  const int64_t total = (int64_t)num_dets * f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / f), j = (int)(i - (int64_t)row * f);
+    const int b = __ldg(row_ptr + row), e = __ldg(row_ptr + row + 1);
+    const float m = pooled[i], g = dpooled[i];
+    int cnt = 0;
+    for (int p = b; p < e; ++p) cnt += (h[(size_t)p * f + j] == m);
+    const float share = cnt > 0 ? g / (float)cnt : 0.f;
+    for (int p = b; p < e; ++p) dh[(size_t)p * f + j] = (h[(size_t)p * f + j] == m) ? share : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// gradient of [pw | feats[c] | nfeats[n] (0 on self pairs)] (network.py:367-376)
+//   dpw_accum[p, :w]  += dx[p, :w]
+//   dfeats[c, :]      += sum over the row's pairs of dx[p, w:w+r]   (contiguous segment)
+//   dnfeats[n, :]     += dx[p, w+r:]  for c != n                    (scatter, atomicAdd)
+// ---------------------------------------------------------------------------
+__global__ void gather_concat_bwd_pw_kernel(const float* __restrict__ dx, int w, int width,
+                                            const int32_t* __restrict__ num_pairs, int capacity,
+                                            float* __restrict__ dpw) {
+  const int64_t total = (int64_t)min(__ldg(num_pairs), capacity) * w;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / w;
+    const int j = (int)(i - p * w);
+    dpw[i] += dx[p * width + j];
+  }
+}
+
+__global__ void gather_concat_bwd_c_kernel(const float* __restrict__ dx, int w, int r, int width,
+                                           const int32_t* __restrict__ row_ptr, int num_dets,
+                                           float* __restrict__ dfeats) {
+  const int64_t total = (int64_t)num_dets * r;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / r), j = (int)(i - (int64_t)row * r);
+    const int b = __ldg(row_ptr + row), e = __ldg(row_ptr + row + 1);
+    float s = 0.f;
+    for (int p = b; p < e; ++p) s += dx[(size_t)p * width + w + j];
+    dfeats[i] += s;
+  }
+}
+
+__global__ void gather_concat_bwd_n_kernel(const float* __restrict__ dx, int w, int r, int width,
+                                           const int32_t* __restrict__ pair_c,
+                                           const int32_t* __restrict__ pair_n,
+                                           const int32_t* __restrict__ num_pairs, int capacity,
+                                           float* __restrict__ dnfeats) {
+  const int64_t total = (int64_t)min(__ldg(num_pairs), capacity) * r;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / r;
+    const int j = (int)(i - p * r);
+    const int c = __ldg(pair_c + p), n = __ldg(pair_n + p);
+    if (c == n) continue;   // tf.select zeroed these rows: no gradient
+    const float g = dx[p * width + w + r + j];
+    if (g != 0.f) atomicAdd(dnfeats + (size_t)n * r + j, g);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// optimizers on the flat parameter buffer
+//   g = grad_scale * grad + decay[i] * theta        (slim l2_regularizer: wd * sum(w^2)/2)
+// Adam (tf.train.AdamOptimizer): lr_t = lr * sqrt(1-b2^t) / (1-b1^t);
+//   m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; theta -= lr_t * m / (sqrt(v) + eps)
+// Momentum (tf.train.MomentumOptimizer): a = mom * a + g; theta -= lr * a
+// ---------------------------------------------------------------------------
+__global__ void adam_step_kernel(float* __restrict__ theta, const float* __restrict__ grad,
+                                 float* __restrict__ m, float* __restrict__ v,
+                                 const float* __restrict__ decay, int64_t n, float lr_t, float b1,
+                                 float b2, float eps, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float th = theta[i];
+    const float g = grad_scale * grad[i] + (decay != nullptr ? decay[i] * th : 0.f);
+    const float mi = b1 * m[i] + (1.f - b1) * g;
+    const float vi = b2 * v[i] + (1.f - b2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] = th - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+__global__ void momentum_step_kernel(float* __restrict__ theta, const float* __restrict__ grad,
+                                     float* __restrict__ accum, const float* __restrict__ decay,
+                                     int64_t n, float lr, float momentum, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float th = theta[i];
+    const float g = grad_scale * grad[i] + (decay != nullptr ? decay[i] * th : 0.f);
+    const float a = momentum * accum[i] + g;
+    accum[i] = a;
+    theta[i] = th - lr * a;
+  }
+}
+
+static inline int ew_grid(int64_t n) {
+  int64_t b = ceil_div64(n, 256);
+  const int cap = 16 * sm_count();
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace gn
+
+extern "C" int gn_relu_mask(float* dy, const float* y, int rows, const int32_t* rows_dev,
+                            int width, gn_stream_t stream) {
+  GN_REQUIRE(rows >= 0 && width > 0, "gn_relu_mask: bad sizes");
+  if (rows == 0) return GN_OK;
+  GN_REQUIRE(dy && y, "gn_relu_mask: null pointer");
+  const int64_t n = (int64_t)rows * width;
+  gn::relu_mask_kernel<<<gn::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dy, y, n, rows_dev, width);
+  GN_CHECK_LAUNCH("gn_relu_mask");
+  return GN_OK;
+}
+
+extern "C" int gn_add_inplace(float* dst, const float* src, int rows, const int32_t* rows_dev,
+                              int width, gn_stream_t stream) {
+  GN_REQUIRE(rows >= 0 && width > 0, "gn_add_inplace: bad sizes");
+  if (rows == 0) return GN_OK;
+  GN_REQUIRE(dst && src, "gn_add_inplace: null pointer");
+  const int64_t n = (int64_t)rows * width;
+  gn::add_inplace_kernel<<<gn::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(dst, src, n, rows_dev, width);
+  GN_CHECK_LAUNCH("gn_add_inplace");
+  return GN_OK;
+}
+
+extern "C" int gn_transpose(const float* w, int k, int n, float* wt, gn_stream_t stream) {
+  GN_REQUIRE(k > 0 && n > 0 && w && wt, "gn_transpose: bad arguments");
+  dim3 grid(gn::ceil_div(n, 32), gn::ceil_div(k, 32));
+  gn::transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(w, k, n, wt);
+  GN_CHECK_LAUNCH("gn_transpose");
+  return GN_OK;
+}
+
+extern "C" int gn_fc_bwd_weight(const float* x, int ldx, const float* dy, int ldy, float* dw,
+                                float* db, int rows, const int32_t* rows_dev, int k, int n,
+                                gn_stream_t stream) {
+  GN_REQUIRE(rows >= 0 && k > 0 && n > 0 && ldx >= k && ldy >= n, "gn_fc_bwd_weight: bad shape");
+  if (rows == 0) return GN_OK;
+  GN_REQUIRE(x && dy && dw, "gn_fc_bwd_weight: null pointer");
+  int chunks = gn::ceil_div(rows, gn::WG_ROWS_PER_CTA);
+  const int tiles = gn::ceil_div(k, gn::WG_T) * gn::ceil_div(n, gn::WG_T);
+  const int cap = (8 * gn::sm_count() + tiles - 1) / tiles;
+  if (chunks > cap) chunks = cap;
+  dim3 grid(gn::ceil_div(k, gn::WG_T), gn::ceil_div(n, gn::WG_T), chunks);
+  gn::fc_bwd_weight_kernel<<<grid, gn::WG_THREADS, 0, (cudaStream_t)stream>>>(
+      x, ldx, dy, ldy, dw, db, rows, rows_dev, k, n);
+  GN_CHECK_LAUNCH("gn_fc_bwd_weight");
+  return GN_OK;
+}
+
+extern "C" int gn_segment_max_bwd(const float* h, const float* pooled, const float* dpooled, int f,
+                                  const int32_t* row_ptr, int num_dets, float* dh,
+                                  gn_stream_t stream) {
+  GN_REQUIRE(f > 0 && num_dets >= 0, "gn_segment_max_bwd: bad sizes");
+  if (num_dets == 0) return GN_OK;
+  GN_REQUIRE(h && pooled && dpooled && row_ptr && dh, "gn_segment_max_bwd: null pointer");
+  gn::segment_max_bwd_kernel<<<gn::ew_grid((int64_t)num_dets * f), 256, 0, (cudaStream_t)stream>>>(
+      h, pooled, dpooled, f, row_ptr, num_dets, dh);
+  GN_CHECK_LAUNCH("gn_segment_max_bwd");
+  return GN_OK;
+}
+
+extern "C" int gn_gather_concat_bwd(const float* dx, int w, int r, const int32_t* pair_c,
+                                    const int32_t* pair_n, const int32_t* row_ptr, int num_dets,
+                                    const int32_t* num_pairs, int capacity, float* dpw_accum,
+                                    float* dfeats, float* dnfeats, gn_stream_t stream) {
+  GN_REQUIRE(w > 0 && r > 0 && num_dets >= 0 && capacity >= 0, "gn_gather_concat_bwd: bad sizes");
+  if (capacity == 0 || num_dets == 0) return GN_OK;
+  GN_REQUIRE(dx && pair_c && pair_n && row_ptr && num_pairs && dpw_accum && dfeats && dnfeats,
+             "gn_gather_concat_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int width = w + 2 * r;
+  gn::gather_concat_bwd_pw_kernel<<<gn::ew_grid((int64_t)capacity * w), 256, 0, s>>>(
+      dx, w, width, num_pairs, capacity, dpw_accum);
+  gn::gather_concat_bwd_c_kernel<<<gn::ew_grid((int64_t)num_dets * r), 256, 0, s>>>(
+      dx, w, r, width, row_ptr, num_dets, dfeats);
+  gn::gather_concat_bwd_n_kernel<<<gn::ew_grid((int64_t)capacity * r), 256, 0, s>>>(
+      dx, w, r, width, pair_c, pair_n, num_pairs, capacity, dnfeats);
+  GN_CHECK_LAUNCH("gn_gather_concat_bwd");
+  return GN_OK;
+}
+
+extern "C" int gn_adam_step(float* params, const float* grads, float* m, float* v,
+                            const float* decay, int64_t n, float lr, float beta1, float beta2,
+                            float eps, int64_t step, float grad_scale, gn_stream_t stream) {
+  GN_REQUIRE(n >= 0 && step >= 1, "gn_adam_step: bad arguments (step counts from 1)");
+  if (n == 0) return GN_OK;
+  GN_REQUIRE(params && grads && m && v, "gn_adam_step: null pointer");
+  const double lr_t = (double)lr * sqrt(1.0 - pow((double)beta2, (double)step)) /
+                      (1.0 - pow((double)beta1, (double)step));
+  gn::adam_step_kernel<<<gn::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, m, v, decay, n, (float)lr_t, beta1, beta2, eps, grad_scale);
+  GN_CHECK_LAUNCH("gn_adam_step");
+  return GN_OK;
+}
+
+extern "C" int gn_momentum_step(float* params, const float* grads, float* accum,
+                                const float* decay, int64_t n, float lr, float momentum,
+                                float grad_scale, gn_stream_t stream) {
+  GN_REQUIRE(n >= 0, "gn_momentum_step: bad arguments");
+  if (n == 0) return GN_OK;
+  GN_REQUIRE(params && grads && accum, "gn_momentum_step: null pointer");
+  gn::momentum_step_kernel<<<gn::ew_grid(n), 256, 0, (cudaStream_t)stream>>>(
+      params, grads, accum, decay, n, lr, momentum, grad_scale);
+  GN_CHECK_LAUNCH("gn_momentum_step");
+  return GN_OK;
+}

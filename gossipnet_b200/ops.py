@@ -223,6 +223,76 @@ def loss_fwd(prediction, labels, weights, assignment, gt_crowd, gt_classes, img_
     return loss_out, dlogit
 
 
+# ---------------------------------------------------------------------- training
+def relu_mask(dy, y, rows_dev=None):
+    """dy *= (y > 0) in place (rows beyond *rows_dev untouched)."""
+    rows, width = dy.shape
+    _lib.call('gn_relu_mask', _chk(dy, torch.float32, 'dy'), _chk(y, torch.float32, 'y'), rows,
+              _chk(rows_dev, torch.int32, 'rows_dev', True), width, _stream())
+    return dy
+
+
+def add_inplace(dst, src, rows_dev=None):
+    rows, width = (dst.shape[0], dst.numel() // max(dst.shape[0], 1)) if dst.dim() > 1 \
+        else (1, dst.numel())
+    _lib.call('gn_add_inplace', _chk(dst, torch.float32, 'dst'), _chk(src, torch.float32, 'src'),
+              rows, _chk(rows_dev, torch.int32, 'rows_dev', True), width, _stream())
+    return dst
+
+
+def transpose(w, out=None):
+    k, n = w.shape
+    if out is None:
+        out = torch.empty((n, k), dtype=torch.float32, device=w.device)
+    _lib.call('gn_transpose', _chk(w, torch.float32, 'w'), k, n, _chk(out, torch.float32, 'wt'),
+              _stream())
+    return out
+
+
+def fc_bwd_weight(x, dy, dw, db, rows_dev=None):
+    """dw[k,n] += x^T dy; db[n] += colsum(dy)."""
+    rows, k = x.shape
+    n = dy.shape[1]
+    _lib.call('gn_fc_bwd_weight', _chk(x, torch.float32, 'x'), x.stride(0),
+              _chk(dy, torch.float32, 'dy'), dy.stride(0), _chk(dw, torch.float32, 'dw'),
+              _chk(db, torch.float32, 'db', True), rows,
+              _chk(rows_dev, torch.int32, 'rows_dev', True), k, n, _stream())
+
+
+def segment_max_bwd(h, pooled, dpooled, row_ptr, out):
+    num_dets, f = pooled.shape
+    _lib.call('gn_segment_max_bwd', _chk(h, torch.float32, 'h'),
+              _chk(pooled, torch.float32, 'pooled'), _chk(dpooled, torch.float32, 'dpooled'), f,
+              _chk(row_ptr, torch.int32, 'row_ptr'), num_dets, _chk(out, torch.float32, 'dh'),
+              _stream())
+    return out
+
+
+def gather_concat_bwd(dx, w, r, pair_c, pair_n, row_ptr, num_dets, num_pairs, capacity,
+                      dpw_accum, dfeats, dnfeats):
+    _lib.call('gn_gather_concat_bwd', _chk(dx, torch.float32, 'dx'), w, r,
+              _chk(pair_c, torch.int32, 'pair_c'), _chk(pair_n, torch.int32, 'pair_n'),
+              _chk(row_ptr, torch.int32, 'row_ptr'), num_dets,
+              _chk(num_pairs, torch.int32, 'num_pairs'), int(capacity),
+              _chk(dpw_accum, torch.float32, 'dpw_accum'), _chk(dfeats, torch.float32, 'dfeats'),
+              _chk(dnfeats, torch.float32, 'dnfeats'), _stream())
+
+
+def adam_step(params, grads, m, v, decay, lr, beta1, beta2, eps, step, grad_scale):
+    _lib.call('gn_adam_step', _chk(params, torch.float32, 'params'),
+              _chk(grads, torch.float32, 'grads'), _chk(m, torch.float32, 'm'),
+              _chk(v, torch.float32, 'v'), _chk(decay, torch.float32, 'decay', True),
+              params.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
+              float(grad_scale), _stream())
+
+
+def momentum_step(params, grads, accum, decay, lr, momentum, grad_scale):
+    _lib.call('gn_momentum_step', _chk(params, torch.float32, 'params'),
+              _chk(grads, torch.float32, 'grads'), _chk(accum, torch.float32, 'accum'),
+              _chk(decay, torch.float32, 'decay', True), params.numel(), float(lr),
+              float(momentum), float(grad_scale), _stream())
+
+
 # -------------------------------------------------------------------- diagnostics
 def selftest_umma(a, w):
     """c[128,64] = a[128,k] @ w[k,64] through tcgen05 (see gn_selftest.cu)."""

@@ -1,0 +1,226 @@
+"""Training step of the reference (train.py:64-77, 222-238, 316-320) on the B200
+path: forward with kept activations -> DetectionMatching -> loss -> backward ->
+(NCCL all-reduce of the flat gradient) -> fused Adam / Momentum update.
+
+The reference trains one image per step (dataset.py:105).  A step here takes a
+list of images; the objective is the MEAN over all images of the step (over all
+ranks) of the reference's per-image loss, plus the L2 regulariser
+`weight_decay * sum(W^2)/2` over the FC weights built with `weight_reg`
+(everything but the predict head, network.py:261-272) applied once.  With one
+image and one rank this is exactly the reference's step.
+
+Backward follows what TF autodiff generates for network.py:
+geometry features are constants (stop_gradient, :454), the pair-feature MLP
+receives the sum of the gradients of all blocks, gather -> scatter-add (self
+pairs excluded on the neighbour side), segment_max -> rows equal to the max
+share the gradient, DetectionMatching is not differentiable (labels / weights
+are constants of the step).  All arithmetic is in libgossipnet_b200.so
+(csrc/gn_train.cu + the forward pieces); this file only sequences the calls.
+"""
+import numpy as np
+import torch
+
+from gossipnet_b200 import ops, parallel
+from gossipnet_b200.nms_net.config import cfg
+
+
+class Trainer(object):
+
+    def __init__(self, net, optimizer=None, weight_decay=None, momentum=None,
+                 beta1=0.9, beta2=0.999, eps=1e-8):
+        self.net = net
+        self.eng = net.engine
+        eng = self.eng
+        self.optimizer = optimizer or cfg.train.optimizer
+        if self.optimizer not in ('adam', 'sgd'):
+            raise ValueError('unknown optimizer {}'.format(self.optimizer))   # train.py:73
+        self.momentum = cfg.train.momentum if momentum is None else momentum
+        self.beta1, self.beta2, self.eps = beta1, beta2, eps
+        wd = cfg.train.weight_decay if weight_decay is None else weight_decay
+        dev = eng.device
+        # flat gradient buffer + one trailing slot carrying the image count, so a
+        # single all-reduce delivers both
+        self.gradbuf = torch.zeros(eng.total + 1, dtype=torch.float32, device=dev)
+        self.grad = self.gradbuf[:eng.total]
+        self.g = dict((e.name, self.grad[e.offset:e.offset + e.size].view(*e.shape))
+                      for e in eng.layout.values())
+        decay = np.zeros(eng.total, dtype=np.float32)
+        for e in eng.layout.values():
+            if e.regularized:
+                decay[e.offset:e.offset + e.size] = wd
+        self.decay = torch.from_numpy(decay).to(dev)
+        self.state1 = torch.zeros(eng.total, dtype=torch.float32, device=dev)   # Adam m / momentum
+        self.state2 = torch.zeros(eng.total, dtype=torch.float32, device=dev)   # Adam v
+        self.global_step = 0
+        self._zero_bias = torch.zeros(1024, dtype=torch.float32, device=dev)
+
+    # ---------------------------------------------------------------- helpers
+    def _fc(self, x, scope, relu, residual=None, rows_dev=None):
+        e = self.eng
+        return ops.fc_fwd(x, e.p[scope + '/weights'], e.p[scope + '/biases'], relu,
+                          residual=residual, rows_dev=rows_dev)
+
+    def _fc_bwd(self, x, dy, scope, rows_dev=None, need_dx=True):
+        """dW, db += ; returns dx = dy @ W^T (rows beyond *rows_dev are not written)."""
+        ops.fc_bwd_weight(x, dy, self.g[scope + '/weights'], self.g[scope + '/biases'],
+                          rows_dev=rows_dev)
+        if not need_dx:
+            return None
+        w = self.eng.p[scope + '/weights']
+        wt = ops.transpose(w)
+        return ops.fc_fwd(dy, wt, self._zero_bias[:w.shape[0]], False, rows_dev=rows_dev)
+
+    # -------------------------------------------------------- forward + backward
+    def forward_backward(self, batches, zero_grad=True):
+        """Accumulates d(sum over these images of the per-image loss)/d(theta) into
+        self.grad and the image count into self.gradbuf[-1].  Returns the forward
+        results (prediction, labels, weights, loss_out[B,3], ...)."""
+        net, eng, g = self.net, self.eng, self.eng.g
+        io = net._pack(batches, eng.device, True)
+        dets, scores, classes, img_off = io['dets'], io['det_scores'], io['det_classes'], io['img_off']
+        T = dets.shape[0]
+        if zero_grad:
+            self.gradbuf.zero_()
+
+        # ---- forward, keeping activations (unfused CUDA pieces) ---------------------
+        row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dets, img_off)
+        P = int(num_pairs.item())
+        if P > cap:   # grow and redo the fill
+            eng.capacity = int(P * 1.25) + 256
+            row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dets, img_off)
+        cls = classes if eng.multiclass else None
+        raw = ops.pair_geometry(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
+                                eng.num_classes, g['pw_feat_multiplyer'])
+        pw_acts = [raw]
+        for i in range(1, g['num_pwfeat_fc'] + 1):
+            pw_acts.append(self._fc(pw_acts[-1], 'gnet/pw_feats/fc%d' % i, True, rows_dev=num_pairs))
+        pw = pw_acts[-1]
+        w, r, f = pw.shape[1], g['reduced_dim'], g['pairfeat_dim']
+
+        feats = torch.zeros((T, g['shortcut_dim']), dtype=torch.float32, device=eng.device)
+        tape = []
+        for b in range(1, g['num_blocks'] + 1):
+            s = 'gnet/block%d/' % b
+            red = self._fc(feats, s + 'reduce_dim', True)
+            nred = self._fc(feats, s + 'reduce_dim_neighbor', True) if g['neighbor_feats'] else red
+            x = ops.block_gather_concat(pw, red, nred, pair_c, pair_n, num_pairs, cap)
+            hs = []
+            h = x
+            for i in range(1, g['num_block_pw_fc'] + 1):
+                h = self._fc(h, s + 'pw_fc%d' % i, True, rows_dev=num_pairs)
+                hs.append(h)
+            del x   # recomputed in backward: one gather instead of P x 96 floats per block
+            pooled = ops.segment_max(h, row_ptr, T)
+            ds = [pooled]
+            for i in range(1, g['num_block_fc']):
+                ds.append(self._fc(ds[-1], s + 'fc%d' % i, True))
+            out = self._fc(ds[-1], s + 'fc%d' % g['num_block_fc'], True, residual=feats)
+            tape.append((feats, red, nred, hs, ds, out))
+            feats = out
+        pred_acts = [feats]
+        for i in range(1, g['num_predict_fc']):
+            pred_acts.append(self._fc(pred_acts[-1], 'gnet/predict/fc%d/fully_connected' % i, False))
+        prediction = self._fc(pred_acts[-1], 'gnet/predict/logits/fully_connected', False).view(-1)
+
+        res = eng.matching_and_loss(prediction, dets, classes, img_off, io['img_off_host'],
+                                    io['gt_boxes'], io['gt_crowd'], io['gt_classes'],
+                                    io['gt_off_host'], net.class_weights, want_grad=True)
+        res.update(prediction=prediction, P=P, num_images=len(batches))
+
+        # ---- backward --------------------------------------------------------------
+        d = res['dlogit'].view(-1, 1).contiguous()
+        d = self._fc_bwd(pred_acts[-1], d, 'gnet/predict/logits/fully_connected')
+        for i in range(g['num_predict_fc'] - 1, 0, -1):
+            d = self._fc_bwd(pred_acts[i - 1], d, 'gnet/predict/fc%d/fully_connected' % i)
+        dfeats = d
+        dpw = torch.zeros((cap, w), dtype=torch.float32, device=eng.device)
+        for b in range(g['num_blocks'], 0, -1):
+            s = 'gnet/block%d/' % b
+            feats_in, red, nred, hs, ds, out = tape[b - 1]
+            ops.relu_mask(dfeats, out)                      # shortcut relu (network.py:407-408)
+            dd = self._fc_bwd(ds[-1], dfeats, s + 'fc%d' % g['num_block_fc'])
+            for i in range(g['num_block_fc'] - 1, 0, -1):
+                ops.relu_mask(dd, ds[i])
+                dd = self._fc_bwd(ds[i - 1], dd, s + 'fc%d' % i)
+            dh = torch.empty_like(hs[-1]) if hs else None
+            x = ops.block_gather_concat(pw, red, nred, pair_c, pair_n, num_pairs, cap)
+            if hs:
+                ops.segment_max_bwd(hs[-1], ds[0], dd, row_ptr, dh)
+                for i in range(g['num_block_pw_fc'], 0, -1):
+                    ops.relu_mask(dh, hs[i - 1], rows_dev=num_pairs)
+                    dh = self._fc_bwd(hs[i - 2] if i > 1 else x, dh, s + 'pw_fc%d' % i,
+                                      rows_dev=num_pairs)
+            else:
+                dh = torch.empty_like(x)
+                ops.segment_max_bwd(x, ds[0], dd, row_ptr, dh)
+            dred = torch.zeros_like(red)
+            dnred = torch.zeros_like(red) if g['neighbor_feats'] else dred
+            ops.gather_concat_bwd(dh, w, r, pair_c, pair_n, row_ptr, T, num_pairs, cap, dpw,
+                                  dred, dnred)
+            ops.relu_mask(dred, red)
+            dx = self._fc_bwd(feats_in, dred, s + 'reduce_dim', need_dx=b > 1)
+            if g['neighbor_feats']:
+                ops.relu_mask(dnred, nred)
+                dxn = self._fc_bwd(feats_in, dnred, s + 'reduce_dim_neighbor', need_dx=b > 1)
+                if dxn is not None:
+                    ops.add_inplace(dfeats, dxn)
+            # block 1's input is the constant zero start feature (network.py:241-246)
+            if dx is not None:
+                ops.add_inplace(dfeats, dx)
+        # pair-feature MLP: sum of the gradients of all blocks; raw features are constants
+        d = dpw
+        for i in range(g['num_pwfeat_fc'], 0, -1):
+            ops.relu_mask(d, pw_acts[i], rows_dev=num_pairs)
+            d = self._fc_bwd(pw_acts[i - 1], d, 'gnet/pw_feats/fc%d' % i, rows_dev=num_pairs,
+                             need_dx=i > 1)
+        self.gradbuf[-1] += float(len(batches))
+        return res
+
+    # ------------------------------------------------------------------- update
+    def apply_gradients(self, lr):
+        """All-reduce (sum) the flat gradient + image count, then the optimizer update
+        with grad_scale = 1 / (images of the step over all ranks)."""
+        parallel.allreduce_sum_(self.gradbuf)
+        n_images = float(self.gradbuf[-1].item())
+        scale = 1.0 / max(n_images, 1.0)
+        self.global_step += 1
+        if self.optimizer == 'adam':
+            ops.adam_step(self.eng.flat, self.grad, self.state1, self.state2, self.decay, lr,
+                          self.beta1, self.beta2, self.eps, self.global_step, scale)
+        else:
+            ops.momentum_step(self.eng.flat, self.grad, self.state1, self.decay, lr,
+                              self.momentum, scale)
+        return n_images
+
+    def step(self, batches, lr):
+        res = self.forward_backward(batches)
+        res['images_in_step'] = self.apply_gradients(lr)
+        return res
+
+    # ------------------------------------------------------- checkpoint / resume
+    def state_dict(self):
+        return {'params': self.eng.flat.detach().cpu(), 'state1': self.state1.cpu(),
+                'state2': self.state2.cpu(), 'global_step': self.global_step,
+                'optimizer': self.optimizer}
+
+    def load_state_dict(self, sd):
+        self.eng.flat.copy_(sd['params'].to(self.eng.device))
+        self.state1.copy_(sd['state1'].to(self.eng.device))
+        self.state2.copy_(sd['state2'].to(self.eng.device))
+        self.global_step = int(sd['global_step'])
+
+
+class LearningRate(object):
+    """cfg.train.lr_multi_step schedule, same (stateful) behaviour as train.py:26-37."""
+
+    def __init__(self):
+        self.steps = cfg.train.lr_multi_step
+        self.current_step = 0
+
+    def get_lr(self, iter):
+        if self.current_step >= len(self.steps):
+            return self.steps[-1][1]
+        lr = self.steps[self.current_step][1]
+        if iter == self.steps[self.current_step][0]:
+            self.current_step += 1
+        return lr

@@ -200,6 +200,42 @@ int gn_loss_fwd(const float* prediction, const float* labels, float* weights_io,
                 const float* class_weights, int normalize, float loss_multiplier,
                 float* loss_out, float* dlogit, gn_stream_t stream);
 
+/* ---- A11: training step ----------------------------------------------------------
+ * Backward pieces of the graph TF autodiff builds for nms_net/network.py and the
+ * optimizer update of train.py:64-77.  The training forward runs the unfused
+ * pieces above and keeps each FC's output, so every FC backward is
+ *   gn_relu_mask     dy *= (y > 0)                      (tf.nn.relu grad, in place)
+ *   gn_fc_bwd_weight dW[k,n] += x^T dy ; db[n] += colsum(dy)   (accumulates)
+ *   dx = dy @ W^T    via gn_transpose + gn_fc_fwd(dy, W^T, zero bias)
+ * rows_dev (nullable) overrides `rows` with a device-side count, as in gn_fc_fwd.
+ *   gn_segment_max_bwd   tf.segment_max grad: rows equal to the max share the grad evenly
+ *   gn_gather_concat_bwd grad of [pw | feats[c] | nfeats[n]] (network.py:367-376):
+ *                        dpw_accum[P,w] += ; dfeats[T,r] += segment sums ;
+ *                        dnfeats[T,r] += scatter (self pairs excluded)
+ *   gn_add_inplace       dst += src
+ *   gn_adam_step / gn_momentum_step  tf.train.AdamOptimizer / MomentumOptimizer on the
+ *                        flat parameter buffer with g = grad_scale*grad + decay[i]*theta
+ *                        (decay = weight_decay on regularised FC weights, else 0;
+ *                        train.py:231, slim l2_regularizer); step counts from 1. */
+int gn_relu_mask(float* dy, const float* y, int rows, const int32_t* rows_dev, int width,
+                 gn_stream_t stream);
+int gn_add_inplace(float* dst, const float* src, int rows, const int32_t* rows_dev, int width,
+                   gn_stream_t stream);
+int gn_transpose(const float* w, int k, int n, float* wt, gn_stream_t stream);
+int gn_fc_bwd_weight(const float* x, int ldx, const float* dy, int ldy, float* dw, float* db,
+                     int rows, const int32_t* rows_dev, int k, int n, gn_stream_t stream);
+int gn_segment_max_bwd(const float* h, const float* pooled, const float* dpooled, int f,
+                       const int32_t* row_ptr, int num_dets, float* dh, gn_stream_t stream);
+int gn_gather_concat_bwd(const float* dx, int w, int r, const int32_t* pair_c,
+                         const int32_t* pair_n, const int32_t* row_ptr, int num_dets,
+                         const int32_t* num_pairs, int capacity, float* dpw_accum,
+                         float* dfeats, float* dnfeats, gn_stream_t stream);
+int gn_adam_step(float* params, const float* grads, float* m, float* v, const float* decay,
+                 int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                 float grad_scale, gn_stream_t stream);
+int gn_momentum_step(float* params, const float* grads, float* accum, const float* decay,
+                     int64_t n, float lr, float momentum, float grad_scale, gn_stream_t stream);
+
 /* ---- diagnostics ---------------------------------------------------------------
  * c[128,64] = a[128,k] @ w[k,64] on the tensor cores with the building blocks of
  * the FC kernels (bf16x3 split operands, tcgen05.mma into TMEM, tcgen05.ld).

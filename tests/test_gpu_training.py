@@ -1,0 +1,122 @@
+"""GPU: the training step (A10/A11) - CUDA gradients vs the float64 gradient oracle,
+the optimizer updates vs their closed forms, and a few descending steps."""
+import numpy as np
+import pytest
+import torch
+
+from gossipnet_b200 import ops
+from gossipnet_b200 import params as P
+from gossipnet_b200 import synthetic
+from gossipnet_b200.nms_net.config import cfg
+from gossipnet_b200.nms_net.network import Gnet
+from gossipnet_b200.trainer import LearningRate, Trainer
+from oracle import gnet_grad_oracle as gg
+from oracle import gnet_oracle as go
+from tests.helpers import load_experiment
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_grad_for(img, flat, layout, num_classes, labels, weights):
+    bd = go.xyxy_to_boxdata(img['dets'])
+    m = go.iou(bd, bd)
+    pairs = go.neighbor_pairs(m, cfg.gnet.neighbor_thresh)
+    raw = go.geometry_feats(bd, m, img['det_scores'], img['det_classes'], pairs, num_classes,
+                            cfg.gnet.pw_feat_multiplyer)
+    grads, _ = gg.gradients(P.views(layout, flat.astype(np.float64)), cfg, pairs, raw,
+                            img['dets'].shape[0], labels, weights)
+    out = np.zeros(flat.shape[0])
+    for e in layout.values():
+        out[e.offset:e.offset + e.size] = grads[e.name].reshape(-1)
+    return out
+
+
+def grad_check(num_classes, imgs, tol=2e-3):
+    layout, total = P.param_layout(num_classes, cfg)
+    flat = P.init_flat(layout, total, cfg, seed=21)
+    cw = np.linspace(0.5, 1.5, num_classes + 1).astype(np.float32)
+    net = Gnet(num_classes, class_weights=cw, params=flat)
+    tr = Trainer(net)
+    res = tr.forward_backward(imgs)
+    got = tr.grad.cpu().numpy().astype(np.float64)
+    assert float(tr.gradbuf[-1]) == len(imgs)
+    off = res['img_off_host'] if 'img_off_host' in res else np.cumsum([0] + [i['dets'].shape[0] for i in imgs])
+    labels = res['labels'].cpu().numpy()
+    weights = res['weights'].cpu().numpy()        # already class-weighted (constants of the step)
+    want = np.zeros(total)
+    for i, img in enumerate(imgs):
+        s = slice(int(off[i]), int(off[i + 1]))
+        want += oracle_grad_for(img, flat, layout, num_classes, labels[s], weights[s])
+    for e in layout.values():
+        a, b = got[e.offset:e.offset + e.size], want[e.offset:e.offset + e.size]
+        scale = max(np.max(np.abs(b)), 1e-6)
+        assert np.max(np.abs(a - b)) / scale < tol, (e.name, np.max(np.abs(a - b)) / scale)
+    return tr, res
+
+
+def test_gradients_coco_person_two_blocks():
+    load_experiment('coco_person', num_blocks=2)
+    grad_check(1, [synthetic.make_image(300, 1, image_index=0)])
+
+
+def test_gradients_multi_image_batch_sum():
+    load_experiment('coco_person', num_blocks=3)
+    grad_check(1, [synthetic.make_image(n, 1, image_index=i) for i, n in enumerate([120, 57, 200])])
+
+
+def test_gradients_multiclass_and_normalized_loss():
+    load_experiment('coco_multiclass', num_blocks=2)
+    cfg.train.normalize_loss = True
+    cfg.train.loss_multiplyer = 3.0
+    grad_check(80, [synthetic.make_image(150, 80, image_index=2)])
+
+
+def test_gradients_neighbor_feats_and_raw_pair_features():
+    cfg.gnet.num_blocks = 2
+    cfg.gnet.neighbor_feats = True          # reduce_dim_neighbor branch, num_pwfeat_fc = 0
+    cfg.gnet.bias_const_init = 0.05
+    grad_check(1, [synthetic.make_image(90, 1, image_index=4)])
+
+
+def test_adam_and_momentum_updates_closed_form():
+    rs = np.random.RandomState(0)
+    n = 1000
+    theta = rs.normal(0, 1, n).astype(np.float32)
+    grad = rs.normal(0, 1, n).astype(np.float32)
+    decay = (rs.uniform(0, 1, n) < 0.5).astype(np.float32) * 0.0005
+    d = lambda a: torch.from_numpy(a.copy()).cuda()
+    th, m, v = d(theta), torch.zeros(n, device='cuda'), torch.zeros(n, device='cuda')
+    ref_t, ref_m, ref_v = theta.astype(np.float64), np.zeros(n), np.zeros(n)
+    for step in (1, 2, 3):
+        ops.adam_step(th, d(grad), m, v, d(decay), 1e-3, 0.9, 0.999, 1e-8, step, 0.25)
+        g = 0.25 * grad + decay * ref_t
+        ref_t, ref_m, ref_v = gg.adam_reference(ref_t, g, ref_m, ref_v, 1e-3, step)
+        assert np.allclose(th.cpu().numpy(), ref_t, rtol=1e-5, atol=1e-6)
+    th, acc = d(theta), torch.zeros(n, device='cuda')
+    ops.momentum_step(th, d(grad), acc, None, 0.1, 0.9, 1.0)
+    ops.momentum_step(th, d(grad), acc, None, 0.1, 0.9, 1.0)
+    assert np.allclose(th.cpu().numpy(), theta - 0.1 * grad - 0.1 * 1.9 * grad, rtol=1e-5, atol=1e-6)
+
+
+def test_training_steps_reduce_the_loss():
+    load_experiment('coco_person', num_blocks=2)
+    imgs = [synthetic.make_image(200, 1, image_index=i) for i in range(4)]
+    net = Gnet(1)
+    tr = Trainer(net, optimizer='adam')
+    losses = []
+    for it in range(12):
+        res = tr.step(imgs, 1e-3)
+        losses.append(float(res['loss_out'][:, 2].sum()))
+    assert res['images_in_step'] == 4 and tr.global_step == 12
+    assert losses[-1] < 0.8 * losses[0], losses
+    sd = tr.state_dict()
+    tr2 = Trainer(Gnet(1))
+    tr2.load_state_dict(sd)
+    assert tr2.global_step == 12 and torch.equal(tr2.eng.flat.cpu(), sd['params'])
+
+
+def test_learning_rate_schedule_matches_reference_semantics():
+    cfg.train.lr_multi_step = [[3, 0.1], [5, 0.01]]
+    lr = LearningRate()
+    got = [lr.get_lr(i) for i in range(1, 8)]
+    assert got == [0.1, 0.1, 0.1, 0.01, 0.01, 0.01, 0.01]
