@@ -293,6 +293,47 @@ def momentum_step(params, grads, accum, decay, lr, momentum, grad_scale):
               float(momentum), float(grad_scale), _stream())
 
 
+# ---------------------------------------------------------------------- roi pool
+def _roi_args(bottom_data, bottom_rois):
+    # the reference op's rank checks (roi_pooling_op.cc:88-93)
+    if bottom_data.dim() != 4:
+        raise ValueError('data must be 4-dimensional')
+    if bottom_rois.dim() != 2:
+        raise ValueError('rois must be 2-dimensional')
+    if bottom_rois.shape[1] != 5:
+        raise ValueError('rois must be [num_rois, 5] (batch_idx, x1, y1, x2, y2)')
+
+
+def roi_pool_fwd(bottom_data, bottom_rois, pooled_height, pooled_width, spatial_scale):
+    _roi_args(bottom_data, bottom_rois)
+    b, h, w, c = bottom_data.shape
+    r = bottom_rois.shape[0]
+    shape = (r, int(pooled_height), int(pooled_width), c)
+    top = torch.empty(shape, dtype=torch.float32, device=bottom_data.device)
+    argmax = torch.empty(shape, dtype=torch.int32, device=bottom_data.device)
+    _lib.call('gn_roi_pool_fwd', _chk(bottom_data, torch.float32, 'bottom_data'), b, h, w, c,
+              _chk(bottom_rois, torch.float32, 'bottom_rois'), r, int(pooled_height),
+              int(pooled_width), float(spatial_scale), _chk(top, torch.float32, 'top_data'),
+              _chk(argmax, torch.int32, 'argmax'), _stream())
+    return top, argmax
+
+
+def roi_pool_bwd(bottom_data, bottom_rois, argmax, grad, pooled_height, pooled_width,
+                 spatial_scale):
+    _roi_args(bottom_data, bottom_rois)
+    if argmax.dim() != 4:
+        raise ValueError('argmax_data must be 4-dimensional')
+    if grad.dim() != 4:
+        raise ValueError('out_backprop must be 4-dimensional')
+    b, h, w, c = bottom_data.shape
+    out = torch.empty_like(bottom_data)
+    _lib.call('gn_roi_pool_bwd', b, h, w, c, _chk(bottom_rois, torch.float32, 'bottom_rois'),
+              bottom_rois.shape[0], _chk(argmax, torch.int32, 'argmax'),
+              _chk(grad, torch.float32, 'grad'), int(pooled_height), int(pooled_width),
+              float(spatial_scale), _chk(out, torch.float32, 'bottom_diff'), _stream())
+    return out
+
+
 # -------------------------------------------------------------------- diagnostics
 def selftest_umma(a, w):
     """c[128,64] = a[128,k] @ w[k,64] through tcgen05 (see gn_selftest.cu)."""

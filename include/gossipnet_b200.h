@@ -236,6 +236,25 @@ int gn_adam_step(float* params, const float* grads, float* m, float* v, const fl
 int gn_momentum_step(float* params, const float* grads, float* accum, const float* decay,
                      int64_t n, float lr, float momentum, float grad_scale, gn_stream_t stream);
 
+/* ---- RoiPool / RoiPoolGrad ----------------------------------
+ * Replace the RoiPool / RoiPoolGrad ops (nms_net/roi_pooling_layer/roi_pooling_op.cc:
+ * 35-54 op definitions, :128-187 / :374-449 CPU semantics; python names
+ * roi_pooling_op.roi_pool / roi_pool_grad, roi_pooling_op.py:6-7).
+ *   bottom_data[batch,height,width,channels] f32 (NHWC), bottom_rois[num_rois,5] f32
+ *   (batch_idx, x1, y1, x2, y2) -> top_data / argmax [num_rois,ph,pw,channels]
+ *   (argmax: (h*W + w)*C + c inside the roi's image, -1 for an empty bin).
+ *   gn_roi_pool_bwd: bottom_diff[batch,height,width,channels] = sum of top_diff over
+ *   the pooled cells whose argmax is this element, accumulated in the reference's
+ *   order (deterministic, bit-identical to the CPU op).
+ * Bit-exact with the reference CPU kernels.  Errors: pooled sizes < 0 (:64-73). */
+int gn_roi_pool_fwd(const float* bottom_data, int batch, int height, int width, int channels,
+                    const float* bottom_rois, int num_rois, int pooled_height, int pooled_width,
+                    float spatial_scale, float* top_data, int32_t* argmax, gn_stream_t stream);
+int gn_roi_pool_bwd(int batch, int height, int width, int channels, const float* bottom_rois,
+                    int num_rois, const int32_t* argmax, const float* top_diff,
+                    int pooled_height, int pooled_width, float spatial_scale,
+                    float* bottom_diff, gn_stream_t stream);
+
 /* ---- diagnostics ---------------------------------------------------------------
  * c[128,64] = a[128,k] @ w[k,64] on the tensor cores with the building blocks of
  * the FC kernels (bf16x3 split operands, tcgen05.mma into TMEM, tcgen05.ld).

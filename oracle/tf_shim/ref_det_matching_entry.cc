@@ -11,7 +11,8 @@ extern "C" int ref_detection_matching(const float* iou, const float* score,
                                       int32_t* assignment, char* err, int err_len) {
   auto it = KernelRegistry().find("DetectionMatching:CPU");
   if (it == KernelRegistry().end()) return 2;
-  std::unique_ptr<OpKernel> k(it->second());
+  OpKernelConstruction cons;
+  std::unique_ptr<OpKernel> k(it->second(&cons));
   static_assert(sizeof(bool) == 1, "bool is one byte");
   Tensor t_iou((void*)iou, TensorShape({n_dets, n_gt}));
   Tensor t_score((void*)score, TensorShape({n_dets}));
@@ -23,9 +24,9 @@ extern "C" int ref_detection_matching(const float* iou, const float* score,
   ctx.inputs = {&t_iou, &t_score, &t_ign};
   ctx.outputs = {&t_lab, &t_w, &t_as};
   k->Compute(&ctx);
-  if (!ctx.status.ok()) {
+  if (!ctx.status().ok()) {
     if (err && err_len > 0) {
-      std::strncpy(err, ctx.status.error_message().c_str(), err_len - 1);
+      std::strncpy(err, ctx.status().error_message().c_str(), err_len - 1);
       err[err_len - 1] = 0;
     }
     return 1;

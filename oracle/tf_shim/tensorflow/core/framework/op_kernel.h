@@ -1,13 +1,17 @@
 // ORACLE SUPPORT (test infrastructure): a minimal stand-in for the handful of
 // TensorFlow C++ framework types that the reference's custom CPU op sources
 // touch, so that /root/reference/nms_net/matching_module/det_matching.cc can be
-// compiled UNMODIFIED, from where it lies, into oracle/_ref/ and run as the
-// ground truth for the DetectionMatching parity tests.  Nothing here is
+// (and nms_net/roi_pooling_layer/roi_pooling_op.cc) can be
+// compiled UNMODIFIED, from where they lie, into oracle/_ref/ and run as the
+// ground truth for the DetectionMatching / RoiPool parity tests.  Nothing here is
 // TensorFlow code; it only mimics names and call shapes (TF ~0.12 API).
 #ifndef ORACLE_TF_SHIM_OP_KERNEL_H_
 #define ORACLE_TF_SHIM_OP_KERNEL_H_
 
+#include <math.h>
 #include <algorithm>
+#include <cfloat>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -67,6 +71,12 @@ class TensorShape {
 struct TensorShapeUtils {
   static bool IsVector(const TensorShape& s) { return s.dims() == 1; }
   static bool IsMatrix(const TensorShape& s) { return s.dims() == 2; }
+  template <typename I>
+  static Status MakeShape(const I* dims, int n, TensorShape* out) {
+    std::vector<int64> d(dims, dims + n);
+    *out = TensorShape(d);
+    return Status::OK();
+  }
 };
 
 template <typename T, int R>
@@ -76,6 +86,12 @@ class TensorView {
     for (int i = 0; i < R; ++i) dims_[i] = dims[i];
   }
   int64 dimension(int i) const { return dims_[i]; }
+  T* data() const { return data_; }
+  int64 size() const {
+    int64 n = 1;
+    for (int i = 0; i < R; ++i) n *= dims_[i];
+    return n;
+  }
   T& operator()(int64 i) const { return data_[i]; }
   T& operator()(int64 i, int64 j) const { return data_[i * dims_[1] + j]; }
   void setZero() { setConstant(T(0)); }
@@ -107,6 +123,8 @@ class Tensor {
       : shape_(shape), store_(new char[elem_size * (size_t)std::max<int64>(shape.num_elements(), 1)]),
         data_(store_.get()) {}
   const TensorShape& shape() const { return shape_; }
+  int dims() const { return shape_.dims(); }
+  int64 dim_size(int i) const { return shape_.dim_size(i); }
   void* raw() const { return data_; }
 
   template <typename T> TensorView<T, 1> flat() {
@@ -133,19 +151,47 @@ class Tensor {
   void* data_;
 };
 
-class OpKernelConstruction {};
+namespace thread { class ThreadPool {}; }
+struct DeviceBase {
+  struct CpuWorkerThreads {
+    int num_threads = 1;
+    thread::ThreadPool* workers = nullptr;
+  };
+  CpuWorkerThreads cpu_threads;
+  const CpuWorkerThreads* tensorflow_cpu_worker_threads() const { return &cpu_threads; }
+};
+
+// op attributes are supplied by the driver before the kernel is constructed
+class OpKernelConstruction {
+ public:
+  std::map<std::string, double> attrs;
+  Status status_;
+  const Status& status() const { return status_; }
+  template <typename V>
+  Status GetAttr(const char* name, V* out) const {
+    auto it = attrs.find(name);
+    if (it == attrs.end()) return Status(std::string("missing attr ") + name);
+    *out = static_cast<V>(it->second);
+    return Status::OK();
+  }
+  void CtxFailure(const Status& s) { status_ = s; }
+};
 
 class OpKernelContext {
  public:
   std::vector<const Tensor*> inputs;
   std::vector<Tensor*> outputs;  // caller-provided views, indexed by output slot
-  Status status;
+  Status status_;
+  const Status& status() const { return status_; }
   const Tensor& input(int i) { return *inputs[i]; }
   Status allocate_output(int i, const TensorShape&, Tensor** out) {
     *out = outputs[i];
     return Status::OK();
   }
-  void CtxFailure(const Status& s) { status = s; }
+  void CtxFailure(const Status& s) { status_ = s; }
+  DeviceBase dev;
+  DeviceBase* device() { return &dev; }
+  template <typename D> const D& eigen_device() const { static D d; return d; }
 };
 
 class OpKernel {
@@ -187,7 +233,7 @@ class Name {
   KernelDef def_;
 };
 
-typedef std::function<OpKernel*()> KernelFactory;
+typedef std::function<OpKernel*(OpKernelConstruction*)> KernelFactory;
 inline std::map<std::string, KernelFactory>& KernelRegistry() {
   static std::map<std::string, KernelFactory> r;
   return r;
@@ -201,7 +247,7 @@ struct KernelRegistrar {
 #define TF_SHIM_CAT(a, b) TF_SHIM_CAT2(a, b)
 #define REGISTER_KERNEL_BUILDER(BUILDER, ...)                                 \
   static ::tensorflow::KernelRegistrar TF_SHIM_CAT(_shim_kernel_, __COUNTER__)( \
-      BUILDER, []() -> ::tensorflow::OpKernel* { return new __VA_ARGS__(nullptr); })
+      BUILDER, [](::tensorflow::OpKernelConstruction* c) -> ::tensorflow::OpKernel* { return new __VA_ARGS__(c); })
 
 }  // namespace tensorflow
 

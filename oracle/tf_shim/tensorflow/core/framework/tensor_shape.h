@@ -1,0 +1,2 @@
+// ORACLE SUPPORT: TensorShape lives in the shim's op_kernel.h.
+#include "tensorflow/core/framework/op_kernel.h"
