@@ -41,6 +41,12 @@ SIGNATURES = {
     'gn_block_pair_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                           c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_void_p],
+    'gn_block_pair_fwd_hl': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                             c_void_p, c_void_p],
+    'gn_block_det_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                         c_void_p],
     'gn_block_pair_fwd_ffma': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p],

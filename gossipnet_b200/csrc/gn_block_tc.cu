@@ -73,6 +73,10 @@ __device__ __forceinline__ void stage_weight(const float* __restrict__ w, int ch
   }
 }
 
+// HL = false: feats / nfeats are fp32 [T,32] rows (split here, per pair);
+// HL = true : they are bf16 rows [T,64] = [32 hi | 32 lo] written by
+//             gn_block_det_fwd, copied verbatim (16-byte chunks) into the A tile.
+template <bool HL>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ feats,
                      const float* __restrict__ nfeats, const int32_t* __restrict__ pair_c,
@@ -93,6 +97,7 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   unsigned char* h_lo = h_hi + TC_CH2 * TC_LBO_A;
   float* h2 = reinterpret_cast<float*>(smem + TC_OFF_A);        // aliases h1 (dead after FC2)
   int* c_idx = reinterpret_cast<int*>(smem + TC_OFF_IDX);
+  unsigned* seg_end = reinterpret_cast<unsigned*>(c_idx + TC_TILE);   // 4 x 32-row slices
   float* bias1 = reinterpret_cast<float*>(smem + TC_OFF_BIAS);
   float* bias2 = bias1 + TC_F;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
@@ -129,24 +134,39 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   // UMMA / epilogue phases of tile i.  Warp task = 8 rows x one 128-byte part
   // (pw | c | n); lane = (row % 8) * 4 + piece: every warp request covers 8 rows x
   // 128 contiguous bytes.
+  // Indices run one tile ahead of the data (two ahead of the UMMAs), so neither
+  // load sits on the critical path of a tile.
   float4 pre[6][2];
+  int idx_c[4], idx_n[2];          // units 2..5 need c; units 4,5 also need n
+  auto prefetch_idx = [&](int tile_) {
+    const int q0 = tile_ * TC_TILE;
+#pragma unroll
+    for (int it = 2; it < 6; ++it) {
+      const int task = it * 8 + warp;
+      const int p = q0 + (task & 15) * 8 + (lane >> 2);
+      const bool ok = tile_ < num_tiles && p < P;
+      idx_c[it - 2] = ok ? __ldg(pair_c + p) : -1;
+      if (it >= 4) idx_n[it - 4] = ok ? __ldg(pair_n + p) : -1;
+    }
+  };
   auto prefetch = [&](int tile_) {
     const int q0 = tile_ * TC_TILE;
 #pragma unroll
     for (int it = 0; it < 6; ++it) {
       const int task = it * 8 + warp;        // 0..47
-      const int part = task >> 4;            // 0 pw, 1 c, 2 n   (warp uniform)
+      const int part = task >> 4;            // 0 pw, 1 c, 2 n   (warp uniform; it>>1 == part)
       const int row = (task & 15) * 8 + (lane >> 2);
       const int q = lane & 3;
       const int p = q0 + row;
       const float* src = nullptr;
-      if (tile_ < num_tiles && p < P) {
-        if (part == 0) src = pw + (size_t)p * TC_W;
-        else {
-          const int c = __ldg(pair_c + p);
-          if (part == 1) src = feats + (size_t)c * TC_R;
+      if (it < 2) {
+        if (tile_ < num_tiles && p < P) src = pw + (size_t)p * TC_W;
+      } else {
+        const int c = idx_c[it - 2];
+        if (c >= 0) {
+          if (it < 4) src = feats + (size_t)c * TC_R;
           else {
-            const int n = __ldg(pair_n + p);
+            const int n = idx_n[it - 4];
             if (n != c) src = nfeats + (size_t)n * TC_R;   // self pair: zeros (network.py:372-374)
           }
         }
@@ -154,20 +174,33 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
       pre[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
       pre[it][1] = pre[it][0];
       if (src != nullptr) {
-        pre[it][0] = ldg4(src + q * 8);
-        pre[it][1] = ldg4(src + q * 8 + 4);
+        if (HL && part > 0) {       // 128-byte row: hi chunk q at +16q bytes, lo chunk q at +64+16q
+          pre[it][0] = ldg4(src + q * 4);
+          pre[it][1] = ldg4(src + 16 + q * 4);
+        } else {
+          pre[it][0] = ldg4(src + q * 8);
+          pre[it][1] = ldg4(src + q * 8 + 4);
+        }
       }
     }
   };
+  prefetch_idx(blockIdx.x);
   prefetch(blockIdx.x);
+  prefetch_idx(blockIdx.x + gridDim.x);
 
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int p0 = tile * TC_TILE;
 
-    // ---- 0. segment ids of the tile (for the pooling phase) --------------------------
+    // ---- 0. segment ids of the tile + "last row of its run" masks (pooling phase) ----
     if (t < TC_TILE) {
       const int p = p0 + t;
-      c_idx[t] = p < P ? __ldg(pair_c + p) : -1;
+      const int c = p < P ? __ldg(pair_c + p) : -1;
+      const int cnext = (p + 1 < P && (t & 31) != 31) ? __ldg(pair_c + p + 1) : -2;
+      c_idx[t] = c;
+      // a run ends where the next row has another c, at the end of its 32-row slice,
+      // or at the last valid pair; rows past P never flush
+      const unsigned m = __ballot_sync(0xffffffffu, c >= 0 && c != cnext);
+      if (lane == 0) seg_end[warp] = m;
     }
 
     // ---- 1. fill A (hi / lo) from the prefetched registers ---------------------------
@@ -179,10 +212,15 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
       const int q = lane & 3;
       const float4 v0 = pre[it][0], v1 = pre[it][1];
       uint4 h, l;
-      umma::split_bf16x2(v0.x, v0.y, h.x, l.x);
-      umma::split_bf16x2(v0.z, v0.w, h.y, l.y);
-      umma::split_bf16x2(v1.x, v1.y, h.z, l.z);
-      umma::split_bf16x2(v1.z, v1.w, h.w, l.w);
+      if (HL && part > 0) {
+        h = make_uint4(__float_as_uint(v0.x), __float_as_uint(v0.y), __float_as_uint(v0.z), __float_as_uint(v0.w));
+        l = make_uint4(__float_as_uint(v1.x), __float_as_uint(v1.y), __float_as_uint(v1.z), __float_as_uint(v1.w));
+      } else {
+        umma::split_bf16x2(v0.x, v0.y, h.x, l.x);
+        umma::split_bf16x2(v0.z, v0.w, h.y, l.y);
+        umma::split_bf16x2(v1.x, v1.y, h.z, l.z);
+        umma::split_bf16x2(v1.z, v1.w, h.w, l.w);
+      }
       const uint32_t off = (uint32_t)(part * 4 + q) * TC_LBO_A + (uint32_t)row * 16;
       *reinterpret_cast<uint4*>(a_hi + off) = h;
       *reinterpret_cast<uint4*>(a_lo + off) = l;
@@ -206,7 +244,8 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
       }
       umma::mma_commit(bar);
     }
-    prefetch(tile + gridDim.x);   // in flight during the UMMA / epilogue phases
+    prefetch(tile + gridDim.x);          // data of the next tile (its indices are here already)
+    prefetch_idx(tile + 2 * gridDim.x);  // indices of the tile after that
     umma::mbar_wait(bar, 0);
     umma::tc_fence_after();
 
@@ -274,23 +313,20 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
 
     // ---- 6. segmented max over the tile's rows ---------------------------------------
     {
-      const int j = t & 63;            // column
+      const int j = t & 63;            // column (a warp covers 32 columns of one slice)
       const int r0 = (t >> 6) * 32;    // 32-row slice
-      int cur_c = -1;
+      const unsigned ends = seg_end[t >> 6];
+      const float* col = h2 + r0 * TC_LDH2 + j;
       float cur = 0.f;
-      for (int r = r0; r < r0 + 32; ++r) {
-        const int c = c_idx[r];
-        if (c < 0) break;  // rows past P
-        if (c != cur_c) {
-          if (cur_c >= 0)
-            atomicMax(reinterpret_cast<int*>(pooled + (size_t)cur_c * TC_F + j), __float_as_int(cur));
-          cur_c = c;
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        cur = fmaxf(cur, col[r * TC_LDH2]);
+        if ((ends >> r) & 1u) {        // warp uniform
+          atomicMax(reinterpret_cast<int*>(pooled + (size_t)c_idx[r0 + r] * TC_F + j),
+                    __float_as_int(cur));
           cur = 0.f;
         }
-        cur = fmaxf(cur, h2[r * TC_LDH2 + j]);
       }
-      if (cur_c >= 0)
-        atomicMax(reinterpret_cast<int*>(pooled + (size_t)cur_c * TC_F + j), __float_as_int(cur));
     }
     __syncthreads();  // tile buffers free for the next fill
   }
@@ -302,34 +338,59 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
 
 }  // namespace gn
 
-extern "C" int gn_block_pair_fwd(const float* pw, int w, const float* feats,
-                                 const float* nfeats, int r, const int32_t* pair_c,
-                                 const int32_t* pair_n, const int32_t* num_pairs, int capacity,
-                                 const float* w1, const float* b1, const float* w2,
-                                 const float* b2, int f, float* pooled, gn_stream_t stream) {
-  GN_REQUIRE(capacity >= 0, "gn_block_pair_fwd: negative capacity");
+static int launch_block_pair(const char* name, bool hl, const float* pw, int w, const void* feats,
+                             const void* nfeats, int r, const int32_t* pair_c,
+                             const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                             const float* w1, const float* b1, const float* w2, const float* b2,
+                             int f, float* pooled, gn_stream_t stream) {
+  GN_REQUIRE(capacity >= 0, "%s: negative capacity", name);
   if (w != gn::TC_W || r != gn::TC_R || f != gn::TC_F) {
-    gn::set_error("gn_block_pair_fwd: fused kernel is built for w=%d r=%d f=%d (got %d, %d, %d)",
+    gn::set_error("%s: fused kernel is built for w=%d r=%d f=%d (got %d, %d, %d)", name,
                   gn::TC_W, gn::TC_R, gn::TC_F, w, r, f);
     return GN_ERR_UNSUPPORTED;
   }
   if (capacity == 0) return GN_OK;
   GN_REQUIRE(pw && feats && nfeats && pair_c && pair_n && num_pairs && w1 && b1 && w2 && b2 &&
-                 pooled,
-             "gn_block_pair_fwd: null pointer");
+                 pooled, "%s: null pointer", name);
   GN_REQUIRE((((uintptr_t)pw | (uintptr_t)feats | (uintptr_t)nfeats) & 15) == 0,
-             "gn_block_pair_fwd: pointers must be 16-byte aligned");
-  cudaError_t e = cudaFuncSetAttribute(gn::block_pair_tc_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn::TC_SMEM);
+             "%s: pointers must be 16-byte aligned", name);
+  const void* kern = hl ? (const void*)gn::block_pair_tc_kernel<true>
+                        : (const void*)gn::block_pair_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)gn::TC_SMEM);
   if (e != cudaSuccess) {
-    gn::set_error("gn_block_pair_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    gn::set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
     return GN_ERR_CUDA;
   }
   int grid = gn::ceil_div(capacity, gn::TC_TILE);
   const int cap = 2 * gn::sm_count();
   if (grid > cap) grid = cap;
-  gn::block_pair_tc_kernel<<<grid, gn::TC_THREADS, gn::TC_SMEM, (cudaStream_t)stream>>>(
-      pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2, pooled);
-  GN_CHECK_LAUNCH("gn_block_pair_fwd");
+  const float* fp = static_cast<const float*>(feats);
+  const float* np = static_cast<const float*>(nfeats);
+  if (hl)
+    gn::block_pair_tc_kernel<true><<<grid, gn::TC_THREADS, gn::TC_SMEM, (cudaStream_t)stream>>>(
+        pw, fp, np, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2, pooled);
+  else
+    gn::block_pair_tc_kernel<false><<<grid, gn::TC_THREADS, gn::TC_SMEM, (cudaStream_t)stream>>>(
+        pw, fp, np, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2, pooled);
+  GN_CHECK_LAUNCH(name);
   return GN_OK;
+}
+
+extern "C" int gn_block_pair_fwd(const float* pw, int w, const float* feats,
+                                 const float* nfeats, int r, const int32_t* pair_c,
+                                 const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                                 const float* w1, const float* b1, const float* w2,
+                                 const float* b2, int f, float* pooled, gn_stream_t stream) {
+  return launch_block_pair("gn_block_pair_fwd", false, pw, w, feats, nfeats, r, pair_c, pair_n,
+                           num_pairs, capacity, w1, b1, w2, b2, f, pooled, stream);
+}
+
+extern "C" int gn_block_pair_fwd_hl(const float* pw, int w, const void* feats_hl,
+                                    const void* nfeats_hl, int r, const int32_t* pair_c,
+                                    const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                                    const float* w1, const float* b1, const float* w2,
+                                    const float* b2, int f, float* pooled, gn_stream_t stream) {
+  return launch_block_pair("gn_block_pair_fwd_hl", true, pw, w, feats_hl, nfeats_hl, r, pair_c,
+                           pair_n, num_pairs, capacity, w1, b1, w2, b2, f, pooled, stream);
 }

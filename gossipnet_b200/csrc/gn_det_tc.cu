@@ -1,0 +1,348 @@
+// Detection-level layers of a Gnet block on the tensor cores, fused across the
+// block boundary (network.py:344-409):
+//
+//   stage A (post-pool of block b, skipped when `pooled` is null)
+//     d1        = relu(pooled @ W_fc1 + b_fc1)                      64 -> 64    (:390-397)
+//     feats_out = relu(feats_in + d1 @ W_fc2 + b_fc2)               64 -> 128   (:399-408)
+//     pooled   <- 0   (the next block max-accumulates into it with atomicMax)
+//   stage B (reduce_dim of block b+1, skipped when `w_rd` is null)
+//     red       = relu(feats_out @ W_rd + b_rd)                     128 -> 32   (:348-354)
+//     written as fp32 [T,32] and/or as bf16 (hi | lo) rows [T,64]: the operand
+//     format the pair kernel copies straight into its A tile.
+//
+// Tile = 128 detections = M of one tcgen05.mma; persistent CTAs, weights (hi/lo,
+// K-major) staged once per CTA.  Every GEMM is bf16x3 with fp32 accumulation in
+// TMEM (gn_umma.cuh); epilogues run on 8 warps (TMEM lane quadrant = warp % 4,
+// column half = warp / 4) and write the next GEMM's A operand back to shared
+// memory, so one tile makes a single pass over HBM: read pooled + feats_in, write
+// feats_out + red.
+#include "gn_common.cuh"
+#include "gn_umma.cuh"
+
+namespace gn {
+
+constexpr int DT_TILE = 128, DT_THREADS = 256;
+constexpr int DT_D = 128, DT_F = 64, DT_R = 32;       // shortcut, pairfeat, reduced dims
+constexpr uint32_t DT_SBO = 128;
+constexpr uint32_t DT_LBO_A = DT_TILE * 16 + 32;      // skewed like the pair kernel's A tile
+constexpr uint32_t DT_OFF_W1H = 0;                                   // fc1^T: 8 chunks x 64 rows
+constexpr uint32_t DT_OFF_W1L = DT_OFF_W1H + 8 * DT_F * 16;
+constexpr uint32_t DT_OFF_W2H = DT_OFF_W1L + 8 * DT_F * 16;          // fc2^T: 8 chunks x 128 rows
+constexpr uint32_t DT_OFF_W2L = DT_OFF_W2H + 8 * DT_D * 16;
+constexpr uint32_t DT_OFF_WRH = DT_OFF_W2L + 8 * DT_D * 16;          // rd^T: 16 chunks x 32 rows
+constexpr uint32_t DT_OFF_WRL = DT_OFF_WRH + 16 * DT_R * 16;
+constexpr uint32_t DT_OFF_A = DT_OFF_WRL + 16 * DT_R * 16;           // 65536
+constexpr uint32_t DT_A_BYTES = 2 * 16 * DT_LBO_A;                   // K up to 128, hi + lo
+constexpr uint32_t DT_OFF_BIAS = DT_OFF_A + DT_A_BYTES;              // b_fc1[64] b_fc2[128] b_rd[32]
+constexpr uint32_t DT_OFF_BAR = DT_OFF_BIAS + (DT_F + DT_D + DT_R) * 4;
+constexpr uint32_t DT_SMEM = DT_OFF_BAR + 16;
+static_assert(DT_SMEM <= 227 * 1024, "det tile exceeds shared memory");
+
+// transpose + split w[k_total, n_total] (fp32, [in,out]) into K-major hi/lo tiles
+__device__ __forceinline__ void dt_stage_weight(const float* __restrict__ w, int k_total,
+                                                int n_total, unsigned char* hi, unsigned char* lo,
+                                                int t) {
+  const int chunks = k_total / 8;
+  for (int u = t; u < chunks * n_total; u += DT_THREADS) {
+    const int n = u % n_total, j = u / n_total;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = __ldg(w + (size_t)(j * 8 + e) * n_total + n);
+    uint4 h, l;
+    umma::split_bf16x2(x[0], x[1], h.x, l.x);
+    umma::split_bf16x2(x[2], x[3], h.y, l.y);
+    umma::split_bf16x2(x[4], x[5], h.z, l.z);
+    umma::split_bf16x2(x[6], x[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + (size_t)j * n_total * 16 + n * 16) = h;
+    *reinterpret_cast<uint4*>(lo + (size_t)j * n_total * 16 + n * 16) = l;
+  }
+}
+
+// load a [128 x width] fp32 tile (row pitch = width floats) into the A operand region
+template <int WIDTH>
+__device__ __forceinline__ void dt_load_tile(const float* __restrict__ src, int row0, int rows,
+                                             unsigned char* a_hi, unsigned char* a_lo, int warp,
+                                             int lane, float* __restrict__ zero_after) {
+  constexpr int PIECES = WIDTH / 8;           // 8-float pieces per row
+  constexpr int ROWS_PER_REQ = 32 / (PIECES < 32 ? PIECES : 32);
+  // lane -> (row within request, piece): a warp request covers whole rows (coalesced)
+  for (int base = warp * ROWS_PER_REQ; base < DT_TILE; base += (DT_THREADS / 32) * ROWS_PER_REQ) {
+    const int r = base + lane / PIECES, q = lane % PIECES;
+    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+    if (row0 + r < rows) {
+      const float* p = src + (size_t)(row0 + r) * WIDTH + q * 8;
+      v0 = ldg4(p);
+      v1 = ldg4(p + 4);
+      if (zero_after != nullptr) {
+        float* z = zero_after + (size_t)(row0 + r) * WIDTH + q * 8;
+        *reinterpret_cast<float4*>(z) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(z + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    uint4 h, l;
+    umma::split_bf16x2(v0.x, v0.y, h.x, l.x);
+    umma::split_bf16x2(v0.z, v0.w, h.y, l.y);
+    umma::split_bf16x2(v1.x, v1.y, h.z, l.z);
+    umma::split_bf16x2(v1.z, v1.w, h.w, l.w);
+    const uint32_t off = (uint32_t)q * DT_LBO_A + (uint32_t)r * 16;
+    *reinterpret_cast<uint4*>(a_hi + off) = h;
+    *reinterpret_cast<uint4*>(a_lo + off) = l;
+  }
+}
+
+// bf16x3 GEMM: D[tmem] = A[128 x K] (smem) * B[N x K]^T (smem); issued by one thread
+__device__ __forceinline__ void dt_gemm(uint32_t tmem_d, uint32_t sa_hi, uint32_t sa_lo,
+                                        uint32_t sb_hi, uint32_t sb_lo, uint32_t lbo_b, int ksteps,
+                                        uint32_t idesc) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t dah = umma::smem_desc(sa_hi + ks * 2 * DT_LBO_A, DT_LBO_A, DT_SBO);
+    const uint64_t dal = umma::smem_desc(sa_lo + ks * 2 * DT_LBO_A, DT_LBO_A, DT_SBO);
+    const uint64_t dbh = umma::smem_desc(sb_hi + ks * 2 * lbo_b, lbo_b, DT_SBO);
+    const uint64_t dbl = umma::smem_desc(sb_lo + ks * 2 * lbo_b, lbo_b, DT_SBO);
+    umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, ks > 0);
+    umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1);
+    umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, 1);
+  }
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1)
+block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_in,
+                    const float* __restrict__ w_fc1, const float* __restrict__ b_fc1,
+                    const float* __restrict__ w_fc2, const float* __restrict__ b_fc2,
+                    const float* __restrict__ w_rd, const float* __restrict__ b_rd,
+                    float* __restrict__ feats_out, float* __restrict__ red_f32,
+                    __nv_bfloat16* __restrict__ red_hl, int num_dets) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint32_t tmem_base_s;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int num_tiles = (num_dets + DT_TILE - 1) / DT_TILE;
+  if ((int)blockIdx.x >= num_tiles) return;
+  const bool stage_a = pooled != nullptr, stage_b = w_rd != nullptr;
+
+  unsigned char* a_hi = smem + DT_OFF_A;
+  unsigned char* a_lo = a_hi + 16 * DT_LBO_A;
+  float* bias1 = reinterpret_cast<float*>(smem + DT_OFF_BIAS);
+  float* bias2 = bias1 + DT_F;
+  float* biasr = bias2 + DT_D;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + DT_OFF_BAR);
+
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
+  if (t == 0) {
+    umma::mbar_init(bar, 1);
+    umma::fence_barrier_init();
+  }
+  if (stage_a) {
+    dt_stage_weight(w_fc1, DT_F, DT_F, smem + DT_OFF_W1H, smem + DT_OFF_W1L, t);
+    dt_stage_weight(w_fc2, DT_F, DT_D, smem + DT_OFF_W2H, smem + DT_OFF_W2L, t);
+    if (t < DT_F) bias1[t] = __ldg(b_fc1 + t);
+    if (t < DT_D) bias2[t] = __ldg(b_fc2 + t);
+  }
+  if (stage_b) {
+    dt_stage_weight(w_rd, DT_D, DT_R, smem + DT_OFF_WRH, smem + DT_OFF_WRL, t);
+    if (t < DT_R) biasr[t] = __ldg(b_rd + t);
+  }
+  umma::fence_smem_to_async();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tm1 = tmem, tm2 = tmem + 64, tmr = tmem + 192;
+  const uint32_t sa_hi = umma::smem_u32(a_hi), sa_lo = umma::smem_u32(a_lo);
+  const uint32_t s_w1h = umma::smem_u32(smem + DT_OFF_W1H), s_w1l = umma::smem_u32(smem + DT_OFF_W1L);
+  const uint32_t s_w2h = umma::smem_u32(smem + DT_OFF_W2H), s_w2l = umma::smem_u32(smem + DT_OFF_W2L);
+  const uint32_t s_wrh = umma::smem_u32(smem + DT_OFF_WRH), s_wrl = umma::smem_u32(smem + DT_OFF_WRL);
+  const int erow = (warp & 3) * 32 + lane;
+  const int ehalf = warp >> 2;
+  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+  uint32_t par = 0;
+
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int row0 = tile * DT_TILE;
+    const int grow = row0 + erow;
+    const bool live = grow < num_dets;
+
+    if (stage_a) {
+      // ---- pooled tile -> A (K = 64); pooled <- 0 for the next block ----------------
+      dt_load_tile<DT_F>(pooled, row0, num_dets, a_hi, a_lo, warp, lane, pooled);
+      umma::fence_smem_to_async();
+      umma::tc_fence_before();
+      __syncthreads();
+      if (t == 0) {
+        umma::tc_fence_after();
+        dt_gemm(tm1, sa_hi, sa_lo, s_w1h, s_w1l, DT_F * 16, DT_F / 16, umma::idesc_bf16_f32(DT_TILE, DT_F));
+        umma::mma_commit(bar);
+      }
+      umma::mbar_wait(bar, par);
+      par ^= 1;
+      umma::tc_fence_after();
+      // ---- d1 = relu(acc + b_fc1) -> A (K = 64) ---------------------------------------
+#pragma unroll
+      for (int cc = 0; cc < 32; cc += 16) {
+        const int col0 = ehalf * 32 + cc;
+        float v[16];
+        umma::tmem_ld16(tm1 + tlane + col0, v);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] = fmaxf(v[g * 8 + e] + bias1[col0 + g * 8 + e], 0.f);
+          uint4 h, l;
+          umma::split_bf16x2(x[0], x[1], h.x, l.x);
+          umma::split_bf16x2(x[2], x[3], h.y, l.y);
+          umma::split_bf16x2(x[4], x[5], h.z, l.z);
+          umma::split_bf16x2(x[6], x[7], h.w, l.w);
+          const uint32_t off = (uint32_t)((col0 >> 3) + g) * DT_LBO_A + (uint32_t)erow * 16;
+          *reinterpret_cast<uint4*>(a_hi + off) = h;
+          *reinterpret_cast<uint4*>(a_lo + off) = l;
+        }
+      }
+      umma::fence_smem_to_async();
+      umma::tc_fence_before();
+      __syncthreads();
+      if (t == 0) {
+        umma::tc_fence_after();
+        dt_gemm(tm2, sa_hi, sa_lo, s_w2h, s_w2l, DT_D * 16, DT_F / 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
+        umma::mma_commit(bar);
+      }
+      umma::mbar_wait(bar, par);
+      par ^= 1;
+      umma::tc_fence_after();
+      // ---- feats_out = relu(feats_in + acc + b_fc2) -> global, and -> A (K = 128) ------
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 16) {
+        const int col0 = ehalf * 64 + cc;
+        float v[16];
+        umma::tmem_ld16(tm2 + tlane + col0, v);
+        float4 res[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          res[g] = live ? ldg4(feats_in + (size_t)grow * DT_D + col0 + g * 4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        umma::tmem_ld_wait();
+        float x[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          x[g * 4 + 0] = fmaxf(res[g].x + (v[g * 4 + 0] + bias2[col0 + g * 4 + 0]), 0.f);
+          x[g * 4 + 1] = fmaxf(res[g].y + (v[g * 4 + 1] + bias2[col0 + g * 4 + 1]), 0.f);
+          x[g * 4 + 2] = fmaxf(res[g].z + (v[g * 4 + 2] + bias2[col0 + g * 4 + 2]), 0.f);
+          x[g * 4 + 3] = fmaxf(res[g].w + (v[g * 4 + 3] + bias2[col0 + g * 4 + 3]), 0.f);
+        }
+        if (live) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(feats_out + (size_t)grow * DT_D + col0 + g * 4) =
+                make_float4(x[g * 4 + 0], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
+        }
+        if (stage_b) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 h, l;
+            umma::split_bf16x2(x[g * 8 + 0], x[g * 8 + 1], h.x, l.x);
+            umma::split_bf16x2(x[g * 8 + 2], x[g * 8 + 3], h.y, l.y);
+            umma::split_bf16x2(x[g * 8 + 4], x[g * 8 + 5], h.z, l.z);
+            umma::split_bf16x2(x[g * 8 + 6], x[g * 8 + 7], h.w, l.w);
+            const uint32_t off = (uint32_t)((col0 >> 3) + g) * DT_LBO_A + (uint32_t)erow * 16;
+            *reinterpret_cast<uint4*>(a_hi + off) = h;
+            *reinterpret_cast<uint4*>(a_lo + off) = l;
+          }
+        }
+      }
+    } else {
+      // block 1 / stand-alone reduce: feats_in tile -> A (K = 128)
+      dt_load_tile<DT_D>(feats_in, row0, num_dets, a_hi, a_lo, warp, lane, nullptr);
+    }
+
+    if (stage_b) {
+      umma::fence_smem_to_async();
+      umma::tc_fence_before();
+      __syncthreads();
+      if (t == 0) {
+        umma::tc_fence_after();
+        dt_gemm(tmr, sa_hi, sa_lo, s_wrh, s_wrl, DT_R * 16, DT_D / 16, umma::idesc_bf16_f32(DT_TILE, DT_R));
+        umma::mma_commit(bar);
+      }
+      umma::mbar_wait(bar, par);
+      par ^= 1;
+      umma::tc_fence_after();
+      // ---- red = relu(acc + b_rd): 16 columns per thread --------------------------------
+      {
+        const int col0 = ehalf * 16;
+        float v[16];
+        umma::tmem_ld16(tmr + tlane + col0, v);
+        umma::tmem_ld_wait();
+        float x[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) x[e] = fmaxf(v[e] + biasr[col0 + e], 0.f);
+        if (live) {
+          if (red_f32 != nullptr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<float4*>(red_f32 + (size_t)grow * DT_R + col0 + g * 4) =
+                  make_float4(x[g * 4 + 0], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
+          }
+          if (red_hl != nullptr) {
+            // row layout: [32 hi | 32 lo] bf16 = 128 B; this thread owns 16 of the 32
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint4 h, l;
+              umma::split_bf16x2(x[g * 8 + 0], x[g * 8 + 1], h.x, l.x);
+              umma::split_bf16x2(x[g * 8 + 2], x[g * 8 + 3], h.y, l.y);
+              umma::split_bf16x2(x[g * 8 + 4], x[g * 8 + 5], h.z, l.z);
+              umma::split_bf16x2(x[g * 8 + 6], x[g * 8 + 7], h.w, l.w);
+              __nv_bfloat16* row = red_hl + (size_t)grow * 2 * DT_R;
+              *reinterpret_cast<uint4*>(row + col0 + g * 8) = h;
+              *reinterpret_cast<uint4*>(row + DT_R + col0 + g * 8) = l;
+            }
+          }
+        }
+      }
+    }
+    umma::tc_fence_before();
+    __syncthreads();   // A region and TMEM columns are reused by the next tile
+  }
+
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace gn
+
+extern "C" int gn_block_det_fwd(float* pooled, const float* feats_in, const float* w_fc1,
+                                const float* b_fc1, const float* w_fc2, const float* b_fc2,
+                                const float* w_rd, const float* b_rd, float* feats_out,
+                                float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
+                                int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
+  GN_REQUIRE(num_dets >= 0, "gn_block_det_fwd: negative size");
+  if (shortcut_dim != gn::DT_D || pairfeat_dim != gn::DT_F || reduced_dim != gn::DT_R) {
+    gn::set_error("gn_block_det_fwd: fused kernel is built for d=%d f=%d r=%d (got %d, %d, %d)",
+                  gn::DT_D, gn::DT_F, gn::DT_R, shortcut_dim, pairfeat_dim, reduced_dim);
+    return GN_ERR_UNSUPPORTED;
+  }
+  if (num_dets == 0) return GN_OK;
+  GN_REQUIRE(feats_in != nullptr, "gn_block_det_fwd: null feats_in");
+  GN_REQUIRE(pooled != nullptr || w_rd != nullptr, "gn_block_det_fwd: nothing to do");
+  GN_REQUIRE(pooled == nullptr || (w_fc1 && b_fc1 && w_fc2 && b_fc2 && feats_out),
+             "gn_block_det_fwd: stage A needs fc1 / fc2 parameters and feats_out");
+  GN_REQUIRE(w_rd == nullptr || (b_rd && (red_f32 || red_hl)),
+             "gn_block_det_fwd: stage B needs b_rd and an output");
+  GN_REQUIRE((((uintptr_t)pooled | (uintptr_t)feats_in | (uintptr_t)feats_out |
+               (uintptr_t)red_f32 | (uintptr_t)red_hl) & 15) == 0,
+             "gn_block_det_fwd: pointers must be 16-byte aligned");
+  cudaError_t e = cudaFuncSetAttribute(gn::block_det_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn::DT_SMEM);
+  if (e != cudaSuccess) {
+    gn::set_error("gn_block_det_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
+  int grid = gn::ceil_div(num_dets, gn::DT_TILE);
+  const int sms = gn::sm_count();
+  if (grid > sms) grid = sms;
+  gn::block_det_tc_kernel<<<grid, gn::DT_THREADS, gn::DT_SMEM, (cudaStream_t)stream>>>(
+      pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd, feats_out, red_f32,
+      static_cast<__nv_bfloat16*>(red_hl), num_dets);
+  GN_CHECK_LAUNCH("gn_block_det_fwd");
+  return GN_OK;
+}

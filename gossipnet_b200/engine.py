@@ -67,6 +67,9 @@ class GnetEngine(object):
                          and g.pwfeat_narrow_dim == 32)
         self.fused_block = (self.pw_width == 32 and g.reduced_dim == 32
                             and g.pairfeat_dim == 64 and g.num_block_pw_fc == 2)
+        # detection-level layers fused across the block boundary (gn_block_det_fwd)
+        self.fused_det = (self.fused_block and g.shortcut_dim == 128 and g.num_block_fc == 2
+                          and not g.neighbor_feats)
         self.capacity = 0
         self._ws = {}
         self.keep_block_feats = False
@@ -184,6 +187,32 @@ class GnetEngine(object):
         # last FC has no activation; shortcut: relu(infeats + feats) (:399-408)
         return self._fc(x, s + 'fc%d' % g['num_block_fc'], True, residual=infeats, out=out)
 
+    def _blocks_fused(self, feats, pair_c, pair_n, num_pairs, cap, pw, block_feats):
+        """All blocks with two launches each: the tensor-core pair stage and the
+        fused detection-level kernel (fc1, fc2, shortcut of block b + reduce_dim of
+        block b+1); reduced features travel as bf16 (hi | lo) operand rows."""
+        g, p = self.g, self.p
+        T, d = feats.shape
+        pooled = self._buf('pooled', (T, g['pairfeat_dim']))
+        pooled.zero_()   # every det launch re-zeroes it; this covers a dirty workspace
+        red_hl = self._buf('red_hl', (T, 2 * g['reduced_dim']), torch.bfloat16)
+        wb = lambda scope: (p[scope + '/weights'], p[scope + '/biases'])
+        ops.block_det_fwd(None, feats, None, None, wb('gnet/block1/reduce_dim'), red_hl=red_hl)
+        nb = g['num_blocks']
+        for b in range(1, nb + 1):
+            s = 'gnet/block%d/' % b
+            ops.block_pair_fwd(pw, red_hl, red_hl, pair_c, pair_n, num_pairs, cap,
+                               p[s + 'pw_fc1/weights'], p[s + 'pw_fc1/biases'],
+                               p[s + 'pw_fc2/weights'], p[s + 'pw_fc2/biases'], pooled)
+            out = self._buf('feats%d' % (b % 2), (T, d))
+            rd = wb('gnet/block%d/reduce_dim' % (b + 1)) if b < nb else None
+            ops.block_det_fwd(pooled, feats, wb(s + 'fc1'), wb(s + 'fc2'), rd, feats_out=out,
+                              red_hl=red_hl if rd is not None else None)
+            feats = out
+            if block_feats is not None:
+                block_feats.append(feats.clone())
+        return feats
+
     def predict(self, feats):
         """A8: two LINEAR layers then the logit (network.py:257-273)."""
         g = self.g
@@ -209,11 +238,14 @@ class GnetEngine(object):
         feats = self._buf('feats0', (T, d))
         feats.zero_()  # network.py:241-246
         block_feats = [feats.clone()] if self.keep_block_feats else None
-        for b in range(1, g['num_blocks'] + 1):
-            out = self._buf('feats%d' % (b % 2), (T, d))
-            feats = self.block(b, feats, row_ptr, pair_c, pair_n, num_pairs, cap, pw, out)
-            if self.keep_block_feats:
-                block_feats.append(feats.clone())
+        if self.fused_det and self.use_fused and self.use_tensor_cores and g['num_blocks'] > 0:
+            feats = self._blocks_fused(feats, pair_c, pair_n, num_pairs, cap, pw, block_feats)
+        else:
+            for b in range(1, g['num_blocks'] + 1):
+                out = self._buf('feats%d' % (b % 2), (T, d))
+                feats = self.block(b, feats, row_ptr, pair_c, pair_n, num_pairs, cap, pw, out)
+                if self.keep_block_feats:
+                    block_feats.append(feats.clone())
         prediction = self.predict(feats)
         res = dict(prediction=prediction, row_ptr=row_ptr, num_pairs=num_pairs, pair_c=pair_c,
                    pair_n=pair_n, pair_iou=pair_iou, pw_feats=pw, feats=feats, capacity=cap)

@@ -179,12 +179,41 @@ def block_pair_fwd(pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, w1, b
     """pooled[num_dets,f] must be zero-filled; it is max-accumulated in place.
     ffma=True runs the fp32 CUDA-core variant instead of the tensor-core kernel."""
     f32 = torch.float32
+    if feats.dtype == torch.bfloat16:
+        # bf16 (hi | lo) rows from block_det_fwd: [num_dets, 2r]
+        r = feats.shape[1] // 2
+        _lib.call('gn_block_pair_fwd_hl', _chk(pw, f32, 'pw'), pw.shape[1],
+                  _chk(feats, torch.bfloat16, 'feats_hl'), _chk(nfeats, torch.bfloat16, 'nfeats_hl'),
+                  r, _chk(pair_c, torch.int32, 'pair_c'), _chk(pair_n, torch.int32, 'pair_n'),
+                  _chk(num_pairs, torch.int32, 'num_pairs'), int(capacity), _chk(w1, f32, 'w1'),
+                  _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2'), _chk(b2, f32, 'b2'), w2.shape[1],
+                  _chk(pooled, f32, 'pooled'), _stream())
+        return pooled
     _lib.call('gn_block_pair_fwd_ffma' if ffma else 'gn_block_pair_fwd', _chk(pw, f32, 'pw'), pw.shape[1], _chk(feats, f32, 'feats'),
               _chk(nfeats, f32, 'nfeats'), feats.shape[1], _chk(pair_c, torch.int32, 'pair_c'),
               _chk(pair_n, torch.int32, 'pair_n'), _chk(num_pairs, torch.int32, 'num_pairs'),
               int(capacity), _chk(w1, f32, 'w1'), _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2'),
               _chk(b2, f32, 'b2'), w2.shape[1], _chk(pooled, f32, 'pooled'), _stream())
     return pooled
+
+
+def block_det_fwd(pooled, feats_in, fc1, fc2, rd, feats_out=None, red_f32=None, red_hl=None):
+    """Fused detection-level layers (see gn_block_det_fwd).  fc1 / fc2 / rd are
+    (weights, biases) pairs or None; pooled=None skips stage A, rd=None stage B."""
+    f32 = torch.float32
+    T, d = feats_in.shape
+    f = fc1[0].shape[0] if fc1 is not None else 64
+    r = rd[0].shape[1] if rd is not None else 32
+    nul = (None, None)
+    w1, b1 = fc1 if fc1 is not None else nul
+    w2, b2 = fc2 if fc2 is not None else nul
+    wr, br = rd if rd is not None else nul
+    _lib.call('gn_block_det_fwd', _chk(pooled, f32, 'pooled', True), _chk(feats_in, f32, 'feats_in'),
+              _chk(w1, f32, 'w_fc1', True), _chk(b1, f32, 'b_fc1', True),
+              _chk(w2, f32, 'w_fc2', True), _chk(b2, f32, 'b_fc2', True),
+              _chk(wr, f32, 'w_rd', True), _chk(br, f32, 'b_rd', True),
+              _chk(feats_out, f32, 'feats_out', True), _chk(red_f32, f32, 'red_f32', True),
+              _chk(red_hl, torch.bfloat16, 'red_hl', True), T, d, f, r, _stream())
 
 
 # ---------------------------------------------------------------- matching, loss
@@ -306,6 +335,10 @@ def _roi_args(bottom_data, bottom_rois):
 
 def roi_pool_fwd(bottom_data, bottom_rois, pooled_height, pooled_width, spatial_scale):
     _roi_args(bottom_data, bottom_rois)
+    if pooled_height < 0:      # roi_pooling_op.cc:64-73
+        raise ValueError('Need pooled_height >= 0, got %d' % pooled_height)
+    if pooled_width < 0:
+        raise ValueError('Need pooled_width >= 0, got %d' % pooled_width)
     b, h, w, c = bottom_data.shape
     r = bottom_rois.shape[0]
     shape = (r, int(pooled_height), int(pooled_width), c)

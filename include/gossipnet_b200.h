@@ -158,6 +158,27 @@ int gn_block_pair_fwd(const float* pw, int w, const float* feats,
                       const int32_t* pair_n, const int32_t* num_pairs, int capacity,
                       const float* w1, const float* b1, const float* w2,
                       const float* b2, int f, float* pooled, gn_stream_t stream);
+/* gn_block_pair_fwd_hl: same kernel, but feats / nfeats are the bf16 rows
+ * [num_dets, 2r] = [r hi | r lo] that gn_block_det_fwd writes (hi = bf16(x),
+ * lo = bf16(x - hi)): the operand chunks are copied, not re-split per pair. */
+int gn_block_pair_fwd_hl(const float* pw, int w, const void* feats_hl,
+                         const void* nfeats_hl, int r, const int32_t* pair_c,
+                         const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                         const float* w1, const float* b1, const float* w2,
+                         const float* b2, int f, float* pooled, gn_stream_t stream);
+/* Detection-level layers fused across the block boundary (network.py:344-409), on
+ * the tensor cores:
+ *   stage A (pooled != NULL): d1 = relu(pooled @ w_fc1 + b_fc1);
+ *           feats_out = relu(feats_in + d1 @ w_fc2 + b_fc2); pooled <- 0
+ *   stage B (w_rd != NULL):   red = relu(X @ w_rd + b_rd), X = feats_out (or
+ *           feats_in when stage A is skipped); written to red_f32[num_dets, r]
+ *           and / or red_hl[num_dets, 2r] (bf16 hi | lo), either may be NULL.
+ * Built for shortcut_dim 128, pairfeat_dim 64, reduced_dim 32, num_block_fc 2. */
+int gn_block_det_fwd(float* pooled, const float* feats_in, const float* w_fc1,
+                     const float* b_fc1, const float* w_fc2, const float* b_fc2,
+                     const float* w_rd, const float* b_rd, float* feats_out,
+                     float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
+                     int pairfeat_dim, int reduced_dim, gn_stream_t stream);
 /* Same contract, evaluated with fp32 FFMA on the CUDA cores (no tensor cores):
  * the in-library cross-check of gn_block_pair_fwd's bf16x3 tensor-core product. */
 int gn_block_pair_fwd_ffma(const float* pw, int w, const float* feats,

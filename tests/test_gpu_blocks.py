@@ -153,3 +153,36 @@ def test_unsupported_fused_shape_is_reported():
         ops.block_pair_fwd(z, z, z, i, i, i[:1], 8, torch.zeros((48, 64), device='cuda'),
                            torch.zeros(64, device='cuda'), torch.zeros((64, 64), device='cuda'),
                            torch.zeros(64, device='cuda'), torch.zeros((8, 64), device='cuda'))
+
+
+@pytest.mark.parametrize('n', [1, 100, 128, 1000, 3001])
+def test_fused_det_level_kernel(n):
+    """gn_block_det_fwd (fc1, fc2, shortcut, next reduce_dim on the tensor cores) vs float64."""
+    rs = np.random.RandomState(n)
+    pooled = np.maximum(rs.normal(0, 1, (n, 64)), 0).astype(F32)
+    feats = np.maximum(rs.normal(0, 1, (n, 128)), 0).astype(F32)
+    mk = lambda k, m: (rs.normal(0, 0.15, (k, m)).astype(F32), rs.normal(0, 0.1, m).astype(F32))
+    fc1, fc2, rd = mk(64, 64), mk(64, 128), mk(128, 32)
+    d1 = np.maximum(pooled.astype(np.float64) @ fc1[0] + fc1[1], 0)
+    out = np.maximum(feats + d1 @ fc2[0] + fc2[1], 0)
+    red = np.maximum(out @ rd[0] + rd[1], 0)
+    dv = lambda pair: (dev(pair[0]), dev(pair[1]))
+    d_pooled = dev(pooled)
+    feats_out = torch.empty((n, 128), device='cuda')
+    red_f32 = torch.empty((n, 32), device='cuda')
+    red_hl = torch.empty((n, 64), dtype=torch.bfloat16, device='cuda')
+    ops.block_det_fwd(d_pooled, dev(feats), dv(fc1), dv(fc2), dv(rd), feats_out=feats_out,
+                      red_f32=red_f32, red_hl=red_hl)
+    assert torch.all(d_pooled == 0)                      # re-armed for the next atomicMax pass
+    assert rel_err(feats_out.cpu().numpy(), out) < 3e-5
+    assert rel_err(red_f32.cpu().numpy(), red) < 3e-5
+    hl = red_hl.float().cpu().numpy()
+    assert rel_err(hl[:, :32] + hl[:, 32:], red) < 3e-5  # hi + lo reconstructs the fp32 value
+    # stage B alone (block 1) and stage A alone (last block)
+    red2 = torch.empty((n, 32), device='cuda')
+    ops.block_det_fwd(None, dev(feats), None, None, dv(rd), red_f32=red2)
+    ref2 = np.maximum(feats.astype(np.float64) @ rd[0] + rd[1], 0)
+    assert rel_err(red2.cpu().numpy(), ref2) < 3e-5
+    out3 = torch.empty((n, 128), device='cuda')
+    ops.block_det_fwd(dev(pooled), dev(feats), dv(fc1), dv(fc2), None, feats_out=out3)
+    assert rel_err(out3.cpu().numpy(), out) < 3e-5

@@ -119,7 +119,8 @@ def test_static_block_matches_oracle():
     pairs = net.neighbor_pair_idxs
     infeats = net.block_feats[1]
     out = Gnet._block(2, infeats, None, None, pairs[:, 0], pairs[:, 1], net.pw_feats, None)
-    assert rel_err(out.cpu().numpy(), net.block_feats[2].cpu().numpy()) < 1e-6
+    # Gnet._block runs the fp32 det-level layers, the full forward the fused bf16x3 ones
+    assert rel_err(out.cpu().numpy(), net.block_feats[2].cpu().numpy()) < 3e-5
 
 
 def test_imfeats_is_rejected_loudly():
