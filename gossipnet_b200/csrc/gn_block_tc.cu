@@ -97,7 +97,7 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   unsigned char* h_lo = h_hi + TC_CH2 * TC_LBO_A;
   float* h2 = reinterpret_cast<float*>(smem + TC_OFF_A);        // aliases h1 (dead after FC2)
   int* c_idx = reinterpret_cast<int*>(smem + TC_OFF_IDX);
-  unsigned* seg_end = reinterpret_cast<unsigned*>(c_idx + TC_TILE);   // 4 x 32-row slices
+  unsigned* seg_end = reinterpret_cast<unsigned*>(c_idx + TC_TILE);   // 4 words: 8 x 16-row slices
   float* bias1 = reinterpret_cast<float*>(smem + TC_OFF_BIAS);
   float* bias2 = bias1 + TC_F;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
@@ -195,12 +195,12 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
     if (t < TC_TILE) {
       const int p = p0 + t;
       const int c = p < P ? __ldg(pair_c + p) : -1;
-      const int cnext = (p + 1 < P && (t & 31) != 31) ? __ldg(pair_c + p + 1) : -2;
+      const int cnext = (p + 1 < P && (t & 15) != 15) ? __ldg(pair_c + p + 1) : -2;
       c_idx[t] = c;
-      // a run ends where the next row has another c, at the end of its 32-row slice,
+      // a run ends where the next row has another c, at the end of its 16-row slice,
       // or at the last valid pair; rows past P never flush
       const unsigned m = __ballot_sync(0xffffffffu, c >= 0 && c != cnext);
-      if (lane == 0) seg_end[warp] = m;
+      if (lane == 0) seg_end[warp] = m;     // bits 0-15: slice 2*warp, bits 16-31: slice 2*warp+1
     }
 
     // ---- 1. fill A (hi / lo) from the prefetched registers ---------------------------
@@ -312,19 +312,24 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
     __syncthreads();
 
     // ---- 6. segmented max over the tile's rows ---------------------------------------
+    // thread = (16-row slice, column pair): one 8-byte shared load per row
     {
-      const int j = t & 63;            // column (a warp covers 32 columns of one slice)
-      const int r0 = (t >> 6) * 32;    // 32-row slice
-      const unsigned ends = seg_end[t >> 6];
+      const int j = (t & 31) * 2;      // columns j, j+1 (a warp covers all 64 columns of a slice)
+      const int slice = t >> 5;        // 8 slices of 16 rows
+      const int r0 = slice * 16;
+      const unsigned ends = (seg_end[slice >> 1] >> ((slice & 1) * 16)) & 0xffffu;
       const float* col = h2 + r0 * TC_LDH2 + j;
-      float cur = 0.f;
-#pragma unroll 8
-      for (int r = 0; r < 32; ++r) {
-        cur = fmaxf(cur, col[r * TC_LDH2]);
+      float cur0 = 0.f, cur1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 v = *reinterpret_cast<const float2*>(col + r * TC_LDH2);
+        cur0 = fmaxf(cur0, v.x);
+        cur1 = fmaxf(cur1, v.y);
         if ((ends >> r) & 1u) {        // warp uniform
-          atomicMax(reinterpret_cast<int*>(pooled + (size_t)c_idx[r0 + r] * TC_F + j),
-                    __float_as_int(cur));
-          cur = 0.f;
+          int* dst = reinterpret_cast<int*>(pooled + (size_t)c_idx[r0 + r] * TC_F + j);
+          atomicMax(dst, __float_as_int(cur0));
+          atomicMax(dst + 1, __float_as_int(cur1));
+          cur0 = cur1 = 0.f;
         }
       }
     }

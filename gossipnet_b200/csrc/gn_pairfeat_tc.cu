@@ -29,7 +29,7 @@ namespace gn {
 constexpr int PT_TILE = 128;
 constexpr int PT_THREADS = 256;
 constexpr int PT_H = 256, PT_O = 32;
-constexpr int PT_RING = 4;
+constexpr int PT_RING = 6;
 constexpr uint32_t PT_SBO = 128;
 constexpr uint32_t PT_LBO_A = PT_TILE * 16;      // activation / A1 chunk pitch (2048)
 constexpr uint32_t PT_LBO_W = PT_H * 16;         // 256-row weight chunk pitch (4096)
@@ -43,14 +43,14 @@ constexpr uint32_t PT_IMG_B3 = PT_IMG_B1 + 2 * 2 * PT_LBO_W; // hi 16 KB, lo 16 
 constexpr uint32_t PT_IMG_BYTES = PT_IMG_B3 + 2 * 32 * PT_LBO_W3;
 
 // shared memory map
-constexpr uint32_t PS_RING = 0;                                   // 4 x 16 KB
+constexpr uint32_t PS_RING = 0;                                   // PT_RING x 16 KB
 constexpr uint32_t PS_H = PS_RING + PT_RING * PT_STAGE;           // hi 32 KB + lo 32 KB
 constexpr uint32_t PS_B1 = PS_H + 2 * 16 * PT_LBO_A;              // 16 KB
 constexpr uint32_t PS_B3 = PS_B1 + 2 * 2 * PT_LBO_W;              // 32 KB
 constexpr uint32_t PS_A1 = PS_B3 + 2 * 32 * PT_LBO_W3;            // hi 4 KB + lo 4 KB
 constexpr uint32_t PS_BIAS = PS_A1 + 2 * 2 * PT_LBO_A;            // b1[256] b2[256] b3[32]
 constexpr uint32_t PS_ROW = PS_BIAS + (2 * PT_H + PT_O) * 4;      // sc[128] sn[128] rc[128] rn[128]
-constexpr uint32_t PS_BAR = PS_ROW + 4 * PT_TILE * 4;             // full[4] empty[4] done
+constexpr uint32_t PS_BAR = PS_ROW + 4 * PT_TILE * 4;             // full[R] empty[R] done
 constexpr uint32_t PS_BYTES = PS_BAR + 16 * 8;
 static_assert(PS_BYTES <= 227 * 1024, "pair MLP tile exceeds shared memory");
 
@@ -112,13 +112,15 @@ struct PtRing {
   uint32_t ring_smem;
   const unsigned char* w2img;
   uint32_t loads_issued, total_loads;
+  uint32_t k0;   // per-CTA rotation of the k-step order inside each K half (spreads the
+                 // CTAs over the L2 lines of the W2 image instead of all hitting the same one)
 
   // issue every W2 k-step load up to (exclusive) index `upto`
   __device__ __forceinline__ void fill(uint32_t upto) {
     while (loads_issued < upto && loads_issued < total_loads) {
       const uint32_t i = loads_issued, s = i % PT_RING;
       if (i >= PT_RING) umma::mbar_wait(&empty[s], ((i / PT_RING) - 1) & 1);
-      bulk_g2s(ring_smem + s * PT_STAGE, w2img + (size_t)(i & 15) * PT_STAGE, PT_STAGE, &full[s]);
+      bulk_g2s(ring_smem + s * PT_STAGE, w2img + (size_t)((i & 8u) | (((i & 7u) + k0) & 7u)) * PT_STAGE, PT_STAGE, &full[s]);
       ++loads_issued;
     }
   }
@@ -190,7 +192,8 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   const uint32_t s_b1h = umma::smem_u32(smem + PS_B1), s_b1l = s_b1h + 2 * PT_LBO_W;
   const uint32_t s_b3h = umma::smem_u32(smem + PS_B3), s_b3l = s_b3h + 32 * PT_LBO_W3;
 
-  PtRing ring{full, empty, s_ring, img + PT_IMG_W2, 0u, (uint32_t)my_tiles * 16u};
+  PtRing ring{full, empty, s_ring, img + PT_IMG_W2, 0u, (uint32_t)my_tiles * 16u,
+              0u};   // rotation off: results stay independent of the tile -> CTA mapping
   uint32_t mma_k = 0;     // W2 k-steps consumed so far (thread 0 only)
   uint32_t done_par = 0;  // parity of the next `done` completion (all threads)
   if (t == 0) ring.fill(PT_RING - 1);
@@ -320,8 +323,9 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
           umma::mbar_wait(&full[s], (g / PT_RING) & 1);
           umma::tc_fence_after();
           const uint32_t sb = s_ring + s * PT_STAGE;
-          const uint64_t dah = umma::smem_desc(s_hh + ksl * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
-          const uint64_t dal = umma::smem_desc(s_hl + ksl * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
+          const uint32_t ksr = ((uint32_t)ksl + ring.k0) & 7u;   // k-step this stage holds
+          const uint64_t dah = umma::smem_desc(s_hh + ksr * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
+          const uint64_t dal = umma::smem_desc(s_hl + ksr * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
           const uint64_t dbh = umma::smem_desc(sb, PT_LBO_W, PT_SBO);
           const uint64_t dbl = umma::smem_desc(sb + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
           const uint32_t acc = (half | ksl) != 0;

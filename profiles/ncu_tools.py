@@ -111,5 +111,39 @@ if __name__ == '__main__':
         launches(sys.argv[2])
     elif cmd == 'raw':
         raw(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
+    elif cmd == 'phases':
+        pass   # defined below
     else:
         stalls(sys.argv[2], sys.argv[3])
+
+
+def phases(path, sub):
+    """Stall samples / executed instructions between barrier-type SASS markers."""
+    out = subprocess.run(['ncu', '-i', path, '--page', 'source', '--csv', '-k', 'regex:' + sub],
+                         capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    his = [i for i, r in enumerate(rows) if 'Source' in r]
+    for hn, hi in enumerate(his):
+        hdr = rows[hi]
+        end = his[hn + 1] if hn + 1 < len(his) else len(rows)
+        si = [i for i, h in enumerate(hdr) if h.startswith('Warp Stall Sampling (All')][0]
+        ex, src = hdr.index('Instructions Executed'), hdr.index('Source')
+        data = [r for r in rows[hi + 1:end] if len(r) == len(hdr)]
+        tot = sum(float(r[si] or 0) for r in data)
+        print('=== launch %d: %d SASS lines, %d samples' % (hn, len(data), tot))
+        acc = inst = 0.0
+        start = 0
+        for i, r in enumerate(data):
+            acc += float(r[si] or 0)
+            inst += float(r[ex] or 0)
+            s = r[src]
+            if 'BAR.SYNC' in s or 'UTCBAR' in s or 'SYNCS.PHASECHK' in s or i == len(data) - 1:
+                if acc > tot * 0.004:
+                    print('%5d-%5d %7.0f %5.1f%%  inst=%10.0f  .. %s' % (
+                        start, i, acc, 100 * acc / max(tot, 1), inst, s.strip()[:46]))
+                acc = inst = 0.0
+                start = i + 1
+
+
+if __name__ == '__main__' and len(sys.argv) > 1 and sys.argv[1] == 'phases':
+    phases(sys.argv[2], sys.argv[3])
