@@ -123,6 +123,11 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   const uint32_t sh_hi = umma::smem_u32(h_hi), sh_lo = umma::smem_u32(h_lo);
   const uint32_t sb1h = umma::smem_u32(smem + TC_OFF_B1H), sb1l = umma::smem_u32(smem + TC_OFF_B1L);
   const uint32_t sb2h = umma::smem_u32(smem + TC_OFF_B2H), sb2l = umma::smem_u32(smem + TC_OFF_B2L);
+  // kernel-lifetime operand descriptors (k-step 0); the issue loops only add offsets
+  const uint64_t d_ah = umma::smem_desc(sa_hi, TC_LBO_A, TC_SBO), d_al = umma::smem_desc(sa_lo, TC_LBO_A, TC_SBO);
+  const uint64_t d_hh = umma::smem_desc(sh_hi, TC_LBO_A, TC_SBO), d_hl = umma::smem_desc(sh_lo, TC_LBO_A, TC_SBO);
+  const uint64_t d_b1h = umma::smem_desc(sb1h, TC_LBO_B, TC_SBO), d_b1l = umma::smem_desc(sb1l, TC_LBO_B, TC_SBO);
+  const uint64_t d_b2h = umma::smem_desc(sb2h, TC_LBO_B, TC_SBO), d_b2l = umma::smem_desc(sb2l, TC_LBO_B, TC_SBO);
 
   // epilogue mapping: TMEM lane quadrant = warp % 4, column half = warp / 4
   const int erow = (warp & 3) * 32 + lane;
@@ -233,15 +238,9 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
     if (t == 0) {
       umma::tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < TC_K1 / 16; ++ks) {
-        const uint64_t dah = umma::smem_desc(sa_hi + ks * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
-        const uint64_t dal = umma::smem_desc(sa_lo + ks * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
-        const uint64_t dbh = umma::smem_desc(sb1h + ks * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
-        const uint64_t dbl = umma::smem_desc(sb1l + ks * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
-        umma::mma_bf16_ss(tmem_d1, dal, dbh, idesc, ks > 0);
-        umma::mma_bf16_ss(tmem_d1, dah, dbl, idesc, 1);
-        umma::mma_bf16_ss(tmem_d1, dah, dbh, idesc, 1);
-      }
+      for (int ks = 0; ks < TC_K1 / 16; ++ks)
+        umma::mma_bf16x3(tmem_d1, d_ah, d_al, d_b1h, d_b1l, ks * (2 * TC_LBO_A >> 4),
+                         ks * (2 * TC_LBO_B >> 4), idesc, ks > 0);
       umma::mma_commit(bar);
     }
     prefetch(tile + gridDim.x);          // data of the next tile (its indices are here already)
@@ -279,15 +278,9 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
     if (t == 0) {
       umma::tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < TC_F / 16; ++ks) {
-        const uint64_t dah = umma::smem_desc(sh_hi + ks * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
-        const uint64_t dal = umma::smem_desc(sh_lo + ks * 2 * TC_LBO_A, TC_LBO_A, TC_SBO);
-        const uint64_t dbh = umma::smem_desc(sb2h + ks * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
-        const uint64_t dbl = umma::smem_desc(sb2l + ks * 2 * TC_LBO_B, TC_LBO_B, TC_SBO);
-        umma::mma_bf16_ss(tmem_d2, dal, dbh, idesc, ks > 0);
-        umma::mma_bf16_ss(tmem_d2, dah, dbl, idesc, 1);
-        umma::mma_bf16_ss(tmem_d2, dah, dbh, idesc, 1);
-      }
+      for (int ks = 0; ks < TC_F / 16; ++ks)
+        umma::mma_bf16x3(tmem_d2, d_hh, d_hl, d_b2h, d_b2l, ks * (2 * TC_LBO_A >> 4),
+                         ks * (2 * TC_LBO_B >> 4), idesc, ks > 0);
       umma::mma_commit(bar);
     }
     umma::mbar_wait(bar, 1);

@@ -91,18 +91,14 @@ __device__ __forceinline__ void dt_load_tile(const float* __restrict__ src, int 
 }
 
 // bf16x3 GEMM: D[tmem] = A[128 x K] (smem) * B[N x K]^T (smem); issued by one thread
-__device__ __forceinline__ void dt_gemm(uint32_t tmem_d, uint32_t sa_hi, uint32_t sa_lo,
-                                        uint32_t sb_hi, uint32_t sb_lo, uint32_t lbo_b, int ksteps,
+template <int KSTEPS>
+__device__ __forceinline__ void dt_gemm(uint32_t tmem_d, uint64_t d_ah, uint64_t d_al,
+                                        uint64_t d_bh, uint64_t d_bl, uint32_t lbo_b,
                                         uint32_t idesc) {
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint64_t dah = umma::smem_desc(sa_hi + ks * 2 * DT_LBO_A, DT_LBO_A, DT_SBO);
-    const uint64_t dal = umma::smem_desc(sa_lo + ks * 2 * DT_LBO_A, DT_LBO_A, DT_SBO);
-    const uint64_t dbh = umma::smem_desc(sb_hi + ks * 2 * lbo_b, lbo_b, DT_SBO);
-    const uint64_t dbl = umma::smem_desc(sb_lo + ks * 2 * lbo_b, lbo_b, DT_SBO);
-    umma::mma_bf16_ss(tmem_d, dal, dbh, idesc, ks > 0);
-    umma::mma_bf16_ss(tmem_d, dah, dbl, idesc, 1);
-    umma::mma_bf16_ss(tmem_d, dah, dbh, idesc, 1);
-  }
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    umma::mma_bf16x3(tmem_d, d_ah, d_al, d_bh, d_bl, ks * (2 * DT_LBO_A >> 4),
+                     ks * (2 * lbo_b >> 4), idesc, ks > 0);
 }
 
 __global__ void __launch_bounds__(DT_THREADS, 1)
@@ -152,6 +148,10 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
   const uint32_t s_w1h = umma::smem_u32(smem + DT_OFF_W1H), s_w1l = umma::smem_u32(smem + DT_OFF_W1L);
   const uint32_t s_w2h = umma::smem_u32(smem + DT_OFF_W2H), s_w2l = umma::smem_u32(smem + DT_OFF_W2L);
   const uint32_t s_wrh = umma::smem_u32(smem + DT_OFF_WRH), s_wrl = umma::smem_u32(smem + DT_OFF_WRL);
+  const uint64_t d_ah = umma::smem_desc(sa_hi, DT_LBO_A, DT_SBO), d_al = umma::smem_desc(sa_lo, DT_LBO_A, DT_SBO);
+  const uint64_t d_w1h = umma::smem_desc(s_w1h, DT_F * 16, DT_SBO), d_w1l = umma::smem_desc(s_w1l, DT_F * 16, DT_SBO);
+  const uint64_t d_w2h = umma::smem_desc(s_w2h, DT_D * 16, DT_SBO), d_w2l = umma::smem_desc(s_w2l, DT_D * 16, DT_SBO);
+  const uint64_t d_wrh = umma::smem_desc(s_wrh, DT_R * 16, DT_SBO), d_wrl = umma::smem_desc(s_wrl, DT_R * 16, DT_SBO);
   const int erow = (warp & 3) * 32 + lane;
   const int ehalf = warp >> 2;
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
@@ -170,7 +170,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       __syncthreads();
       if (t == 0) {
         umma::tc_fence_after();
-        dt_gemm(tm1, sa_hi, sa_lo, s_w1h, s_w1l, DT_F * 16, DT_F / 16, umma::idesc_bf16_f32(DT_TILE, DT_F));
+        dt_gemm<DT_F / 16>(tm1, d_ah, d_al, d_w1h, d_w1l, DT_F * 16, umma::idesc_bf16_f32(DT_TILE, DT_F));
         umma::mma_commit(bar);
       }
       umma::mbar_wait(bar, par);
@@ -203,7 +203,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       __syncthreads();
       if (t == 0) {
         umma::tc_fence_after();
-        dt_gemm(tm2, sa_hi, sa_lo, s_w2h, s_w2l, DT_D * 16, DT_F / 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
+        dt_gemm<DT_F / 16>(tm2, d_ah, d_al, d_w2h, d_w2l, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
         umma::mma_commit(bar);
       }
       umma::mbar_wait(bar, par);
@@ -260,7 +260,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       __syncthreads();
       if (t == 0) {
         umma::tc_fence_after();
-        dt_gemm(tmr, sa_hi, sa_lo, s_wrh, s_wrl, DT_R * 16, DT_D / 16, umma::idesc_bf16_f32(DT_TILE, DT_R));
+        dt_gemm<DT_D / 16>(tmr, d_ah, d_al, d_wrh, d_wrl, DT_R * 16, umma::idesc_bf16_f32(DT_TILE, DT_R));
         umma::mma_commit(bar);
       }
       umma::mbar_wait(bar, par);

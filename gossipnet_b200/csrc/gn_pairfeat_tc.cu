@@ -37,8 +37,12 @@ constexpr uint32_t PT_LBO_W3 = PT_O * 16;        // 32-row weight chunk pitch (5
 constexpr uint32_t PT_STAGE = 2 * 2 * PT_LBO_W;  // one W2 k-step: (hi, lo) x 2 chunks = 16 KB
 
 // prepared weight image (global workspace), bytes
-constexpr uint32_t PT_IMG_W2 = 0;                            // 16 k-steps x 16 KB
-constexpr uint32_t PT_IMG_B1 = PT_IMG_W2 + 16 * PT_STAGE;    // hi 8 KB, lo 8 KB
+// The W2 image can be replicated (CTA i streams copy i % COPIES).  Measured: 8 copies
+// do not change the kernel time (profiles/r1_tc_kernels.md), so L2 line contention is
+// not what limits the W2 stream; one copy is kept.
+constexpr int PT_W2_COPIES = 1;
+constexpr uint32_t PT_IMG_W2 = 0;                            // COPIES x 16 k-steps x 16 KB
+constexpr uint32_t PT_IMG_B1 = PT_IMG_W2 + PT_W2_COPIES * 16 * PT_STAGE;   // hi 8 KB, lo 8 KB
 constexpr uint32_t PT_IMG_B3 = PT_IMG_B1 + 2 * 2 * PT_LBO_W; // hi 16 KB, lo 16 KB
 constexpr uint32_t PT_IMG_BYTES = PT_IMG_B3 + 2 * 32 * PT_LBO_W3;
 
@@ -73,8 +77,11 @@ __global__ void pwfeat_prepare_kernel(const float* __restrict__ w1, const float*
   for (int i = tid; i < PT_H * PT_H; i += nth) {
     const int k = i / PT_H, n = i - k * PT_H;
     const int ks = k >> 4, c = (k >> 3) & 1, e = k & 7;
-    unsigned char* st = img + PT_IMG_W2 + ks * PT_STAGE;
-    put_split(st, st + 2 * PT_LBO_W, c * PT_LBO_W + n * 16, e, __ldg(w2 + i));
+    const float x = __ldg(w2 + i);
+    for (int rep = 0; rep < PT_W2_COPIES; ++rep) {
+      unsigned char* st = img + PT_IMG_W2 + (rep * 16 + ks) * PT_STAGE;
+      put_split(st, st + 2 * PT_LBO_W, c * PT_LBO_W + n * 16, e, x);
+    }
   }
   // B1: 16 K rows selected from W1 (zero padded)
   const bool multi = num_classes > 1;
@@ -192,11 +199,21 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   const uint32_t s_b1h = umma::smem_u32(smem + PS_B1), s_b1l = s_b1h + 2 * PT_LBO_W;
   const uint32_t s_b3h = umma::smem_u32(smem + PS_B3), s_b3l = s_b3h + 32 * PT_LBO_W3;
 
-  PtRing ring{full, empty, s_ring, img + PT_IMG_W2, 0u, (uint32_t)my_tiles * 16u,
+  // kernel-lifetime operand descriptors; the issue loops only add start-address offsets
+  const uint64_t d_a1h = umma::smem_desc(s_a1h, PT_LBO_A, PT_SBO), d_a1l = umma::smem_desc(s_a1l, PT_LBO_A, PT_SBO);
+  const uint64_t d_b1h = umma::smem_desc(s_b1h, PT_LBO_W, PT_SBO), d_b1l = umma::smem_desc(s_b1l, PT_LBO_W, PT_SBO);
+  const uint64_t d_hh = umma::smem_desc(s_hh, PT_LBO_A, PT_SBO), d_hl = umma::smem_desc(s_hl, PT_LBO_A, PT_SBO);
+  const uint64_t d_ringh = umma::smem_desc(s_ring, PT_LBO_W, PT_SBO);
+  const uint64_t d_ringl = umma::smem_desc(s_ring + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
+  const uint64_t d_b3h = umma::smem_desc(s_b3h, PT_LBO_W3, PT_SBO), d_b3l = umma::smem_desc(s_b3l, PT_LBO_W3, PT_SBO);
+
+  PtRing ring{full, empty, s_ring,
+              img + PT_IMG_W2 + (size_t)(blockIdx.x % PT_W2_COPIES) * 16 * PT_STAGE, 0u, (uint32_t)my_tiles * 16u,
               0u};   // rotation off: results stay independent of the tile -> CTA mapping
   uint32_t mma_k = 0;     // W2 k-steps consumed so far (thread 0 only)
   uint32_t done_par = 0;  // parity of the next `done` completion (all threads)
-  if (t == 0) ring.fill(PT_RING - 1);
+  uint32_t load_target = PT_RING;   // W2 k-steps requested so far (producer thread only)
+  if (t == 32) ring.fill(load_target);
 
   // epilogue mapping: TMEM lane quadrant = warp % 4; within a 128-column half the
   // warp owns columns [64 * (warp / 4), +64)
@@ -302,11 +319,7 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
     // ---- layer 1 ------------------------------------------------------------------
     if (t == 0) {
       umma::tc_fence_after();
-      const uint64_t dah = umma::smem_desc(s_a1h, PT_LBO_A, PT_SBO), dal = umma::smem_desc(s_a1l, PT_LBO_A, PT_SBO);
-      const uint64_t dbh = umma::smem_desc(s_b1h, PT_LBO_W, PT_SBO), dbl = umma::smem_desc(s_b1l, PT_LBO_W, PT_SBO);
-      umma::mma_bf16_ss(tm_l1, dal, dbh, idesc256, 0);
-      umma::mma_bf16_ss(tm_l1, dah, dbl, idesc256, 1);
-      umma::mma_bf16_ss(tm_l1, dah, dbh, idesc256, 1);
+      umma::mma_bf16x3(tm_l1, d_a1h, d_a1l, d_b1h, d_b1l, 0, 0, idesc256, 0);
       umma::mma_commit(done);
     }
     wait_done();
@@ -322,20 +335,19 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
           const uint32_t g = mma_k++, s = g % PT_RING;
           umma::mbar_wait(&full[s], (g / PT_RING) & 1);
           umma::tc_fence_after();
-          const uint32_t sb = s_ring + s * PT_STAGE;
           const uint32_t ksr = ((uint32_t)ksl + ring.k0) & 7u;   // k-step this stage holds
-          const uint64_t dah = umma::smem_desc(s_hh + ksr * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
-          const uint64_t dal = umma::smem_desc(s_hl + ksr * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
-          const uint64_t dbh = umma::smem_desc(sb, PT_LBO_W, PT_SBO);
-          const uint64_t dbl = umma::smem_desc(sb + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
-          const uint32_t acc = (half | ksl) != 0;
-          umma::mma_bf16_ss(tm_l2, dal, dbh, idesc256, acc);
-          umma::mma_bf16_ss(tm_l2, dah, dbl, idesc256, 1);
-          umma::mma_bf16_ss(tm_l2, dah, dbh, idesc256, 1);
-          umma::mma_commit(&empty[s]);
-          ring.fill(g + PT_RING);   // keep RING-1 k-steps in flight behind the running one
+          umma::mma_bf16x3(tm_l2, d_hh, d_hl, d_ringh, d_ringl, ksr * (2 * PT_LBO_A >> 4),
+                           s * (PT_STAGE >> 4), idesc256, (half | ksl) != 0);
+          umma::mma_commit(&empty[s]);   // slot s is free once these UMMAs have run
         }
         umma::mma_commit(done);
+      } else if (t == 32) {
+        // W2 producer (its own thread, so the UMMA issuer never waits on a completion:
+        // the commit -> mbarrier latency would otherwise sit on the issue path of every
+        // k-step).  Refill every slot this round frees; the last wait resolves with the
+        // round's last UMMA.
+        load_target += 8;
+        ring.fill(load_target);
       }
       wait_done();
     }
@@ -349,14 +361,8 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
 #pragma unroll
         for (int ksl = 0; ksl < 8; ++ksl) {
           const int kc = (half * 8 + ksl) * 2;   // chunk index into W3^T
-          const uint64_t dah = umma::smem_desc(s_hh + ksl * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
-          const uint64_t dal = umma::smem_desc(s_hl + ksl * 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
-          const uint64_t dbh = umma::smem_desc(s_b3h + kc * PT_LBO_W3, PT_LBO_W3, PT_SBO);
-          const uint64_t dbl = umma::smem_desc(s_b3l + kc * PT_LBO_W3, PT_LBO_W3, PT_SBO);
-          const uint32_t acc = (half | ksl) != 0;
-          umma::mma_bf16_ss(tm_l3, dal, dbh, idesc32, acc);
-          umma::mma_bf16_ss(tm_l3, dah, dbl, idesc32, 1);
-          umma::mma_bf16_ss(tm_l3, dah, dbh, idesc32, 1);
+          umma::mma_bf16x3(tm_l3, d_hh, d_hl, d_b3h, d_b3l, ksl * (2 * PT_LBO_A >> 4),
+                           kc * (PT_LBO_W3 >> 4), idesc32, (half | ksl) != 0);
         }
         umma::mma_commit(done);
       }

@@ -112,3 +112,75 @@ extern "C" int gn_selftest_umma(const float* a, const float* w, float* c, int k,
   GN_CHECK_LAUNCH("gn_selftest_umma");
   return GN_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// Micro-benchmark: cycles per tcgen05.mma (M=128, K=16, bf16, SS mode, no-swizzle
+// K-major operands) for a given N, issued back to back by one thread.  out[0] =
+// cycles for `reps` UMMAs (clock64 around issue .. commit wait), out[1] = reps.
+// ---------------------------------------------------------------------------------
+namespace gn {
+__global__ void __launch_bounds__(128, 1)
+umma_rate_kernel(int n, int reps, int distinct_b, long long* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int t = threadIdx.x, warp = t >> 5;
+  // A: 2 chunks x 128 rows; B: distinct_b copies of 2 chunks x n rows
+  for (int i = t; i < (2 * 128 * 16 + distinct_b * 2 * n * 16) / 4; i += 128)
+    reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u + i;   // arbitrary finite bf16 pairs
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
+  if (t == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_barrier_init();
+  }
+  umma::fence_smem_to_async();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (t == 0) {
+    const uint32_t idesc = umma::idesc_bf16_f32(128, n);
+    const uint32_t sa = umma::smem_u32(smem), sb = sa + 2 * 128 * 16;
+    const uint64_t da = umma::smem_desc(sa, 128 * 16, 128);
+    const uint64_t db = umma::smem_desc(sb, n * 16, 128);
+    const uint32_t bstep = (2 * n * 16) >> 4;
+    const long long t0 = clock64();
+    // tight issue loop: 4 UMMAs per iteration over (up to) 4 distinct B tiles
+    const uint32_t m = (uint32_t)distinct_b - 1u;      // distinct_b in {1, 2, 4}
+    const uint64_t db0 = db, db1 = db + (1u & m) * bstep, db2 = db + (2u & m) * bstep,
+                   db3 = db + (3u & m) * bstep;
+    umma::mma_bf16_ss(tmem, da, db0, idesc, 0);
+    for (int r = 1; r + 4 <= reps; r += 4) {
+      umma::mma_bf16_ss(tmem, da, db1, idesc, 1);
+      umma::mma_bf16_ss(tmem, da, db2, idesc, 1);
+      umma::mma_bf16_ss(tmem, da, db3, idesc, 1);
+      umma::mma_bf16_ss(tmem, da, db0, idesc, 1);
+    }
+    umma::mma_commit(&bar);
+    umma::mbar_wait(&bar, 0);
+    out[0] = clock64() - t0;
+    out[1] = reps;
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+}  // namespace gn
+
+extern "C" int gn_selftest_umma_rate(int n, int reps, int distinct_b, int ctas, int64_t* out_dev,
+                                     gn_stream_t stream) {
+  GN_REQUIRE(n >= 16 && n <= 256 && n % 16 == 0 && reps > 4 && (distinct_b == 1 || distinct_b == 2 || distinct_b == 4) && ctas >= 1 &&
+                 out_dev, "gn_selftest_umma_rate: bad arguments");
+  const int smem = 2 * 128 * 16 + distinct_b * 2 * n * 16;
+  GN_REQUIRE(smem <= 200 * 1024, "gn_selftest_umma_rate: too many distinct B tiles");
+  cudaError_t e = cudaFuncSetAttribute(gn::umma_rate_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    gn::set_error("gn_selftest_umma_rate: %s", cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
+  gn::umma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(
+      n, reps, distinct_b, reinterpret_cast<long long*>(out_dev));
+  GN_CHECK_LAUNCH("gn_selftest_umma_rate");
+  return GN_OK;
+}

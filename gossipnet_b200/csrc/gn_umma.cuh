@@ -126,6 +126,21 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                ::"r"(smem_u32(bar)) : "memory");
 }
 
+// The three UMMAs of one bf16x3 k-step.  Descriptors are kernel-lifetime constants
+// plus a small start-address offset: `off16` values are byte offsets >> 4 added to
+// the 14-bit start-address field (shared memory is < 256 KB, so the sum never
+// carries into the neighbouring field).  Keeping the issue path this short matters:
+// ONE thread issues every UMMA of a CTA, and ~100 scalar instructions per k-step
+// (building descriptors from scratch) made that thread, not the tensor pipe, the
+// bottleneck of the first version of these kernels (profiles/r1_tc_kernels.md).
+__device__ __forceinline__ void mma_bf16x3(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo,
+                                           uint64_t b_hi, uint64_t b_lo, uint32_t a_off16,
+                                           uint32_t b_off16, uint32_t idesc, uint32_t accumulate) {
+  mma_bf16_ss(tmem_d, a_lo + a_off16, b_hi + b_off16, idesc, accumulate);
+  mma_bf16_ss(tmem_d, a_hi + a_off16, b_lo + b_off16, idesc, 1);
+  mma_bf16_ss(tmem_d, a_hi + a_off16, b_hi + b_off16, idesc, 1);
+}
+
 // ---- fp32 -> (hi, lo) bf16 split --------------------------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
