@@ -42,8 +42,14 @@ SIGNATURES = {
                           c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                           c_void_p, c_void_p],
     'gn_block_pair_fwd_hl': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                             c_void_p, c_void_p],
+                             c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int, c_void_p, c_void_p],
+    'gn_block_pair_image_bytes': [],
+    'gn_block_det_image_bytes': [],
+    'gn_prepare_operands': [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    'gn_block_det_fwd_img': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                             c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                             c_void_p],
     'gn_block_det_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                          c_void_p],
@@ -76,7 +82,9 @@ SIGNATURES = {
     'gn_selftest_umma': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     'gn_selftest_umma_rate': [c_int, c_int, c_int, c_int, c_void_p, c_void_p],
 }
-_RESTYPES = {'gn_last_error': ctypes.c_char_p, 'gn_pwfeat_prep_bytes': ctypes.c_int64}
+_RESTYPES = {'gn_last_error': ctypes.c_char_p, 'gn_pwfeat_prep_bytes': ctypes.c_int64,
+             'gn_block_pair_image_bytes': ctypes.c_int64,
+             'gn_block_det_image_bytes': ctypes.c_int64}
 
 _lib = None
 # number of C-ABI compute calls made so far (each is one kernel launch of this

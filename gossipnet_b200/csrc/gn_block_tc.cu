@@ -50,7 +50,7 @@ constexpr uint32_t TC_A_BYTES = 2 * TC_CH1 * TC_LBO_A;                   // hi +
 constexpr uint32_t TC_OFF_IDX = TC_OFF_A + TC_A_BYTES;                   // c[128], n[128]
 constexpr uint32_t TC_OFF_BIAS = TC_OFF_IDX + 2 * TC_TILE * 4;          // b1[64], b2[64]
 constexpr uint32_t TC_OFF_BAR = TC_OFF_BIAS + 2 * TC_F * 4;
-constexpr uint32_t TC_SMEM = TC_OFF_BAR + 16;
+constexpr uint32_t TC_SMEM = TC_OFF_BAR + 16;   // two mbarriers: UMMA completion, weight image
 static_assert(2 * TC_CH2 * TC_LBO_A <= TC_A_BYTES, "h1 operand tile must fit the A region");
 static_assert(TC_TILE * TC_LDH2 * 4 <= TC_A_BYTES, "h2 tile must fit the A region");
 static_assert(2 * TC_SMEM <= 227 * 1024, "two CTAs per SM");
@@ -83,7 +83,7 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
                      const int32_t* __restrict__ pair_n, const int32_t* __restrict__ num_pairs,
                      int capacity, const float* __restrict__ w1, const float* __restrict__ b1,
                      const float* __restrict__ w2, const float* __restrict__ b2,
-                     float* __restrict__ pooled) {
+                     const unsigned char* __restrict__ wimg, float* __restrict__ pooled) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -107,8 +107,20 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
     umma::mbar_init(bar, 1);
     umma::fence_barrier_init();
   }
-  stage_weight(w1, TC_CH1, smem + TC_OFF_B1H, smem + TC_OFF_B1L, t);
-  stage_weight(w2, TC_CH2, smem + TC_OFF_B2H, smem + TC_OFF_B2L, t);
+  uint64_t* wbar = bar + 1;
+  if (wimg != nullptr) {
+    // operand image prepared by gn_prepare_operands: [W1^T hi | lo | W2^T hi | lo], 40 KB,
+    // laid out exactly like the shared-memory region -> one bulk copy
+    if (t == 0) {
+      umma::mbar_init(wbar, 1);
+      umma::fence_barrier_init();
+      umma::mbar_expect_tx(wbar, TC_OFF_A);
+      umma::bulk_copy_g2s(umma::smem_u32(smem), wimg, TC_OFF_A, wbar);
+    }
+  } else {
+    stage_weight(w1, TC_CH1, smem + TC_OFF_B1H, smem + TC_OFF_B1L, t);
+    stage_weight(w2, TC_CH2, smem + TC_OFF_B2H, smem + TC_OFF_B2L, t);
+  }
   if (t < TC_F) {
     bias1[t] = __ldg(b1 + t);
     bias2[t] = __ldg(b2 + t);
@@ -192,6 +204,7 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   prefetch_idx(blockIdx.x);
   prefetch(blockIdx.x);
   prefetch_idx(blockIdx.x + gridDim.x);
+  if (wimg != nullptr) umma::mbar_wait(wbar, 0);   // weights have landed (async proxy writes)
 
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int p0 = tile * TC_TILE;
@@ -340,7 +353,7 @@ static int launch_block_pair(const char* name, bool hl, const float* pw, int w, 
                              const void* nfeats, int r, const int32_t* pair_c,
                              const int32_t* pair_n, const int32_t* num_pairs, int capacity,
                              const float* w1, const float* b1, const float* w2, const float* b2,
-                             int f, float* pooled, gn_stream_t stream) {
+                             const void* wimg, int f, float* pooled, gn_stream_t stream) {
   GN_REQUIRE(capacity >= 0, "%s: negative capacity", name);
   if (w != gn::TC_W || r != gn::TC_R || f != gn::TC_F) {
     gn::set_error("%s: fused kernel is built for w=%d r=%d f=%d (got %d, %d, %d)", name,
@@ -348,8 +361,9 @@ static int launch_block_pair(const char* name, bool hl, const float* pw, int w, 
     return GN_ERR_UNSUPPORTED;
   }
   if (capacity == 0) return GN_OK;
-  GN_REQUIRE(pw && feats && nfeats && pair_c && pair_n && num_pairs && w1 && b1 && w2 && b2 &&
-                 pooled, "%s: null pointer", name);
+  GN_REQUIRE(pw && feats && nfeats && pair_c && pair_n && num_pairs && b1 && b2 && pooled &&
+                 ((w1 && w2) || wimg), "%s: null pointer", name);
+  GN_REQUIRE(((uintptr_t)wimg & 15) == 0, "%s: weight image must be 16-byte aligned", name);
   GN_REQUIRE((((uintptr_t)pw | (uintptr_t)feats | (uintptr_t)nfeats) & 15) == 0,
              "%s: pointers must be 16-byte aligned", name);
   const void* kern = hl ? (const void*)gn::block_pair_tc_kernel<true>
@@ -367,10 +381,12 @@ static int launch_block_pair(const char* name, bool hl, const float* pw, int w, 
   const float* np = static_cast<const float*>(nfeats);
   if (hl)
     gn::block_pair_tc_kernel<true><<<grid, gn::TC_THREADS, gn::TC_SMEM, (cudaStream_t)stream>>>(
-        pw, fp, np, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2, pooled);
+        pw, fp, np, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2,
+        static_cast<const unsigned char*>(wimg), pooled);
   else
     gn::block_pair_tc_kernel<false><<<grid, gn::TC_THREADS, gn::TC_SMEM, (cudaStream_t)stream>>>(
-        pw, fp, np, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2, pooled);
+        pw, fp, np, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2,
+        static_cast<const unsigned char*>(wimg), pooled);
   GN_CHECK_LAUNCH(name);
   return GN_OK;
 }
@@ -381,14 +397,17 @@ extern "C" int gn_block_pair_fwd(const float* pw, int w, const float* feats,
                                  const float* w1, const float* b1, const float* w2,
                                  const float* b2, int f, float* pooled, gn_stream_t stream) {
   return launch_block_pair("gn_block_pair_fwd", false, pw, w, feats, nfeats, r, pair_c, pair_n,
-                           num_pairs, capacity, w1, b1, w2, b2, f, pooled, stream);
+                           num_pairs, capacity, w1, b1, w2, b2, nullptr, f, pooled, stream);
 }
 
 extern "C" int gn_block_pair_fwd_hl(const float* pw, int w, const void* feats_hl,
                                     const void* nfeats_hl, int r, const int32_t* pair_c,
                                     const int32_t* pair_n, const int32_t* num_pairs, int capacity,
                                     const float* w1, const float* b1, const float* w2,
-                                    const float* b2, int f, float* pooled, gn_stream_t stream) {
+                                    const float* b2, const void* wimg, int f, float* pooled,
+                                    gn_stream_t stream) {
   return launch_block_pair("gn_block_pair_fwd_hl", true, pw, w, feats_hl, nfeats_hl, r, pair_c,
-                           pair_n, num_pairs, capacity, w1, b1, w2, b2, f, pooled, stream);
+                           pair_n, num_pairs, capacity, w1, b1, w2, b2, wimg, f, pooled, stream);
 }
+
+extern "C" int64_t gn_block_pair_image_bytes(void) { return (int64_t)gn::TC_OFF_A; }

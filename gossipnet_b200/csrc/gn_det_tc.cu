@@ -35,7 +35,7 @@ constexpr uint32_t DT_OFF_A = DT_OFF_WRL + 16 * DT_R * 16;           // 65536
 constexpr uint32_t DT_A_BYTES = 2 * 16 * DT_LBO_A;                   // K up to 128, hi + lo
 constexpr uint32_t DT_OFF_BIAS = DT_OFF_A + DT_A_BYTES;              // b_fc1[64] b_fc2[128] b_rd[32]
 constexpr uint32_t DT_OFF_BAR = DT_OFF_BIAS + (DT_F + DT_D + DT_R) * 4;
-constexpr uint32_t DT_SMEM = DT_OFF_BAR + 16;
+constexpr uint32_t DT_SMEM = DT_OFF_BAR + 16;   // two mbarriers: UMMA completion, weight image
 static_assert(DT_SMEM <= 227 * 1024, "det tile exceeds shared memory");
 
 // transpose + split w[k_total, n_total] (fp32, [in,out]) into K-major hi/lo tiles
@@ -64,26 +64,35 @@ __device__ __forceinline__ void dt_load_tile(const float* __restrict__ src, int 
                                              unsigned char* a_hi, unsigned char* a_lo, int warp,
                                              int lane, float* __restrict__ zero_after) {
   constexpr int PIECES = WIDTH / 8;           // 8-float pieces per row
-  constexpr int ROWS_PER_REQ = 32 / (PIECES < 32 ? PIECES : 32);
-  // lane -> (row within request, piece): a warp request covers whole rows (coalesced)
-  for (int base = warp * ROWS_PER_REQ; base < DT_TILE; base += (DT_THREADS / 32) * ROWS_PER_REQ) {
-    const int r = base + lane / PIECES, q = lane % PIECES;
-    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+  constexpr int ROWS_PER_REQ = 32 / PIECES;   // lane -> (row within request, piece)
+  constexpr int ITERS = DT_TILE / ((DT_THREADS / 32) * ROWS_PER_REQ);
+  // all loads first (ITERS x 32 bytes in flight per thread), then the stores / splits:
+  // this phase is pure memory latency, so it is paid once per tile, not once per row group
+  float4 v[ITERS][2];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int r = (it * (DT_THREADS / 32) + warp) * ROWS_PER_REQ + lane / PIECES, q = lane % PIECES;
+    v[it][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    v[it][1] = v[it][0];
     if (row0 + r < rows) {
       const float* p = src + (size_t)(row0 + r) * WIDTH + q * 8;
-      v0 = ldg4(p);
-      v1 = ldg4(p + 4);
-      if (zero_after != nullptr) {
-        float* z = zero_after + (size_t)(row0 + r) * WIDTH + q * 8;
-        *reinterpret_cast<float4*>(z) = make_float4(0.f, 0.f, 0.f, 0.f);
-        *reinterpret_cast<float4*>(z + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      v[it][0] = ldg4(p);
+      v[it][1] = ldg4(p + 4);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int r = (it * (DT_THREADS / 32) + warp) * ROWS_PER_REQ + lane / PIECES, q = lane % PIECES;
+    if (zero_after != nullptr && row0 + r < rows) {
+      float* z = zero_after + (size_t)(row0 + r) * WIDTH + q * 8;
+      *reinterpret_cast<float4*>(z) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(z + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     uint4 h, l;
-    umma::split_bf16x2(v0.x, v0.y, h.x, l.x);
-    umma::split_bf16x2(v0.z, v0.w, h.y, l.y);
-    umma::split_bf16x2(v1.x, v1.y, h.z, l.z);
-    umma::split_bf16x2(v1.z, v1.w, h.w, l.w);
+    umma::split_bf16x2(v[it][0].x, v[it][0].y, h.x, l.x);
+    umma::split_bf16x2(v[it][0].z, v[it][0].w, h.y, l.y);
+    umma::split_bf16x2(v[it][1].x, v[it][1].y, h.z, l.z);
+    umma::split_bf16x2(v[it][1].z, v[it][1].w, h.w, l.w);
     const uint32_t off = (uint32_t)q * DT_LBO_A + (uint32_t)r * 16;
     *reinterpret_cast<uint4*>(a_hi + off) = h;
     *reinterpret_cast<uint4*>(a_lo + off) = l;
@@ -106,14 +115,15 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
                     const float* __restrict__ w_fc1, const float* __restrict__ b_fc1,
                     const float* __restrict__ w_fc2, const float* __restrict__ b_fc2,
                     const float* __restrict__ w_rd, const float* __restrict__ b_rd,
-                    float* __restrict__ feats_out, float* __restrict__ red_f32,
-                    __nv_bfloat16* __restrict__ red_hl, int num_dets) {
+                    const unsigned char* __restrict__ wimg, float* __restrict__ feats_out,
+                    float* __restrict__ red_f32, __nv_bfloat16* __restrict__ red_hl, int num_dets,
+                    int has_a, int has_b) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int num_tiles = (num_dets + DT_TILE - 1) / DT_TILE;
   if ((int)blockIdx.x >= num_tiles) return;
-  const bool stage_a = pooled != nullptr, stage_b = w_rd != nullptr;
+  const bool stage_a = has_a != 0, stage_b = has_b != 0;
 
   unsigned char* a_hi = smem + DT_OFF_A;
   unsigned char* a_lo = a_hi + 16 * DT_LBO_A;
@@ -127,16 +137,29 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
     umma::mbar_init(bar, 1);
     umma::fence_barrier_init();
   }
+  uint64_t* wbar = bar + 1;
+  if (wimg != nullptr) {
+    // operand image from gn_prepare_operands, laid out like the shared-memory weight
+    // region [fc1^T hi|lo, fc2^T hi|lo, rd^T hi|lo] (64 KB): two bulk copies
+    if (t == 0) {
+      umma::mbar_init(wbar, 1);
+      umma::fence_barrier_init();
+      umma::mbar_expect_tx(wbar, DT_OFF_A);
+      umma::bulk_copy_g2s(umma::smem_u32(smem), wimg, DT_OFF_A / 2, wbar);
+      umma::bulk_copy_g2s(umma::smem_u32(smem) + DT_OFF_A / 2, wimg + DT_OFF_A / 2, DT_OFF_A / 2, wbar);
+    }
+  } else {
+    if (stage_a) {
+      dt_stage_weight(w_fc1, DT_F, DT_F, smem + DT_OFF_W1H, smem + DT_OFF_W1L, t);
+      dt_stage_weight(w_fc2, DT_F, DT_D, smem + DT_OFF_W2H, smem + DT_OFF_W2L, t);
+    }
+    if (stage_b) dt_stage_weight(w_rd, DT_D, DT_R, smem + DT_OFF_WRH, smem + DT_OFF_WRL, t);
+  }
   if (stage_a) {
-    dt_stage_weight(w_fc1, DT_F, DT_F, smem + DT_OFF_W1H, smem + DT_OFF_W1L, t);
-    dt_stage_weight(w_fc2, DT_F, DT_D, smem + DT_OFF_W2H, smem + DT_OFF_W2L, t);
     if (t < DT_F) bias1[t] = __ldg(b_fc1 + t);
     if (t < DT_D) bias2[t] = __ldg(b_fc2 + t);
   }
-  if (stage_b) {
-    dt_stage_weight(w_rd, DT_D, DT_R, smem + DT_OFF_WRH, smem + DT_OFF_WRL, t);
-    if (t < DT_R) biasr[t] = __ldg(b_rd + t);
-  }
+  if (stage_b && t < DT_R) biasr[t] = __ldg(b_rd + t);
   umma::fence_smem_to_async();
   umma::tc_fence_before();
   __syncthreads();
@@ -156,6 +179,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
   const int ehalf = warp >> 2;
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
   uint32_t par = 0;
+  bool weights_pending = wimg != nullptr;
 
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int row0 = tile * DT_TILE;
@@ -165,6 +189,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
     if (stage_a) {
       // ---- pooled tile -> A (K = 64); pooled <- 0 for the next block ----------------
       dt_load_tile<DT_F>(pooled, row0, num_dets, a_hi, a_lo, warp, lane, pooled);
+      if (weights_pending) { umma::mbar_wait(wbar, 0); weights_pending = false; }
       umma::fence_smem_to_async();
       umma::tc_fence_before();
       __syncthreads();
@@ -252,6 +277,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
     } else {
       // block 1 / stand-alone reduce: feats_in tile -> A (K = 128)
       dt_load_tile<DT_D>(feats_in, row0, num_dets, a_hi, a_lo, warp, lane, nullptr);
+      if (weights_pending) { umma::mbar_wait(wbar, 0); weights_pending = false; }
     }
 
     if (stage_b) {
@@ -310,39 +336,108 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
 
 }  // namespace gn
 
-extern "C" int gn_block_det_fwd(float* pooled, const float* feats_in, const float* w_fc1,
-                                const float* b_fc1, const float* w_fc2, const float* b_fc2,
-                                const float* w_rd, const float* b_rd, float* feats_out,
-                                float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
-                                int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
-  GN_REQUIRE(num_dets >= 0, "gn_block_det_fwd: negative size");
+static int launch_block_det(const char* name, float* pooled, const float* feats_in,
+                            const float* w_fc1, const float* b_fc1, const float* w_fc2,
+                            const float* b_fc2, const float* w_rd, const float* b_rd,
+                            const void* wimg, int has_a, int has_b, float* feats_out,
+                            float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
+                            int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
+  GN_REQUIRE(num_dets >= 0, "%s: negative size", name);
   if (shortcut_dim != gn::DT_D || pairfeat_dim != gn::DT_F || reduced_dim != gn::DT_R) {
-    gn::set_error("gn_block_det_fwd: fused kernel is built for d=%d f=%d r=%d (got %d, %d, %d)",
+    gn::set_error("%s: fused kernel is built for d=%d f=%d r=%d (got %d, %d, %d)", name,
                   gn::DT_D, gn::DT_F, gn::DT_R, shortcut_dim, pairfeat_dim, reduced_dim);
     return GN_ERR_UNSUPPORTED;
   }
   if (num_dets == 0) return GN_OK;
-  GN_REQUIRE(feats_in != nullptr, "gn_block_det_fwd: null feats_in");
-  GN_REQUIRE(pooled != nullptr || w_rd != nullptr, "gn_block_det_fwd: nothing to do");
-  GN_REQUIRE(pooled == nullptr || (w_fc1 && b_fc1 && w_fc2 && b_fc2 && feats_out),
-             "gn_block_det_fwd: stage A needs fc1 / fc2 parameters and feats_out");
-  GN_REQUIRE(w_rd == nullptr || (b_rd && (red_f32 || red_hl)),
-             "gn_block_det_fwd: stage B needs b_rd and an output");
+  GN_REQUIRE(feats_in != nullptr, "%s: null feats_in", name);
+  GN_REQUIRE(has_a || has_b, "%s: nothing to do", name);
+  GN_REQUIRE(!has_a || (pooled && b_fc1 && b_fc2 && feats_out && ((w_fc1 && w_fc2) || wimg)),
+             "%s: stage A needs pooled, fc1 / fc2 parameters and feats_out", name);
+  GN_REQUIRE(!has_b || (b_rd && (red_f32 || red_hl) && (w_rd || wimg)),
+             "%s: stage B needs reduce_dim parameters and an output", name);
   GN_REQUIRE((((uintptr_t)pooled | (uintptr_t)feats_in | (uintptr_t)feats_out |
-               (uintptr_t)red_f32 | (uintptr_t)red_hl) & 15) == 0,
-             "gn_block_det_fwd: pointers must be 16-byte aligned");
+               (uintptr_t)red_f32 | (uintptr_t)red_hl | (uintptr_t)wimg) & 15) == 0,
+             "%s: pointers must be 16-byte aligned", name);
   cudaError_t e = cudaFuncSetAttribute(gn::block_det_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn::DT_SMEM);
   if (e != cudaSuccess) {
-    gn::set_error("gn_block_det_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    gn::set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
     return GN_ERR_CUDA;
   }
   int grid = gn::ceil_div(num_dets, gn::DT_TILE);
   const int sms = gn::sm_count();
   if (grid > sms) grid = sms;
   gn::block_det_tc_kernel<<<grid, gn::DT_THREADS, gn::DT_SMEM, (cudaStream_t)stream>>>(
-      pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd, feats_out, red_f32,
-      static_cast<__nv_bfloat16*>(red_hl), num_dets);
-  GN_CHECK_LAUNCH("gn_block_det_fwd");
+      pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd,
+      static_cast<const unsigned char*>(wimg), feats_out, red_f32,
+      static_cast<__nv_bfloat16*>(red_hl), num_dets, has_a, has_b);
+  GN_CHECK_LAUNCH(name);
+  return GN_OK;
+}
+
+extern "C" int gn_block_det_fwd(float* pooled, const float* feats_in, const float* w_fc1,
+                                const float* b_fc1, const float* w_fc2, const float* b_fc2,
+                                const float* w_rd, const float* b_rd, float* feats_out,
+                                float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
+                                int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
+  return launch_block_det("gn_block_det_fwd", pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd,
+                          b_rd, nullptr, pooled != nullptr, w_rd != nullptr, feats_out, red_f32,
+                          red_hl, num_dets, shortcut_dim, pairfeat_dim, reduced_dim, stream);
+}
+
+extern "C" int gn_block_det_fwd_img(float* pooled, const float* feats_in, const void* wimg,
+                                    const float* b_fc1, const float* b_fc2, const float* b_rd,
+                                    int has_stage_a, int has_stage_b, float* feats_out,
+                                    float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
+                                    int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
+  GN_REQUIRE(wimg != nullptr, "gn_block_det_fwd_img: null weight image");
+  return launch_block_det("gn_block_det_fwd_img", pooled, feats_in, nullptr, b_fc1, nullptr, b_fc2,
+                          nullptr, b_rd, wimg, has_stage_a, has_stage_b, feats_out, red_f32, red_hl,
+                          num_dets, shortcut_dim, pairfeat_dim, reduced_dim, stream);
+}
+
+extern "C" int64_t gn_block_det_image_bytes(void) { return (int64_t)gn::DT_OFF_A; }
+
+// ---------------------------------------------------------------------------------
+// gn_prepare_operands: fp32 [k, n] weights ([in, out]) of the flat parameter buffer ->
+// bf16 hi / lo K-major operand tiles (chunk j of row n at j * n * 16 + n_row * 16).
+// table: 5 int32 per entry: src offset (floats), k, n, dst_hi offset, dst_lo offset (bytes).
+// One launch converts every block's weights of a forward pass.
+// ---------------------------------------------------------------------------------
+namespace gn {
+__global__ void prepare_operands_kernel(const float* __restrict__ flat,
+                                        const int32_t* __restrict__ table,
+                                        unsigned char* __restrict__ image) {
+  const int32_t* e = table + blockIdx.y * 5;
+  const float* w = flat + e[0];
+  const int k = e[1], n = e[2];
+  unsigned char* hi = image + e[3];
+  unsigned char* lo = image + e[4];
+  const int units = (k / 8) * n;
+  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += gridDim.x * blockDim.x) {
+    const int col = u % n, j = u / n;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __ldg(w + (size_t)(j * 8 + i) * n + col);
+    uint4 h, l;
+    umma::split_bf16x2(x[0], x[1], h.x, l.x);
+    umma::split_bf16x2(x[2], x[3], h.y, l.y);
+    umma::split_bf16x2(x[4], x[5], h.z, l.z);
+    umma::split_bf16x2(x[6], x[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + (size_t)j * n * 16 + col * 16) = h;
+    *reinterpret_cast<uint4*>(lo + (size_t)j * n * 16 + col * 16) = l;
+  }
+}
+}  // namespace gn
+
+extern "C" int gn_prepare_operands(const float* flat_params, const int32_t* table, int entries,
+                                   void* image, gn_stream_t stream) {
+  GN_REQUIRE(entries >= 0, "gn_prepare_operands: negative entry count");
+  if (entries == 0) return GN_OK;
+  GN_REQUIRE(flat_params && table && image, "gn_prepare_operands: null pointer");
+  GN_REQUIRE(((uintptr_t)image & 15) == 0, "gn_prepare_operands: image must be 16-byte aligned");
+  gn::prepare_operands_kernel<<<dim3(8, entries), 256, 0, (cudaStream_t)stream>>>(
+      flat_params, table, static_cast<unsigned char*>(image));
+  GN_CHECK_LAUNCH("gn_prepare_operands");
   return GN_OK;
 }

@@ -50,6 +50,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > (1u << 26)) __trap();
 }
 
+// ---- bulk global -> shared copy (TMA, non-tensor) ----------------------------------
+// One thread: arm `bar` with the byte count, then issue the copy; the barrier
+// completes (phase flips) when all bytes have landed.  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                              uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address
 // is written to *dst_smem.

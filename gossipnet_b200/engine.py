@@ -187,27 +187,73 @@ class GnetEngine(object):
         # last FC has no activation; shortcut: relu(infeats + feats) (:399-408)
         return self._fc(x, s + 'fc%d' % g['num_block_fc'], True, residual=infeats, out=out)
 
+    def _operand_images(self):
+        """Per-block operand images (bf16 hi/lo K-major tiles of the block weights) and the
+        table that lets ONE gn_prepare_operands launch rebuild them from the flat buffer."""
+        if 'wimg' in self._ws:
+            return self._ws['wimg'], self._ws['wimg_table'], self._img_layout
+        lib = ops._lib.load()
+        pair_b, det_b = int(lib.gn_block_pair_image_bytes()), int(lib.gn_block_det_image_bytes())
+        nb = self.g['num_blocks']
+        rows, off = [], 0
+        pair_off, det_off = [], []
+
+        def add(name, dst):
+            e = self.layout[name + '/weights']
+            k, n = e.shape
+            tile = (k // 8) * n * 16
+            rows.append([e.offset, k, n, dst, dst + tile])
+            return dst + 2 * tile
+
+        for b in range(1, nb + 1):
+            s = 'gnet/block%d/' % b
+            pair_off.append(off)
+            o = add(s + 'pw_fc1', off)
+            o = add(s + 'pw_fc2', o)
+            assert o - off == pair_b
+            off = o
+        for b in range(0, nb + 1):     # det image b: fc1/fc2 of block b, reduce_dim of block b+1
+            det_off.append(off)
+            o = off
+            if b >= 1:
+                o = add('gnet/block%d/fc1' % b, o)
+                o = add('gnet/block%d/fc2' % b, o)
+            else:
+                o += (8 * 64 + 8 * 128) * 16 * 2
+            if b + 1 <= nb:
+                o = add('gnet/block%d/reduce_dim' % (b + 1), o)
+            off += det_b
+        table = torch.tensor(rows, dtype=torch.int32, device=self.device)
+        image = torch.zeros(off, dtype=torch.uint8, device=self.device)
+        self._ws['wimg'], self._ws['wimg_table'] = image, table
+        self._img_layout = (pair_off, det_off, pair_b, det_b)
+        return image, table, self._img_layout
+
     def _blocks_fused(self, feats, pair_c, pair_n, num_pairs, cap, pw, block_feats):
         """All blocks with two launches each: the tensor-core pair stage and the
         fused detection-level kernel (fc1, fc2, shortcut of block b + reduce_dim of
-        block b+1); reduced features travel as bf16 (hi | lo) operand rows."""
+        block b+1); reduced features travel as bf16 (hi | lo) operand rows and the
+        weights as operand images prepared by one launch per forward."""
         g, p = self.g, self.p
         T, d = feats.shape
         pooled = self._buf('pooled', (T, g['pairfeat_dim']))
         pooled.zero_()   # every det launch re-zeroes it; this covers a dirty workspace
         red_hl = self._buf('red_hl', (T, 2 * g['reduced_dim']), torch.bfloat16)
-        wb = lambda scope: (p[scope + '/weights'], p[scope + '/biases'])
-        ops.block_det_fwd(None, feats, None, None, wb('gnet/block1/reduce_dim'), red_hl=red_hl)
+        image, table, (pair_off, det_off, pair_b, det_b) = self._operand_images()
+        ops.prepare_operands(self.flat, table, image)
         nb = g['num_blocks']
+        ops.block_det_fwd_img(None, feats, image[det_off[0]:det_off[0] + det_b], None, None,
+                              p['gnet/block1/reduce_dim/biases'], red_hl=red_hl)
         for b in range(1, nb + 1):
             s = 'gnet/block%d/' % b
             ops.block_pair_fwd(pw, red_hl, red_hl, pair_c, pair_n, num_pairs, cap,
-                               p[s + 'pw_fc1/weights'], p[s + 'pw_fc1/biases'],
-                               p[s + 'pw_fc2/weights'], p[s + 'pw_fc2/biases'], pooled)
+                               None, p[s + 'pw_fc1/biases'], None, p[s + 'pw_fc2/biases'], pooled,
+                               wimg=image[pair_off[b - 1]:pair_off[b - 1] + pair_b])
             out = self._buf('feats%d' % (b % 2), (T, d))
-            rd = wb('gnet/block%d/reduce_dim' % (b + 1)) if b < nb else None
-            ops.block_det_fwd(pooled, feats, wb(s + 'fc1'), wb(s + 'fc2'), rd, feats_out=out,
-                              red_hl=red_hl if rd is not None else None)
+            b_rd = p['gnet/block%d/reduce_dim/biases' % (b + 1)] if b < nb else None
+            ops.block_det_fwd_img(pooled, feats, image[det_off[b]:det_off[b] + det_b],
+                                  p[s + 'fc1/biases'], p[s + 'fc2/biases'], b_rd, feats_out=out,
+                                  red_hl=red_hl if b_rd is not None else None)
             feats = out
             if block_feats is not None:
                 block_feats.append(feats.clone())

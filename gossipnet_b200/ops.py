@@ -175,7 +175,7 @@ def segment_max(x, row_ptr, num_dets, out=None):
 
 
 def block_pair_fwd(pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, w1, b1, w2, b2,
-                   pooled, ffma=False):
+                   pooled, ffma=False, wimg=None):
     """pooled[num_dets,f] must be zero-filled; it is max-accumulated in place.
     ffma=True runs the fp32 CUDA-core variant instead of the tensor-core kernel."""
     f32 = torch.float32
@@ -185,8 +185,9 @@ def block_pair_fwd(pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, w1, b
         _lib.call('gn_block_pair_fwd_hl', _chk(pw, f32, 'pw'), pw.shape[1],
                   _chk(feats, torch.bfloat16, 'feats_hl'), _chk(nfeats, torch.bfloat16, 'nfeats_hl'),
                   r, _chk(pair_c, torch.int32, 'pair_c'), _chk(pair_n, torch.int32, 'pair_n'),
-                  _chk(num_pairs, torch.int32, 'num_pairs'), int(capacity), _chk(w1, f32, 'w1'),
-                  _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2'), _chk(b2, f32, 'b2'), w2.shape[1],
+                  _chk(num_pairs, torch.int32, 'num_pairs'), int(capacity),
+                  _chk(w1, f32, 'w1', True), _chk(b1, f32, 'b1'), _chk(w2, f32, 'w2', True),
+                  _chk(b2, f32, 'b2'), _chk(wimg, torch.uint8, 'wimg', True), b2.numel(),
                   _chk(pooled, f32, 'pooled'), _stream())
         return pooled
     _lib.call('gn_block_pair_fwd_ffma' if ffma else 'gn_block_pair_fwd', _chk(pw, f32, 'pw'), pw.shape[1], _chk(feats, f32, 'feats'),
@@ -214,6 +215,29 @@ def block_det_fwd(pooled, feats_in, fc1, fc2, rd, feats_out=None, red_f32=None, 
               _chk(wr, f32, 'w_rd', True), _chk(br, f32, 'b_rd', True),
               _chk(feats_out, f32, 'feats_out', True), _chk(red_f32, f32, 'red_f32', True),
               _chk(red_hl, torch.bfloat16, 'red_hl', True), T, d, f, r, _stream())
+
+
+def prepare_operands(flat_params, table, image):
+    """One launch: every [k,n] weight listed in `table` (int32 [entries,5]) -> bf16 hi/lo
+    K-major operand tiles inside `image` (uint8)."""
+    _lib.call('gn_prepare_operands', _chk(flat_params, torch.float32, 'flat_params'),
+              _chk(table, torch.int32, 'table'), table.shape[0],
+              _chk(image, torch.uint8, 'image'), _stream())
+
+
+def block_det_fwd_img(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out=None, red_f32=None,
+                      red_hl=None):
+    """gn_block_det_fwd with weights from a prepared operand image; a stage runs when
+    its bias is given (b_fc1 & b_fc2 -> stage A, b_rd -> stage B)."""
+    f32 = torch.float32
+    T, d = feats_in.shape
+    _lib.call('gn_block_det_fwd_img', _chk(pooled, f32, 'pooled', True),
+              _chk(feats_in, f32, 'feats_in'), _chk(wimg, torch.uint8, 'wimg'),
+              _chk(b_fc1, f32, 'b_fc1', True), _chk(b_fc2, f32, 'b_fc2', True),
+              _chk(b_rd, f32, 'b_rd', True), 1 if b_fc1 is not None else 0,
+              1 if b_rd is not None else 0, _chk(feats_out, f32, 'feats_out', True),
+              _chk(red_f32, f32, 'red_f32', True), _chk(red_hl, torch.bfloat16, 'red_hl', True),
+              T, d, 64, 32, _stream())
 
 
 # ---------------------------------------------------------------- matching, loss

@@ -165,7 +165,29 @@ int gn_block_pair_fwd_hl(const float* pw, int w, const void* feats_hl,
                          const void* nfeats_hl, int r, const int32_t* pair_c,
                          const int32_t* pair_n, const int32_t* num_pairs, int capacity,
                          const float* w1, const float* b1, const float* w2,
-                         const float* b2, int f, float* pooled, gn_stream_t stream);
+                         const float* b2, const void* wimg, int f, float* pooled,
+                         gn_stream_t stream);
+/* Prepared operand images.  Splitting / transposing the fp32 weights into the bf16
+ * hi / lo K-major tiles inside every CTA of every launch is redundant work; with
+ *   gn_prepare_operands(flat_params, table, entries, image)
+ * ONE launch per forward converts all block weights (table: 5 int32 per matrix:
+ * source offset in floats, k, n, byte offsets of the hi and lo tiles in `image`), and
+ * the kernels fetch their weights with a single bulk copy:
+ *   wimg of gn_block_pair_fwd_hl (nullable; then w1 / w2 may be NULL):
+ *        [pw_fc1^T hi | lo | pw_fc2^T hi | lo], gn_block_pair_image_bytes() bytes
+ *   wimg of gn_block_det_fwd_img: [fc1^T hi | lo | fc2^T hi | lo | reduce_dim^T hi | lo],
+ *        gn_block_det_image_bytes() bytes (parts of a skipped stage may be garbage).
+ * A tile of a [k, n] weight holds chunk j (k = 8j..8j+7) of output column c at byte
+ * offset j * n * 16 + c * 16. */
+int64_t gn_block_pair_image_bytes(void);
+int64_t gn_block_det_image_bytes(void);
+int gn_prepare_operands(const float* flat_params, const int32_t* table, int entries,
+                        void* image, gn_stream_t stream);
+int gn_block_det_fwd_img(float* pooled, const float* feats_in, const void* wimg,
+                         const float* b_fc1, const float* b_fc2, const float* b_rd,
+                         int has_stage_a, int has_stage_b, float* feats_out,
+                         float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
+                         int pairfeat_dim, int reduced_dim, gn_stream_t stream);
 /* Detection-level layers fused across the block boundary (network.py:344-409), on
  * the tensor cores:
  *   stage A (pooled != NULL): d1 = relu(pooled @ w_fc1 + b_fc1);
