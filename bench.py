@@ -316,12 +316,27 @@ def run_b200(args):
                 times.append(a.elapsed_time(b))
             i_ms = float(np.median(times[2:]))
             del out
+            # context for a write-only kernel: sustained pure-store bandwidth of this GPU
+            # (2 GiB memset, >> L2), next to the copy peak the fraction is quoted against
+            wbuf = torch.empty(1 << 31, dtype=torch.uint8, device='cuda')
+            wt = []
+            for rep in range(4):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                wbuf.zero_()
+                b.record(stream)
+                stream.synchronize()
+                wt.append(a.elapsed_time(b))
+            write_peak = (1 << 31) / (min(wt[1:]) * 1e-3) / 1e9
+            del wbuf
         iou_bytes = 4.0 * n_iou * n_iou + 16.0 * 2 * n_iou
-        roof_iou = {'kernel': 'iou_dense_kernel', 'bound': 'hbm',
+        roof_iou = {'kernel': 'iou_symmetric_kernel', 'bound': 'hbm',
                     'achieved': iou_bytes / (i_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': iou_bytes / (i_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
                     'ms_per_launch': i_ms, 'workload': 'N=M=%d, one image' % n_iou,
-                    'peak_source': peak_src}
+                    'peak_source': peak_src + ' copy bandwidth (read+write)',
+                    'write_only_peak_measured_here': write_peak,
+                    'frac_of_write_only_peak': iou_bytes / (i_ms * 1e-3) / 1e9 / write_peak}
 
     # ---- CPU baseline on this box's cores (rank 0, N=1) ---------------------------
     cpu = None

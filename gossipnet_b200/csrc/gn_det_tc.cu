@@ -231,20 +231,23 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
         dt_gemm<DT_F / 16>(tm2, d_ah, d_al, d_w2h, d_w2l, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
         umma::mma_commit(bar);
       }
+      // the shortcut operand (this thread's 64 columns of feats_in) is fetched while the
+      // fc2 UMMAs run: 16 x 16 bytes in flight per thread, latency paid once
+      float4 resid[16];
+#pragma unroll
+      for (int g = 0; g < 16; ++g)
+        resid[g] = live ? ldg4(feats_in + (size_t)grow * DT_D + ehalf * 64 + g * 4)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
       umma::mbar_wait(bar, par);
       par ^= 1;
       umma::tc_fence_after();
       // ---- feats_out = relu(feats_in + acc + b_fc2) -> global, and -> A (K = 128) ------
-#pragma unroll 1
+#pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {
         const int col0 = ehalf * 64 + cc;
         float v[16];
         umma::tmem_ld16(tm2 + tlane + col0, v);
-        float4 res[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          res[g] = live ? ldg4(feats_in + (size_t)grow * DT_D + col0 + g * 4)
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* res = resid + (cc >> 2);
         umma::tmem_ld_wait();
         float x[16];
 #pragma unroll

@@ -14,6 +14,8 @@
 // positive union the quotient (+0) is produced by a select instead; every other
 // case (including zero / NaN unions of degenerate boxes) goes through the exact
 // __fdiv_rn, so results stay bit-identical to the reference arithmetic.
+#include <stdlib.h>
+
 #include "gn_common.cuh"
 
 namespace gn {
@@ -26,17 +28,27 @@ template <bool CROWD, bool CLS, bool VEC4>
 __global__ void __launch_bounds__(IOU_THREADS)
 iou_dense_kernel(const float* __restrict__ a, const float* __restrict__ b,
                  const uint8_t* __restrict__ crowd, const int32_t* __restrict__ a_cls,
-                 const int32_t* __restrict__ b_cls, int n, int m, float* __restrict__ out) {
+                 const int32_t* __restrict__ b_cls, int batch, int n, int m,
+                 float* __restrict__ out) {
   __shared__ float4 row_box[IOU_ROWS];
   __shared__ float row_area[IOU_ROWS];
   __shared__ int row_cls[IOU_ROWS];
-  const int img = blockIdx.z;
-  const int row0 = blockIdx.y * IOU_ROWS;
+  // persistent CTAs walk the (image, row strip, column chunk) items in memory order, so
+  // the CTAs resident at any moment write one contiguous band of the output
+  const int col_chunks = (m + IOU_COLS - 1) / IOU_COLS;
+  const int strips = (n + IOU_ROWS - 1) / IOU_ROWS;
+  const int64_t items = (int64_t)batch * strips * col_chunks;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+  const int chunk = (int)(item % col_chunks);
+  const int strip = (int)((item / col_chunks) % strips);
+  const int img = (int)(item / ((int64_t)col_chunks * strips));
+  const int row0 = strip * IOU_ROWS;
   const int nrows = min(IOU_ROWS, n - row0);
   const float* ai = a + (size_t)img * n * 4;
   const float* bi = b + (size_t)img * m * 4;
   float* oi = out + (size_t)img * n * m;
 
+  __syncthreads();   // previous item's row table fully consumed
   if (threadIdx.x < nrows) {
     const float4 v = ldg4(ai + (size_t)(row0 + threadIdx.x) * 4);
     row_box[threadIdx.x] = v;
@@ -45,8 +57,8 @@ iou_dense_kernel(const float* __restrict__ a, const float* __restrict__ b,
   }
   __syncthreads();
 
-  const int c0 = blockIdx.x * IOU_COLS + threadIdx.x * 4;
-  if (c0 >= m) return;
+  const int c0 = chunk * IOU_COLS + threadIdx.x * 4;
+  if (c0 >= m) continue;
   Box cb[4];
   bool cr[4];
   int cc[4];
@@ -78,11 +90,97 @@ iou_dense_kernel(const float* __restrict__ a, const float* __restrict__ b,
       v[j] = q;
     }
     if (VEC4) {
-      __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+      *reinterpret_cast<float4*>(dst) = (make_float4(v[0], v[1], v[2], v[3]));
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (c0 + j < m) __stcs(dst + j, v[j]);
+        if (c0 + j < m) dst[j] = v[j];
+    }
+  }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Symmetric variant for the det x det matrix (a == b, no crowd / class columns): the
+// kernel is bound by instruction issue (~22 per element, mostly the exact division),
+// not by the 4-byte store, and iou(i,j) == iou(j,i) bit for bit (min / max / + commute).
+// A CTA computes one 64 x 64 tile of the upper triangle (tile row I <= tile column J),
+// stores it, and stores its transpose into tile (J, I) through a shared-memory
+// transposition so both stores are coalesced 256-byte row segments.
+// ---------------------------------------------------------------------------------
+constexpr int SYM_T = 64;
+constexpr int SYM_THREADS = 256;
+
+__global__ void __launch_bounds__(SYM_THREADS)
+iou_symmetric_kernel(const float* __restrict__ a, int n, int tiles, float* __restrict__ out) {
+  __shared__ float tr[SYM_T][SYM_T + 1];
+  // linear upper-triangle tile index -> (I, J), I <= J
+  const int img = blockIdx.y;
+  int rem = blockIdx.x, I = 0;
+  // row I of the triangle holds (tiles - I) tiles
+  {
+    // solve I from rem with a closed form, then fix up (tiles <= 4096 here)
+    const float tf = (float)tiles + 0.5f;
+    I = (int)(tf - sqrtf(tf * tf - 2.0f * (float)rem));
+    if (I < 0) I = 0;
+    while (I > 0 && (int64_t)I * tiles - (int64_t)I * (I - 1) / 2 > rem) --I;
+    while ((int64_t)(I + 1) * tiles - (int64_t)(I + 1) * I / 2 <= rem) ++I;
+    rem -= (int)((int64_t)I * tiles - (int64_t)I * (I - 1) / 2);
+  }
+  const int J = I + rem;
+  const float* ai = a + (size_t)img * n * 4;
+  float* oi = out + (size_t)img * n * n;
+  const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
+  const int r0 = I * SYM_T + ty * 4, c0 = J * SYM_T + tx * 4;
+
+  Box rb[4], cb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    rb[i] = make_box(ldg4(ai + (size_t)min(r0 + i, n - 1) * 4));
+    cb[i] = make_box(ldg4(ai + (size_t)min(c0 + i, n - 1) * 4));
+  }
+  float v[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[i][j] = box_iou(rb[i], cb[j]);
+
+  const bool vec = (n % 4 == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + i;
+    if (r < n) {
+      float* dst = oi + (size_t)r * n + c0;
+      if (vec && c0 + 3 < n) {
+        *reinterpret_cast<float4*>(dst) = (make_float4(v[i][0], v[i][1], v[i][2], v[i][3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + j < n) dst[j] = v[i][j];
+      }
+    }
+  }
+  if (I == J) return;   // diagonal tile: already complete (uniform per CTA)
+  // transpose: tr[c][r] = v[r][c]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tr[tx * 4 + j][ty * 4 + i] = v[i][j];
+  __syncthreads();
+  const int tr0 = J * SYM_T + ty * 4, tc0 = I * SYM_T + tx * 4;   // rows of tile (J, I)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tr0 + i;
+    if (r < n) {
+      const float* src = &tr[ty * 4 + i][tx * 4];
+      float* dst = oi + (size_t)r * n + tc0;
+      if (vec && tc0 + 3 < n) {
+        *reinterpret_cast<float4*>(dst) = (make_float4(src[0], src[1], src[2], src[3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (tc0 + j < n) dst[j] = src[j];
+      }
     }
   }
 }
@@ -91,11 +189,13 @@ template <bool CROWD, bool CLS>
 static void launch_iou(const float* a, const float* b, const uint8_t* crowd, const int32_t* a_cls,
                        const int32_t* b_cls, int batch, int n, int m, float* out, bool vec,
                        cudaStream_t s) {
-  dim3 grid(ceil_div(m, IOU_COLS), ceil_div(n, IOU_ROWS), batch);
+  const int64_t items = (int64_t)batch * ceil_div(n, IOU_ROWS) * ceil_div(m, IOU_COLS);
+  const int64_t cap = (int64_t)sm_count() * 16;     // 16 x 128 threads resident per SM
+  const unsigned grid = (unsigned)(items < cap ? items : cap);
   if (vec)
-    iou_dense_kernel<CROWD, CLS, true><<<grid, IOU_THREADS, 0, s>>>(a, b, crowd, a_cls, b_cls, n, m, out);
+    iou_dense_kernel<CROWD, CLS, true><<<grid, IOU_THREADS, 0, s>>>(a, b, crowd, a_cls, b_cls, batch, n, m, out);
   else
-    iou_dense_kernel<CROWD, CLS, false><<<grid, IOU_THREADS, 0, s>>>(a, b, crowd, a_cls, b_cls, n, m, out);
+    iou_dense_kernel<CROWD, CLS, false><<<grid, IOU_THREADS, 0, s>>>(a, b, crowd, a_cls, b_cls, batch, n, m, out);
 }
 
 }  // namespace gn
@@ -110,11 +210,20 @@ extern "C" int gn_iou_dense(const float* a, const float* b, const uint8_t* crowd
   GN_REQUIRE(a && b && out, "gn_iou_dense: null pointer");
   GN_REQUIRE(((uintptr_t)a & 15) == 0 && ((uintptr_t)b & 15) == 0,
              "gn_iou_dense: box arrays must be 16-byte aligned");
-  GN_REQUIRE(batch <= 65535 && gn::ceil_div(n, gn::IOU_ROWS) <= 65535,
-             "gn_iou_dense: problem too large for one launch");
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (m % 4 == 0) && (((uintptr_t)out & 15) == 0);
   const bool has_crowd = crowd != nullptr, has_cls = a_cls != nullptr;
+  static const int variant = getenv("GN_IOU_VARIANT") ? atoi(getenv("GN_IOU_VARIANT")) : 0;
+  if (variant != 1 && a == b && n == m && !has_crowd && !has_cls && n >= 2 * gn::SYM_T &&
+      (((uintptr_t)out & 15) == 0)) {
+    const int tiles = gn::ceil_div(n, gn::SYM_T);
+    const int64_t tri = (int64_t)tiles * (tiles + 1) / 2;
+    if (tri < (1ll << 31) && batch <= 65535) {
+      gn::iou_symmetric_kernel<<<dim3((unsigned)tri, batch), gn::SYM_THREADS, 0, s>>>(a, n, tiles, out);
+      GN_CHECK_LAUNCH("gn_iou_dense(symmetric)");
+      return GN_OK;
+    }
+  }
   if (has_crowd && has_cls) gn::launch_iou<true, true>(a, b, crowd, a_cls, b_cls, batch, n, m, out, vec, s);
   else if (has_crowd) gn::launch_iou<true, false>(a, b, crowd, a_cls, b_cls, batch, n, m, out, vec, s);
   else if (has_cls) gn::launch_iou<false, true>(a, b, crowd, a_cls, b_cls, batch, n, m, out, vec, s);
