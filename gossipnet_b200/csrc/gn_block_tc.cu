@@ -262,14 +262,13 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
     umma::tc_fence_after();
 
     // ---- 3. epilogue 1: h1 = relu(acc + b1) -> bf16 hi / lo operand tile -----------
-#pragma unroll
-    for (int cc = 0; cc < 32; cc += 16) {
-      float v[16];
-      umma::tmem_ld16(tmem_d1 + tlane + ecol0 + cc, v);
+    {
+      float v[32];
+      umma::tmem_ld32(tmem_d1 + tlane + ecol0, v);
       umma::tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        const int col = ecol0 + cc + g * 8;
+      for (int g = 0; g < 4; ++g) {
+        const int col = ecol0 + g * 8;
         float x[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) x[e] = fmaxf(v[g * 8 + e] + bias1[col + e], 0.f);
@@ -300,15 +299,14 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
     umma::tc_fence_after();
 
     // ---- 5. epilogue 2: h2 = relu(acc + b2) -> fp32 tile ---------------------------
-#pragma unroll
-    for (int cc = 0; cc < 32; cc += 16) {
-      float v[16];
-      umma::tmem_ld16(tmem_d2 + tlane + ecol0 + cc, v);
+    {
+      float v[32];
+      umma::tmem_ld32(tmem_d2 + tlane + ecol0, v);
       umma::tmem_ld_wait();
-      float* dst = h2 + erow * TC_LDH2 + ecol0 + cc;
+      float* dst = h2 + erow * TC_LDH2 + ecol0;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = ecol0 + cc + g * 4;
+      for (int g = 0; g < 8; ++g) {
+        const int col = ecol0 + g * 4;
         *reinterpret_cast<float4*>(dst + g * 4) =
             make_float4(fmaxf(v[g * 4 + 0] + bias2[col + 0], 0.f), fmaxf(v[g * 4 + 1] + bias2[col + 1], 0.f),
                         fmaxf(v[g * 4 + 2] + bias2[col + 2], 0.f), fmaxf(v[g * 4 + 3] + bias2[col + 3], 0.f));

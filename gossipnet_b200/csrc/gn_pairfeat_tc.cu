@@ -223,11 +223,15 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   // one half-epilogue: relu(acc[:, half*128 + ecol ..+64] + bias (+ score rows)) -> h tile
   auto epilogue_to_h = [&](uint32_t tm_src, const float* bias, int half, bool add_scores) {
     const int col_base = half * 128 + ecol;
-#pragma unroll 1
+    float va[32], vb[32];
+    umma::tmem_ld32(tm_src + tlane + col_base, va);
+    umma::tmem_ld32(tm_src + tlane + col_base + 32, vb);   // both in flight, one wait
+    umma::tmem_ld_wait();
+#pragma unroll
     for (int cc = 0; cc < 64; cc += 16) {
       float v[16];
-      umma::tmem_ld16(tm_src + tlane + col_base + cc, v);
-      umma::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = cc < 32 ? va[cc + e] : vb[cc - 32 + e];
       const int col = col_base + cc;
       if (MULTI && add_scores) {
         const float sc = row_sc[erow], sn = row_sn[erow];
