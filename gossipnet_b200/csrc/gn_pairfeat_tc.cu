@@ -27,7 +27,7 @@
 namespace gn {
 
 constexpr int PT_TILE = 128;
-constexpr int PT_THREADS = 256;
+constexpr int PT_THREADS = 512;   // 16 warps: 4 TMEM lane quadrants x 4 column groups
 constexpr int PT_H = 256, PT_O = 32;
 constexpr int PT_RING = 6;
 constexpr uint32_t PT_SBO = 128;
@@ -216,22 +216,21 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   if (t == 32) ring.fill(load_target);
 
   // epilogue mapping: TMEM lane quadrant = warp % 4; within a 128-column half the
-  // warp owns columns [64 * (warp / 4), +64)
+  // warp owns columns [32 * (warp / 4), +32)
   const int erow = (warp & 3) * 32 + lane;
-  const int ecol = (warp >> 2) * 64;
+  const int ecol = (warp >> 2) * 32;
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
-  // one half-epilogue: relu(acc[:, half*128 + ecol ..+64] + bias (+ score rows)) -> h tile
+  // one half-epilogue: relu(acc[:, half*128 + ecol ..+32] + bias (+ score rows)) -> h tile
   auto epilogue_to_h = [&](uint32_t tm_src, const float* bias, int half, bool add_scores) {
     const int col_base = half * 128 + ecol;
-    float va[32], vb[32];
+    float va[32];
     umma::tmem_ld32(tm_src + tlane + col_base, va);
-    umma::tmem_ld32(tm_src + tlane + col_base + 32, vb);   // both in flight, one wait
     umma::tmem_ld_wait();
 #pragma unroll
-    for (int cc = 0; cc < 64; cc += 16) {
+    for (int cc = 0; cc < 32; cc += 16) {
       float v[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = cc < 32 ? va[cc + e] : vb[cc - 32 + e];
+      for (int e = 0; e < 16; ++e) v[e] = va[cc + e];
       const int col = col_base + cc;
       if (MULTI && add_scores) {
         const float sc = row_sc[erow], sn = row_sn[erow];
@@ -275,45 +274,68 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int p0 = tile * PT_TILE;
 
-    // ---- geometry -> A1 (K = 16) ------------------------------------------------
-    if (t < PT_TILE) {
-      const int p = p0 + t;
-      float f[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = 0.f;
-      float sc = 0.f, sn = 0.f;
-      int rc = 0, rn = 0;
-      if (p < P) {
-        const int c = __ldg(pair_c + p), n = __ldg(pair_n + p);
-        float g[7];
-        pair_geometry(ldg4(dets + (size_t)c * 4), ldg4(dets + (size_t)n * 4),
-                      __ldg(pair_iou + p), mult, g);
-        sc = __fmul_rn(__ldg(scores + c), mult);
-        sn = __fmul_rn(__ldg(scores + n), mult);
-        if (MULTI) {
-          rc = __ldg(classes + c) - 1;                 // one-based classes (network.py:413-419)
-          rn = num_classes + __ldg(classes + n) - 1;
-#pragma unroll
-          for (int i = 0; i < 7; ++i) f[i] = g[i];
-        } else {
-          f[0] = sc;
-          f[1] = sn;
-#pragma unroll
-          for (int i = 0; i < 7; ++i) f[2 + i] = g[i];
+    // ---- geometry -> A1 (K = 16): two threads per pair -------------------------------
+    // role 0 (t < 128): iou and the three distances; role 1 (128 <= t < 256): the three
+    // log ratios, the scores and the zero padding.  Each stores its own bf16 hi / lo
+    // elements of the operand row (single class: [sc sn | iou xd yd l2 | wd hd] [ad 0..];
+    // multi class: [iou xd yd l2 | wd hd ad 0] [0..]).
+    if (t < 2 * PT_TILE) {
+      const int row = t & (PT_TILE - 1), role = t >> 7;
+      const int p = p0 + row;
+      const bool live = p < P;
+      int c = 0, n = 0;
+      float4 cbx = make_float4(0.f, 0.f, 1.f, 1.f), nbx = cbx;
+      if (live) {
+        c = __ldg(pair_c + p);
+        n = __ldg(pair_n + p);
+        cbx = ldg4(dets + (size_t)c * 4);
+        nbx = ldg4(dets + (size_t)n * 4);
+      }
+      __nv_bfloat16* hi0 = reinterpret_cast<__nv_bfloat16*>(a1_hi + row * 16);
+      __nv_bfloat16* lo0 = reinterpret_cast<__nv_bfloat16*>(a1_lo + row * 16);
+      auto put2 = [&](int e, float x0, float x1) {      // elements e, e+1 of chunk 0
+        uint32_t h, l;
+        umma::split_bf16x2(x0, x1, h, l);
+        *reinterpret_cast<uint32_t*>(hi0 + e) = h;
+        *reinterpret_cast<uint32_t*>(lo0 + e) = l;
+      };
+      if (role == 0) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) pair_geometry_dist(cbx, nbx, __ldg(pair_iou + p), mult, g);
+        const int e0 = MULTI ? 0 : 2;
+        put2(e0, g[0], g[1]);
+        put2(e0 + 2, g[2], g[3]);
+      } else {
+        float g[3] = {0.f, 0.f, 0.f};
+        float sc = 0.f, sn = 0.f;
+        int rc = 0, rn = 0;
+        if (live) {
+          pair_geometry_logs(cbx, nbx, mult, g);
+          sc = __fmul_rn(__ldg(scores + c), mult);
+          sn = __fmul_rn(__ldg(scores + n), mult);
+          if (MULTI) {
+            rc = __ldg(classes + c) - 1;               // one-based classes (network.py:413-419)
+            rn = num_classes + __ldg(classes + n) - 1;
+          }
         }
-      }
-      if (MULTI) {
-        row_sc[t] = sc; row_sn[t] = sn; row_rc[t] = rc; row_rn[t] = rn;
-      }
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
-        uint4 h, l;
-        umma::split_bf16x2(f[ch * 8 + 0], f[ch * 8 + 1], h.x, l.x);
-        umma::split_bf16x2(f[ch * 8 + 2], f[ch * 8 + 3], h.y, l.y);
-        umma::split_bf16x2(f[ch * 8 + 4], f[ch * 8 + 5], h.z, l.z);
-        umma::split_bf16x2(f[ch * 8 + 6], f[ch * 8 + 7], h.w, l.w);
-        *reinterpret_cast<uint4*>(a1_hi + ch * PT_LBO_A + t * 16) = h;
-        *reinterpret_cast<uint4*>(a1_lo + ch * PT_LBO_A + t * 16) = l;
+        uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        if (MULTI) {
+          row_sc[row] = sc; row_sn[row] = sn; row_rc[row] = rc; row_rn[row] = rn;
+          put2(4, g[0], g[1]);
+          put2(6, g[2], 0.f);
+          *reinterpret_cast<uint4*>(a1_hi + PT_LBO_A + row * 16) = z;
+          *reinterpret_cast<uint4*>(a1_lo + PT_LBO_A + row * 16) = z;
+        } else {
+          put2(0, sc, sn);
+          put2(6, g[0], g[1]);
+          uint32_t h, l;
+          umma::split_bf16x2(g[2], 0.f, h, l);
+          uint4 zh = z, zl = z;
+          zh.x = h;
+          zl.x = l;
+          *reinterpret_cast<uint4*>(a1_hi + PT_LBO_A + row * 16) = zh;
+          *reinterpret_cast<uint4*>(a1_lo + PT_LBO_A + row * 16) = zl;
+        }
       }
     }
     umma::fence_smem_to_async();
