@@ -293,7 +293,10 @@ def run_b200(args):
         flops = 20480.0 * P  # 2*(96*64 + 64*64) per pair
         roof = {'kernel': 'block_pair_tc_kernel', 'bound': 'tensor',
                 'achieved': flops / (k_ms * 1e-3) / 1e12, 'peak': bf16_peak, 'unit': 'TFLOP/s',
-                'frac': flops / (k_ms * 1e-3) / 1e12 / bf16_peak, 'traffic': None,
+                'frac': flops / (k_ms * 1e-3) / 1e12 / bf16_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on
+                # this workload (ncu --set full, profiles/r1_tc_kernels.md); scales with P
+                'traffic': 378.9e6 * (P / 2486884.0),
                 'ms_per_launch': k_ms, 'launches_per_step': args.blocks,
                 'algorithmic_flops_per_launch': flops,
                 'peak_source': '%s bf16 sustained %.1f TF/s (kernel timed inside a long step). '
