@@ -80,6 +80,7 @@ SIGNATURES = {
     'gn_roi_pool_bwd': [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                         c_int, c_float, c_void_p, c_void_p],
     'gn_selftest_umma': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    'gn_selftest_umma_ts': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     'gn_selftest_umma_rate': [c_int, c_int, c_int, c_int, c_void_p, c_void_p],
 }
 _RESTYPES = {'gn_last_error': ctypes.c_char_p, 'gn_pwfeat_prep_bytes': ctypes.c_int64,

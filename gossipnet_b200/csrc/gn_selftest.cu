@@ -114,6 +114,106 @@ extern "C" int gn_selftest_umma(const float* a, const float* w, float* c, int k,
 }
 
 // ---------------------------------------------------------------------------------
+// Same product with the A operand in TENSOR MEMORY (tcgen05.mma "TS" form): each
+// thread stores its row's bf16 hi / lo pairs with tcgen05.st; pins the A-in-TMEM layout.
+// ---------------------------------------------------------------------------------
+namespace gn {
+__global__ void __launch_bounds__(128, 1)
+umma_selftest_ts_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                        float* __restrict__ c, int k) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base;
+  const int t = threadIdx.x, warp = t >> 5;
+  const int chunks = k / 8;
+  uint4* b_hi = reinterpret_cast<uint4*>(smem);
+  uint4* b_lo = b_hi + chunks * ST_N;
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 512);
+  if (t == 0) {
+    umma::mbar_init(&bar, 1);
+    umma::fence_barrier_init();
+  }
+  for (int j = t >> 6; j < chunks; j += 2) {
+    const int n = t & 63;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = __ldg(w + (size_t)(j * 8 + e) * ST_N + n);
+    uint4 h, l;
+    umma::split_bf16x2(x[0], x[1], h.x, l.x);
+    umma::split_bf16x2(x[2], x[3], h.y, l.y);
+    umma::split_bf16x2(x[4], x[5], h.z, l.z);
+    umma::split_bf16x2(x[6], x[7], h.w, l.w);
+    b_hi[j * ST_N + n] = h;
+    b_lo[j * ST_N + n] = l;
+  }
+  umma::fence_smem_to_async();
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  // D: columns [0,64); A hi: [64, 64 + k/2); A lo: [64 + k/2, 64 + k)
+  const uint32_t tlane = (uint32_t)(warp * 32) << 16;
+  const uint32_t ta_hi = tmem + 64, ta_lo = tmem + 64 + k / 2;
+  for (int j = 0; j < chunks; j += 2) {   // 16 elements = 8 columns per store
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x0 = __ldg(a + (size_t)t * k + j * 8 + 2 * e);
+      const float x1 = __ldg(a + (size_t)t * k + j * 8 + 2 * e + 1);
+      umma::split_bf16x2(x0, x1, h[e], l[e]);
+    }
+    umma::tmem_st8(ta_hi + tlane + j * 4, h);
+    umma::tmem_st8(ta_lo + tlane + j * 4, l);
+  }
+  umma::tmem_st_wait();
+  umma::tc_fence_before();
+  __syncthreads();
+  if (t == 0) {
+    umma::tc_fence_after();
+    const uint32_t idesc = umma::idesc_bf16_f32(ST_M, ST_N);
+    const uint32_t lbo_b = ST_N * 16, sbo = 128;
+    for (int ks = 0; ks < k / 16; ++ks) {
+      const uint64_t dbh = umma::smem_desc(umma::smem_u32(b_hi) + ks * 2 * lbo_b, lbo_b, sbo);
+      const uint64_t dbl = umma::smem_desc(umma::smem_u32(b_lo) + ks * 2 * lbo_b, lbo_b, sbo);
+      umma::mma_bf16_ts(tmem, ta_lo + ks * 8, dbh, idesc, ks > 0);
+      umma::mma_bf16_ts(tmem, ta_hi + ks * 8, dbl, idesc, 1);
+      umma::mma_bf16_ts(tmem, ta_hi + ks * 8, dbh, idesc, 1);
+    }
+    umma::mma_commit(&bar);
+  }
+  umma::mbar_wait(&bar, 0);
+  umma::tc_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < ST_N; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tmem + tlane + c0, v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[(size_t)t * ST_N + c0 + i] = v[i];
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 512);
+}
+}  // namespace gn
+
+extern "C" int gn_selftest_umma_ts(const float* a, const float* w, float* c, int k,
+                                   gn_stream_t stream) {
+  GN_REQUIRE(a && w && c, "gn_selftest_umma_ts: null pointer");
+  GN_REQUIRE(k >= 16 && k % 16 == 0 && k <= gn::ST_KMAX, "gn_selftest_umma_ts: bad k=%d", k);
+  const int smem = (k / 8) * gn::ST_N * 16 * 2;
+  cudaError_t e = cudaFuncSetAttribute(gn::umma_selftest_ts_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    gn::set_error("gn_selftest_umma_ts: %s", cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
+  gn::umma_selftest_ts_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a, w, c, k);
+  GN_CHECK_LAUNCH("gn_selftest_umma_ts");
+  return GN_OK;
+}
+
+// ---------------------------------------------------------------------------------
 // Micro-benchmark: cycles per tcgen05.mma (M=128, K=16, bf16, SS mode, no-swizzle
 // K-major operands) for a given N, issued back to back by one thread.  out[0] =
 // cycles for `reps` UMMAs (clock64 around issue .. commit wait), out[1] = reps.

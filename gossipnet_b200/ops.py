@@ -392,11 +392,12 @@ def roi_pool_bwd(bottom_data, bottom_rois, argmax, grad, pooled_height, pooled_w
 
 
 # -------------------------------------------------------------------- diagnostics
-def selftest_umma(a, w):
-    """c[128,64] = a[128,k] @ w[k,64] through tcgen05 (see gn_selftest.cu)."""
+def selftest_umma(a, w, a_in_tmem=False):
+    """c[128,64] = a[128,k] @ w[k,64] through tcgen05 (see gn_selftest.cu); a_in_tmem
+    stages A in tensor memory (tcgen05.st + TS-form UMMA) instead of shared memory."""
     if tuple(a.shape)[0] != 128 or tuple(w.shape) != (a.shape[1], 64):
         raise ValueError('selftest_umma expects a[128,k], w[k,64]')
     c = torch.empty((128, 64), dtype=torch.float32, device=a.device)
-    _lib.call('gn_selftest_umma', _chk(a, torch.float32, 'a'), _chk(w, torch.float32, 'w'),
+    _lib.call('gn_selftest_umma_ts' if a_in_tmem else 'gn_selftest_umma', _chk(a, torch.float32, 'a'), _chk(w, torch.float32, 'w'),
               _chk(c, torch.float32, 'c'), int(a.shape[1]), _stream())
     return c

@@ -304,6 +304,9 @@ int gn_roi_pool_bwd(int batch, int height, int width, int channels, const float*
  * k: multiple of 16, <= 256.  No reference counterpart; used by the tests to pin
  * the descriptor / layout conventions independently of the fused kernels. */
 int gn_selftest_umma(const float* a, const float* w, float* c, int k, gn_stream_t stream);
+/* Same product with the A operand staged in tensor memory (tcgen05.st + the "TS" form of
+ * tcgen05.mma): pins the A-in-TMEM layout. */
+int gn_selftest_umma_ts(const float* a, const float* w, float* c, int k, gn_stream_t stream);
 /* Micro-benchmark: `reps` back-to-back tcgen05.mma (M=128, N=n, K=16, bf16, SS) from
  * one thread per CTA, cycling over `distinct_b` B tiles; out_dev[0] = SM cycles,
  * out_dev[1] = reps (written by the last CTA to finish; all CTAs do the same work). */
