@@ -102,7 +102,7 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   float* bias2 = bias1 + TC_F;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
 
-  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 128);
+  if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
   if (t == 0) {
     umma::mbar_init(bar, 1);
     umma::fence_barrier_init();
@@ -130,6 +130,8 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
   umma::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t tmem_d1 = tmem, tmem_d2 = tmem + TC_F;
+  // h1 (A operand of FC2) lives in tensor memory: bf16 pairs, 32 columns hi + 32 columns lo
+  const uint32_t tmem_hh = tmem + 2 * TC_F, tmem_hl = tmem + 2 * TC_F + TC_F / 2;
   const uint32_t idesc = umma::idesc_bf16_f32(TC_TILE, TC_F);
   const uint32_t sa_hi = umma::smem_u32(a_hi), sa_lo = umma::smem_u32(a_lo);
   const uint32_t sh_hi = umma::smem_u32(h_hi), sh_lo = umma::smem_u32(h_lo);
@@ -261,38 +263,40 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
     umma::mbar_wait(bar, 0);
     umma::tc_fence_after();
 
-    // ---- 3. epilogue 1: h1 = relu(acc + b1) -> bf16 hi / lo operand tile -----------
+    // ---- 3. epilogue 1: h1 = relu(acc + b1) -> bf16 hi / lo A operand in TENSOR MEMORY --
+    // (TS-form UMMA for FC2: no shared-memory round trip for h1, and FC2 reads only its
+    // 2 KB weight slab per UMMA instead of 6 KB)
     {
       float v[32];
       umma::tmem_ld32(tmem_d1 + tlane + ecol0, v);
       umma::tmem_ld_wait();
+      uint32_t hh[16], hl[16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int col = ecol0 + g * 8;
-        float x[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = fmaxf(v[g * 8 + e] + bias1[col + e], 0.f);
-        uint4 h, l;
-        umma::split_bf16x2(x[0], x[1], h.x, l.x);
-        umma::split_bf16x2(x[2], x[3], h.y, l.y);
-        umma::split_bf16x2(x[4], x[5], h.z, l.z);
-        umma::split_bf16x2(x[6], x[7], h.w, l.w);
-        const uint32_t off = (uint32_t)(col >> 3) * TC_LBO_A + (uint32_t)erow * 16;
-        *reinterpret_cast<uint4*>(h_hi + off) = h;
-        *reinterpret_cast<uint4*>(h_lo + off) = l;
+      for (int e = 0; e < 16; ++e) {
+        const int col = ecol0 + 2 * e;
+        umma::split_bf16x2(fmaxf(v[2 * e] + bias1[col], 0.f), fmaxf(v[2 * e + 1] + bias1[col + 1], 0.f),
+                           hh[e], hl[e]);
       }
+      const uint32_t c0 = (uint32_t)(ecol0 >> 1);     // 2 bf16 per 32-bit column
+      umma::tmem_st8(tmem_hh + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hh[0]));
+      umma::tmem_st8(tmem_hh + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hh[8]));
+      umma::tmem_st8(tmem_hl + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hl[0]));
+      umma::tmem_st8(tmem_hl + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hl[8]));
+      umma::tmem_st_wait();
     }
-    umma::fence_smem_to_async();
     umma::tc_fence_before();
     __syncthreads();
 
-    // ---- 4. FC2 ---------------------------------------------------------------------
+    // ---- 4. FC2 (A from tensor memory) ----------------------------------------------------
     if (t == 0) {
       umma::tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < TC_F / 16; ++ks)
-        umma::mma_bf16x3(tmem_d2, d_hh, d_hl, d_b2h, d_b2l, ks * (2 * TC_LBO_A >> 4),
-                         ks * (2 * TC_LBO_B >> 4), idesc, ks > 0);
+      for (int ks = 0; ks < TC_F / 16; ++ks) {
+        const uint32_t boff = ks * (2 * TC_LBO_B >> 4);
+        umma::mma_bf16_ts(tmem_d2, tmem_hl + ks * 8, d_b2h + boff, idesc, ks > 0);
+        umma::mma_bf16_ts(tmem_d2, tmem_hh + ks * 8, d_b2l + boff, idesc, 1);
+        umma::mma_bf16_ts(tmem_d2, tmem_hh + ks * 8, d_b2h + boff, idesc, 1);
+      }
       umma::mma_commit(bar);
     }
     umma::mbar_wait(bar, 1);
@@ -342,7 +346,7 @@ block_pair_tc_kernel(const float* __restrict__ pw, const float* __restrict__ fea
 
   umma::tc_fence_before();
   __syncthreads();
-  if (warp == 0) umma::tmem_dealloc(tmem, 128);
+  if (warp == 0) umma::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace gn
