@@ -48,8 +48,11 @@ SIGNATURES = {
     'gn_block_det_image_bytes': [],
     'gn_prepare_operands': [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     'gn_block_det_fwd_img': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                             c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
-                             c_void_p],
+                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                             c_int, c_int, c_void_p],
+    'gn_block_pair_ab_image_bytes': [],
+    'gn_block_pair_fwd_ab': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                             c_void_p, c_void_p, c_void_p, c_void_p],
     'gn_block_det_fwd': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                          c_void_p],
@@ -85,7 +88,8 @@ SIGNATURES = {
 }
 _RESTYPES = {'gn_last_error': ctypes.c_char_p, 'gn_pwfeat_prep_bytes': ctypes.c_int64,
              'gn_block_pair_image_bytes': ctypes.c_int64,
-             'gn_block_det_image_bytes': ctypes.c_int64}
+             'gn_block_det_image_bytes': ctypes.c_int64,
+             'gn_block_pair_ab_image_bytes': ctypes.c_int64}
 
 _lib = None
 # number of C-ABI compute calls made so far (each is one kernel launch of this

@@ -31,10 +31,12 @@ constexpr uint32_t DT_OFF_W2H = DT_OFF_W1L + 8 * DT_F * 16;          // fc2^T: 8
 constexpr uint32_t DT_OFF_W2L = DT_OFF_W2H + 8 * DT_D * 16;
 constexpr uint32_t DT_OFF_WRH = DT_OFF_W2L + 8 * DT_D * 16;          // rd^T: 16 chunks x 32 rows
 constexpr uint32_t DT_OFF_WRL = DT_OFF_WRH + 16 * DT_R * 16;
-constexpr uint32_t DT_OFF_A = DT_OFF_WRL + 16 * DT_R * 16;           // 65536
+constexpr uint32_t DT_OFF_WABH = DT_OFF_WRL + 16 * DT_R * 16;        // [W1[32:64] | W1[64:96]]^T of
+constexpr uint32_t DT_OFF_WABL = DT_OFF_WABH + 4 * DT_D * 16;        //   the next block's pw_fc1: 4 chunks x 128 rows
+constexpr uint32_t DT_OFF_A = DT_OFF_WABL + 4 * DT_D * 16;           // 81920 = weight image bytes
 constexpr uint32_t DT_A_BYTES = 2 * 16 * DT_LBO_A;                   // K up to 128, hi + lo
-constexpr uint32_t DT_OFF_BIAS = DT_OFF_A + DT_A_BYTES;              // b_fc1[64] b_fc2[128] b_rd[32]
-constexpr uint32_t DT_OFF_BAR = DT_OFF_BIAS + (DT_F + DT_D + DT_R) * 4;
+constexpr uint32_t DT_OFF_BIAS = DT_OFF_A + DT_A_BYTES;              // b_fc1[64] b_fc2[128] b_rd[32] b_ab[64]
+constexpr uint32_t DT_OFF_BAR = DT_OFF_BIAS + (DT_F + DT_D + DT_R + DT_F) * 4;
 constexpr uint32_t DT_SMEM = DT_OFF_BAR + 16;   // two mbarriers: UMMA completion, weight image
 static_assert(DT_SMEM <= 227 * 1024, "det tile exceeds shared memory");
 
@@ -116,7 +118,8 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
                     const float* __restrict__ w_fc2, const float* __restrict__ b_fc2,
                     const float* __restrict__ w_rd, const float* __restrict__ b_rd,
                     const unsigned char* __restrict__ wimg, float* __restrict__ feats_out,
-                    float* __restrict__ red_f32, __nv_bfloat16* __restrict__ red_hl, int num_dets,
+                    float* __restrict__ red_f32, __nv_bfloat16* __restrict__ red_hl,
+                    const float* __restrict__ b_ab, float* __restrict__ ab_out, int num_dets,
                     int has_a, int has_b) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
@@ -130,6 +133,8 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
   float* bias1 = reinterpret_cast<float*>(smem + DT_OFF_BIAS);
   float* bias2 = bias1 + DT_F;
   float* biasr = bias2 + DT_D;
+  float* biasab = biasr + DT_R;
+  const bool stage_ab = ab_out != nullptr;   // needs the prepared image (W_ab part)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + DT_OFF_BAR);
 
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, 256);
@@ -160,6 +165,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
     if (t < DT_D) bias2[t] = __ldg(b_fc2 + t);
   }
   if (stage_b && t < DT_R) biasr[t] = __ldg(b_rd + t);
+  if (stage_ab && t < DT_F) biasab[t] = __ldg(b_ab + t);
   umma::fence_smem_to_async();
   umma::tc_fence_before();
   __syncthreads();
@@ -175,6 +181,8 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
   const uint64_t d_w1h = umma::smem_desc(s_w1h, DT_F * 16, DT_SBO), d_w1l = umma::smem_desc(s_w1l, DT_F * 16, DT_SBO);
   const uint64_t d_w2h = umma::smem_desc(s_w2h, DT_D * 16, DT_SBO), d_w2l = umma::smem_desc(s_w2l, DT_D * 16, DT_SBO);
   const uint64_t d_wrh = umma::smem_desc(s_wrh, DT_R * 16, DT_SBO), d_wrl = umma::smem_desc(s_wrl, DT_R * 16, DT_SBO);
+  const uint64_t d_wabh = umma::smem_desc(umma::smem_u32(smem + DT_OFF_WABH), DT_D * 16, DT_SBO);
+  const uint64_t d_wabl = umma::smem_desc(umma::smem_u32(smem + DT_OFF_WABL), DT_D * 16, DT_SBO);
   const int erow = (warp & 3) * 32 + lane;
   const int ehalf = warp >> 2;
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
@@ -326,6 +334,52 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
             }
           }
         }
+        if (stage_ab) {
+          // red -> A operand (K = 32) of the per-detection halves of the next pair FC
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 h, l;
+            umma::split_bf16x2(x[g * 8 + 0], x[g * 8 + 1], h.x, l.x);
+            umma::split_bf16x2(x[g * 8 + 2], x[g * 8 + 3], h.y, l.y);
+            umma::split_bf16x2(x[g * 8 + 4], x[g * 8 + 5], h.z, l.z);
+            umma::split_bf16x2(x[g * 8 + 6], x[g * 8 + 7], h.w, l.w);
+            const uint32_t off = (uint32_t)((col0 >> 3) + g) * DT_LBO_A + (uint32_t)erow * 16;
+            *reinterpret_cast<uint4*>(a_hi + off) = h;
+            *reinterpret_cast<uint4*>(a_lo + off) = l;
+          }
+        }
+      }
+      if (stage_ab) {
+        // AB[d, 0:64] = red @ W1[32:64] + b1 ; AB[d, 64:128] = red @ W1[64:96]   (gn_block_ab.cu)
+        umma::fence_smem_to_async();
+        umma::tc_fence_before();
+        __syncthreads();
+        if (t == 0) {
+          umma::tc_fence_after();
+          dt_gemm<DT_R / 16>(tm2, d_ah, d_al, d_wabh, d_wabl, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
+          umma::mma_commit(bar);
+        }
+        umma::mbar_wait(bar, par);
+        par ^= 1;
+        umma::tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < 64; cc += 32) {
+          const int col0 = ehalf * 64 + cc;
+          float v[32];
+          umma::tmem_ld32(tm2 + tlane + col0, v);
+          umma::tmem_ld_wait();
+          if (live) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const int col = col0 + g * 4;
+              float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              if (col < DT_F) {          // uniform per warp: ehalf 0 owns the A half
+                o.x += biasab[col]; o.y += biasab[col + 1]; o.z += biasab[col + 2]; o.w += biasab[col + 3];
+              }
+              *reinterpret_cast<float4*>(ab_out + (size_t)grow * DT_D + col) = o;
+            }
+          }
+        }
       }
     }
     umma::tc_fence_before();
@@ -343,8 +397,9 @@ static int launch_block_det(const char* name, float* pooled, const float* feats_
                             const float* w_fc1, const float* b_fc1, const float* w_fc2,
                             const float* b_fc2, const float* w_rd, const float* b_rd,
                             const void* wimg, int has_a, int has_b, float* feats_out,
-                            float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
-                            int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
+                            float* red_f32, void* red_hl, const float* b_ab, float* ab_out,
+                            int num_dets, int shortcut_dim, int pairfeat_dim, int reduced_dim,
+                            gn_stream_t stream) {
   GN_REQUIRE(num_dets >= 0, "%s: negative size", name);
   if (shortcut_dim != gn::DT_D || pairfeat_dim != gn::DT_F || reduced_dim != gn::DT_R) {
     gn::set_error("%s: fused kernel is built for d=%d f=%d r=%d (got %d, %d, %d)", name,
@@ -356,8 +411,11 @@ static int launch_block_det(const char* name, float* pooled, const float* feats_
   GN_REQUIRE(has_a || has_b, "%s: nothing to do", name);
   GN_REQUIRE(!has_a || (pooled && b_fc1 && b_fc2 && feats_out && ((w_fc1 && w_fc2) || wimg)),
              "%s: stage A needs pooled, fc1 / fc2 parameters and feats_out", name);
-  GN_REQUIRE(!has_b || (b_rd && (red_f32 || red_hl) && (w_rd || wimg)),
+  GN_REQUIRE(!has_b || (b_rd && (red_f32 || red_hl || ab_out) && (w_rd || wimg)),
              "%s: stage B needs reduce_dim parameters and an output", name);
+  GN_REQUIRE(ab_out == nullptr || (has_b && wimg && b_ab),
+             "%s: the AB output needs stage B, the prepared image and the pw_fc1 bias", name);
+  GN_REQUIRE(((uintptr_t)ab_out & 15) == 0, "%s: ab_out must be 16-byte aligned", name);
   GN_REQUIRE((((uintptr_t)pooled | (uintptr_t)feats_in | (uintptr_t)feats_out |
                (uintptr_t)red_f32 | (uintptr_t)red_hl | (uintptr_t)wimg) & 15) == 0,
              "%s: pointers must be 16-byte aligned", name);
@@ -373,7 +431,7 @@ static int launch_block_det(const char* name, float* pooled, const float* feats_
   gn::block_det_tc_kernel<<<grid, gn::DT_THREADS, gn::DT_SMEM, (cudaStream_t)stream>>>(
       pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd,
       static_cast<const unsigned char*>(wimg), feats_out, red_f32,
-      static_cast<__nv_bfloat16*>(red_hl), num_dets, has_a, has_b);
+      static_cast<__nv_bfloat16*>(red_hl), b_ab, ab_out, num_dets, has_a, has_b);
   GN_CHECK_LAUNCH(name);
   return GN_OK;
 }
@@ -385,18 +443,20 @@ extern "C" int gn_block_det_fwd(float* pooled, const float* feats_in, const floa
                                 int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
   return launch_block_det("gn_block_det_fwd", pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd,
                           b_rd, nullptr, pooled != nullptr, w_rd != nullptr, feats_out, red_f32,
-                          red_hl, num_dets, shortcut_dim, pairfeat_dim, reduced_dim, stream);
+                          red_hl, nullptr, nullptr, num_dets, shortcut_dim, pairfeat_dim,
+                          reduced_dim, stream);
 }
 
 extern "C" int gn_block_det_fwd_img(float* pooled, const float* feats_in, const void* wimg,
                                     const float* b_fc1, const float* b_fc2, const float* b_rd,
                                     int has_stage_a, int has_stage_b, float* feats_out,
-                                    float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
+                                    float* red_f32, void* red_hl, const float* b_ab,
+                                    float* ab_out, int num_dets, int shortcut_dim,
                                     int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
   GN_REQUIRE(wimg != nullptr, "gn_block_det_fwd_img: null weight image");
   return launch_block_det("gn_block_det_fwd_img", pooled, feats_in, nullptr, b_fc1, nullptr, b_fc2,
                           nullptr, b_rd, wimg, has_stage_a, has_stage_b, feats_out, red_f32, red_hl,
-                          num_dets, shortcut_dim, pairfeat_dim, reduced_dim, stream);
+                          b_ab, ab_out, num_dets, shortcut_dim, pairfeat_dim, reduced_dim, stream);
 }
 
 extern "C" int64_t gn_block_det_image_bytes(void) { return (int64_t)gn::DT_OFF_A; }
@@ -404,18 +464,20 @@ extern "C" int64_t gn_block_det_image_bytes(void) { return (int64_t)gn::DT_OFF_A
 // ---------------------------------------------------------------------------------
 // gn_prepare_operands: fp32 [k, n] weights ([in, out]) of the flat parameter buffer ->
 // bf16 hi / lo K-major operand tiles (chunk j of row n at j * n * 16 + n_row * 16).
-// table: 5 int32 per entry: src offset (floats), k, n, dst_hi offset, dst_lo offset (bytes).
+// table: 6 int32 per entry: src offset (floats), k, n, dst_hi offset, dst_lo offset (bytes),
+// chunk pitch in bytes (0 = n * 16; larger when several matrices share one N-wide tile).
 // One launch converts every block's weights of a forward pass.
 // ---------------------------------------------------------------------------------
 namespace gn {
 __global__ void prepare_operands_kernel(const float* __restrict__ flat,
                                         const int32_t* __restrict__ table,
                                         unsigned char* __restrict__ image) {
-  const int32_t* e = table + blockIdx.y * 5;
+  const int32_t* e = table + blockIdx.y * 6;
   const float* w = flat + e[0];
   const int k = e[1], n = e[2];
   unsigned char* hi = image + e[3];
   unsigned char* lo = image + e[4];
+  const size_t pitch = e[5] > 0 ? (size_t)e[5] : (size_t)n * 16;
   const int units = (k / 8) * n;
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < units; u += gridDim.x * blockDim.x) {
     const int col = u % n, j = u / n;
@@ -427,8 +489,8 @@ __global__ void prepare_operands_kernel(const float* __restrict__ flat,
     umma::split_bf16x2(x[2], x[3], h.y, l.y);
     umma::split_bf16x2(x[4], x[5], h.z, l.z);
     umma::split_bf16x2(x[6], x[7], h.w, l.w);
-    *reinterpret_cast<uint4*>(hi + (size_t)j * n * 16 + col * 16) = h;
-    *reinterpret_cast<uint4*>(lo + (size_t)j * n * 16 + col * 16) = l;
+    *reinterpret_cast<uint4*>(hi + j * pitch + col * 16) = h;
+    *reinterpret_cast<uint4*>(lo + j * pitch + col * 16) = l;
   }
 }
 }  // namespace gn

@@ -75,6 +75,13 @@ class GnetEngine(object):
         self.keep_block_feats = False
         self.use_fused = True
         self.use_tensor_cores = True   # False: fp32 FFMA variants of the fused kernels
+        # 'hl': the reference's K = 96 formulation on bf16 hi/lo feature rows
+        # (gn_block_tc.cu); 'ab': first pair FC split into per-detection halves
+        # (gn_block_ab.cu).  Measured on the bench workload: 256 vs 323 us per block for
+        # the pair kernel (+14 us in the det kernel): 'ab' halves the shared-memory
+        # traffic but doubles the random L2 gather bytes per pair (2 x 256 B fp32 rows
+        # instead of 2 x 128 B), whose latency lands in the epilogue.  Kept selectable.
+        self.pair_mode = 'hl'
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name, shape, dtype=torch.float32):
@@ -189,30 +196,40 @@ class GnetEngine(object):
 
     def _operand_images(self):
         """Per-block operand images (bf16 hi/lo K-major tiles of the block weights) and the
-        table that lets ONE gn_prepare_operands launch rebuild them from the flat buffer."""
-        if 'wimg' in self._ws:
-            return self._ws['wimg'], self._ws['wimg_table'], self._img_layout
+        table that lets ONE gn_prepare_operands launch rebuild them from the flat buffer.
+        pair_mode 'ab': pair image = [pw_fc1[0:32]^T, pw_fc2^T]; det image b = [fc1, fc2 of
+        block b, reduce_dim and (pw_fc1[32:64] | pw_fc1[64:96])^T of block b+1].
+        pair_mode 'hl': pair image = [pw_fc1^T (K = 96), pw_fc2^T]; det image without the
+        last part."""
+        key = 'wimg_' + self.pair_mode
+        if key in self._ws:
+            return self._ws[key]
         lib = ops._lib.load()
-        pair_b, det_b = int(lib.gn_block_pair_image_bytes()), int(lib.gn_block_det_image_bytes())
+        ab = self.pair_mode == 'ab'
+        pair_b = int(lib.gn_block_pair_ab_image_bytes() if ab else lib.gn_block_pair_image_bytes())
+        det_b = int(lib.gn_block_det_image_bytes())
         nb = self.g['num_blocks']
         rows, off = [], 0
         pair_off, det_off = [], []
 
-        def add(name, dst):
+        def add(name, dst, row0=0, k=None, pitch=0, col_off=0):
+            """rows [row0, row0+k) of weight `name` -> hi tile at dst, lo tile right after
+            (tile bytes = (k/8) * max(pitch, n*16)); returns the end offset."""
             e = self.layout[name + '/weights']
-            k, n = e.shape
-            tile = (k // 8) * n * 16
-            rows.append([e.offset, k, n, dst, dst + tile])
+            kk, n = e.shape
+            k = kk - row0 if k is None else k
+            tile = (k // 8) * (pitch if pitch else n * 16)
+            rows.append([e.offset + row0 * n, k, n, dst + col_off, dst + tile + col_off, pitch])
             return dst + 2 * tile
 
         for b in range(1, nb + 1):
             s = 'gnet/block%d/' % b
             pair_off.append(off)
-            o = add(s + 'pw_fc1', off)
+            o = add(s + 'pw_fc1', off, 0, 32 if ab else None)
             o = add(s + 'pw_fc2', o)
-            assert o - off == pair_b
+            assert o - off == pair_b, (o - off, pair_b)
             off = o
-        for b in range(0, nb + 1):     # det image b: fc1/fc2 of block b, reduce_dim of block b+1
+        for b in range(0, nb + 1):     # det image b: fc1/fc2 of block b, reduce_dim (+AB) of b+1
             det_off.append(off)
             o = off
             if b >= 1:
@@ -222,38 +239,60 @@ class GnetEngine(object):
                 o += (8 * 64 + 8 * 128) * 16 * 2
             if b + 1 <= nb:
                 o = add('gnet/block%d/reduce_dim' % (b + 1), o)
+                if ab:   # two [32, 64] row blocks side by side in one N = 128 tile
+                    name = 'gnet/block%d/pw_fc1' % (b + 1)
+                    add(name, o, 32, 32, pitch=128 * 16, col_off=0)
+                    add(name, o, 64, 32, pitch=128 * 16, col_off=64 * 16)
             off += det_b
         table = torch.tensor(rows, dtype=torch.int32, device=self.device)
         image = torch.zeros(off, dtype=torch.uint8, device=self.device)
-        self._ws['wimg'], self._ws['wimg_table'] = image, table
-        self._img_layout = (pair_off, det_off, pair_b, det_b)
-        return image, table, self._img_layout
+        self._ws[key] = (image, table, (pair_off, det_off, pair_b, det_b))
+        return self._ws[key]
 
     def _blocks_fused(self, feats, pair_c, pair_n, num_pairs, cap, pw, block_feats):
-        """All blocks with two launches each: the tensor-core pair stage and the
-        fused detection-level kernel (fc1, fc2, shortcut of block b + reduce_dim of
-        block b+1); reduced features travel as bf16 (hi | lo) operand rows and the
-        weights as operand images prepared by one launch per forward."""
+        """All blocks with two launches each: the tensor-core pair stage and the fused
+        detection-level kernel (fc1, fc2, shortcut of block b + reduce_dim of block b+1
+        + the per-detection halves of block b+1's first pair FC); weights travel as
+        operand images prepared by one launch per forward."""
         g, p = self.g, self.p
         T, d = feats.shape
+        ab_mode = self.pair_mode == 'ab'
         pooled = self._buf('pooled', (T, g['pairfeat_dim']))
         pooled.zero_()   # every det launch re-zeroes it; this covers a dirty workspace
-        red_hl = self._buf('red_hl', (T, 2 * g['reduced_dim']), torch.bfloat16)
+        if ab_mode:
+            inter = self._buf('ab', (T, 2 * g['pairfeat_dim']))
+        else:
+            inter = self._buf('red_hl', (T, 2 * g['reduced_dim']), torch.bfloat16)
         image, table, (pair_off, det_off, pair_b, det_b) = self._operand_images()
         ops.prepare_operands(self.flat, table, image)
         nb = g['num_blocks']
-        ops.block_det_fwd_img(None, feats, image[det_off[0]:det_off[0] + det_b], None, None,
-                              p['gnet/block1/reduce_dim/biases'], red_hl=red_hl)
+
+        def det(b, pooled_in, feats_in, out):
+            """det kernel after block b (b = 0: only the reduce of block 1)."""
+            s = 'gnet/block%d/' % b
+            nxt = 'gnet/block%d/' % (b + 1)
+            last = b == nb
+            ops.block_det_fwd_img(
+                pooled_in, feats_in, image[det_off[b]:det_off[b] + det_b],
+                p[s + 'fc1/biases'] if b >= 1 else None, p[s + 'fc2/biases'] if b >= 1 else None,
+                None if last else p[nxt + 'reduce_dim/biases'], feats_out=out,
+                red_hl=None if (last or ab_mode) else inter,
+                b_ab=p[nxt + 'pw_fc1/biases'] if (ab_mode and not last) else None,
+                ab_out=inter if (ab_mode and not last) else None)
+
+        det(0, None, feats, None)
         for b in range(1, nb + 1):
             s = 'gnet/block%d/' % b
-            ops.block_pair_fwd(pw, red_hl, red_hl, pair_c, pair_n, num_pairs, cap,
-                               None, p[s + 'pw_fc1/biases'], None, p[s + 'pw_fc2/biases'], pooled,
-                               wimg=image[pair_off[b - 1]:pair_off[b - 1] + pair_b])
+            wimg = image[pair_off[b - 1]:pair_off[b - 1] + pair_b]
+            if ab_mode:
+                ops.block_pair_fwd_ab(pw, inter, pair_c, pair_n, num_pairs, cap,
+                                      p[s + 'pw_fc2/biases'], wimg, pooled)
+            else:
+                ops.block_pair_fwd(pw, inter, inter, pair_c, pair_n, num_pairs, cap,
+                                   None, p[s + 'pw_fc1/biases'], None, p[s + 'pw_fc2/biases'],
+                                   pooled, wimg=wimg)
             out = self._buf('feats%d' % (b % 2), (T, d))
-            b_rd = p['gnet/block%d/reduce_dim/biases' % (b + 1)] if b < nb else None
-            ops.block_det_fwd_img(pooled, feats, image[det_off[b]:det_off[b] + det_b],
-                                  p[s + 'fc1/biases'], p[s + 'fc2/biases'], b_rd, feats_out=out,
-                                  red_hl=red_hl if b_rd is not None else None)
+            det(b, pooled, feats, out)
             feats = out
             if block_feats is not None:
                 block_feats.append(feats.clone())

@@ -226,9 +226,10 @@ def prepare_operands(flat_params, table, image):
 
 
 def block_det_fwd_img(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out=None, red_f32=None,
-                      red_hl=None):
+                      red_hl=None, b_ab=None, ab_out=None):
     """gn_block_det_fwd with weights from a prepared operand image; a stage runs when
-    its bias is given (b_fc1 & b_fc2 -> stage A, b_rd -> stage B)."""
+    its bias is given (b_fc1 & b_fc2 -> stage A, b_rd -> stage B); ab_out (+ b_ab)
+    additionally requests the per-detection halves of the next pair FC."""
     f32 = torch.float32
     T, d = feats_in.shape
     _lib.call('gn_block_det_fwd_img', _chk(pooled, f32, 'pooled', True),
@@ -237,7 +238,19 @@ def block_det_fwd_img(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out=None
               _chk(b_rd, f32, 'b_rd', True), 1 if b_fc1 is not None else 0,
               1 if b_rd is not None else 0, _chk(feats_out, f32, 'feats_out', True),
               _chk(red_f32, f32, 'red_f32', True), _chk(red_hl, torch.bfloat16, 'red_hl', True),
+              _chk(b_ab, f32, 'b_ab', True), _chk(ab_out, f32, 'ab_out', True),
               T, d, 64, 32, _stream())
+
+
+def block_pair_fwd_ab(pw, ab, pair_c, pair_n, num_pairs, capacity, b2, wimg, pooled):
+    """Pair stage on per-detection halves AB[T, 2f] (see gn_block_pair_fwd_ab)."""
+    f32 = torch.float32
+    _lib.call('gn_block_pair_fwd_ab', _chk(pw, f32, 'pw'), pw.shape[1], _chk(ab, f32, 'ab'),
+              ab.shape[1] // 2, _chk(pair_c, torch.int32, 'pair_c'),
+              _chk(pair_n, torch.int32, 'pair_n'), _chk(num_pairs, torch.int32, 'num_pairs'),
+              int(capacity), _chk(b2, f32, 'b2'), _chk(wimg, torch.uint8, 'wimg'),
+              _chk(pooled, f32, 'pooled'), _stream())
+    return pooled
 
 
 # ---------------------------------------------------------------- matching, loss

@@ -170,12 +170,14 @@ int gn_block_pair_fwd_hl(const float* pw, int w, const void* feats_hl,
 /* Prepared operand images.  Splitting / transposing the fp32 weights into the bf16
  * hi / lo K-major tiles inside every CTA of every launch is redundant work; with
  *   gn_prepare_operands(flat_params, table, entries, image)
- * ONE launch per forward converts all block weights (table: 5 int32 per matrix:
- * source offset in floats, k, n, byte offsets of the hi and lo tiles in `image`), and
+ * ONE launch per forward converts all block weights (table: 6 int32 per matrix:
+ * source offset in floats, k, n, byte offsets of the hi and lo tiles in `image`, chunk
+ * pitch in bytes or 0 for n * 16), and
  * the kernels fetch their weights with a single bulk copy:
  *   wimg of gn_block_pair_fwd_hl (nullable; then w1 / w2 may be NULL):
  *        [pw_fc1^T hi | lo | pw_fc2^T hi | lo], gn_block_pair_image_bytes() bytes
- *   wimg of gn_block_det_fwd_img: [fc1^T hi | lo | fc2^T hi | lo | reduce_dim^T hi | lo],
+ *   wimg of gn_block_det_fwd_img: [fc1^T hi | lo | fc2^T hi | lo | reduce_dim^T hi | lo |
+ *        (W1[w:w+r] | W1[w+r:])^T hi | lo of the next block's pw_fc1],
  *        gn_block_det_image_bytes() bytes (parts of a skipped stage may be garbage).
  * A tile of a [k, n] weight holds chunk j (k = 8j..8j+7) of output column c at byte
  * offset j * n * 16 + c * 16. */
@@ -186,8 +188,22 @@ int gn_prepare_operands(const float* flat_params, const int32_t* table, int entr
 int gn_block_det_fwd_img(float* pooled, const float* feats_in, const void* wimg,
                          const float* b_fc1, const float* b_fc2, const float* b_rd,
                          int has_stage_a, int has_stage_b, float* feats_out,
-                         float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
-                         int pairfeat_dim, int reduced_dim, gn_stream_t stream);
+                         float* red_f32, void* red_hl, const float* b_ab, float* ab_out,
+                         int num_dets, int shortcut_dim, int pairfeat_dim, int reduced_dim,
+                         gn_stream_t stream);
+/* Pair stage with the first pair FC split by input block (x @ W1 = pw @ W1[0:w] +
+ * feats[c] @ W1[w:w+r] + nfeats[n] @ W1[w+r:]): gn_block_det_fwd_img additionally
+ * writes ab_out[num_dets, 2f] = [red @ W1[w:w+r] + b1 | red @ W1[w+r:]] (b_ab = b1 of the
+ * NEXT block's pw_fc1; its weights are the 4th part of the det image), and
+ *   gn_block_pair_fwd_ab: h1 = relu(pw @ W1[0:w] + ab[c, :f] + (c != n ? ab[n, f:] : 0)),
+ *   then pw_fc2, ReLU and the segment max as gn_block_pair_fwd.
+ * wimg: [W1[0:w]^T hi | lo | W2^T hi | lo], gn_block_pair_ab_image_bytes() bytes.
+ * Same result as the reference formulation up to fp32 summation order. */
+int64_t gn_block_pair_ab_image_bytes(void);
+int gn_block_pair_fwd_ab(const float* pw, int w, const float* ab, int f,
+                         const int32_t* pair_c, const int32_t* pair_n,
+                         const int32_t* num_pairs, int capacity, const float* b2,
+                         const void* wimg, float* pooled, gn_stream_t stream);
 /* Detection-level layers fused across the block boundary (network.py:344-409), on
  * the tensor cores:
  *   stage A (pooled != NULL): d1 = relu(pooled @ w_fc1 + b_fc1);

@@ -38,11 +38,13 @@ def check_against(net, ref, with_loss=True):
 
 
 @pytest.mark.parametrize('name', CASES)
-@pytest.mark.parametrize('fused', [True, False])
+@pytest.mark.parametrize('fused', ['ab', 'hl', False])
 def test_forward_matches_reference_golden(name, fused):
     g, num_classes, layout, flat, img = setup_case(name)
     net = Gnet(num_classes, class_weights=g['class_weights'], params=flat)
-    net.engine.use_fused = fused
+    net.engine.use_fused = bool(fused)
+    if fused:
+        net.engine.pair_mode = fused     # both tensor-core formulations of the pair stage
     net(img)
     check_against(net, g)
     if 'pw_feats' in g:
