@@ -48,8 +48,7 @@ constexpr uint32_t PT_IMG_BYTES = PT_IMG_B3 + 2 * 32 * PT_LBO_W3;
 
 // shared memory map
 constexpr uint32_t PS_RING = 0;                                   // PT_RING x 16 KB
-constexpr uint32_t PS_H = PS_RING + PT_RING * PT_STAGE;           // hi 32 KB + lo 32 KB
-constexpr uint32_t PS_B1 = PS_H + 2 * 16 * PT_LBO_A;              // 16 KB
+constexpr uint32_t PS_B1 = PS_RING + PT_RING * PT_STAGE;          // 16 KB
 constexpr uint32_t PS_B3 = PS_B1 + 2 * 2 * PT_LBO_W;              // 32 KB
 constexpr uint32_t PS_A1 = PS_B3 + 2 * 32 * PT_LBO_W3;            // hi 4 KB + lo 4 KB
 constexpr uint32_t PS_BIAS = PS_A1 + 2 * 2 * PT_LBO_A;            // b1[256] b2[256] b3[32]
@@ -150,8 +149,6 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   if ((int)blockIdx.x >= num_tiles) return;
   const int my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-  unsigned char* h_hi = smem + PS_H;
-  unsigned char* h_lo = h_hi + 16 * PT_LBO_A;
   unsigned char* a1_hi = smem + PS_A1;
   unsigned char* a1_lo = a1_hi + 2 * PT_LBO_A;
   float* bias1 = reinterpret_cast<float*>(smem + PS_BIAS);
@@ -190,11 +187,14 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   umma::tc_fence_after();
 
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tm_l1 = tmem, tm_l2 = tmem + PT_H, tm_l3 = tmem;
+  // TMEM map: layer-1 accumulator of one 128-column half [0,128) (layer-3 accumulator
+  // [0,32) later), activation operand hi [128,192) + lo [192,256) (128 K elements, two
+  // bf16 per column), layer-2 accumulator [256,512)
+  const uint32_t tm_l1 = tmem, tm_hh = tmem + 128, tm_hl = tmem + 192, tm_l2 = tmem + PT_H, tm_l3 = tmem;
+  const uint32_t idesc128 = umma::idesc_bf16_f32(PT_TILE, 128);
   const uint32_t idesc256 = umma::idesc_bf16_f32(PT_TILE, PT_H);
   const uint32_t idesc32 = umma::idesc_bf16_f32(PT_TILE, PT_O);
   const uint32_t s_ring = umma::smem_u32(smem + PS_RING);
-  const uint32_t s_hh = umma::smem_u32(h_hi), s_hl = umma::smem_u32(h_lo);
   const uint32_t s_a1h = umma::smem_u32(a1_hi), s_a1l = umma::smem_u32(a1_lo);
   const uint32_t s_b1h = umma::smem_u32(smem + PS_B1), s_b1l = s_b1h + 2 * PT_LBO_W;
   const uint32_t s_b3h = umma::smem_u32(smem + PS_B3), s_b3l = s_b3h + 32 * PT_LBO_W3;
@@ -202,7 +202,6 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   // kernel-lifetime operand descriptors; the issue loops only add start-address offsets
   const uint64_t d_a1h = umma::smem_desc(s_a1h, PT_LBO_A, PT_SBO), d_a1l = umma::smem_desc(s_a1l, PT_LBO_A, PT_SBO);
   const uint64_t d_b1h = umma::smem_desc(s_b1h, PT_LBO_W, PT_SBO), d_b1l = umma::smem_desc(s_b1l, PT_LBO_W, PT_SBO);
-  const uint64_t d_hh = umma::smem_desc(s_hh, PT_LBO_A, PT_SBO), d_hl = umma::smem_desc(s_hl, PT_LBO_A, PT_SBO);
   const uint64_t d_ringh = umma::smem_desc(s_ring, PT_LBO_W, PT_SBO);
   const uint64_t d_ringl = umma::smem_desc(s_ring + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
   const uint64_t d_b3h = umma::smem_desc(s_b3h, PT_LBO_W3, PT_SBO), d_b3l = umma::smem_desc(s_b3l, PT_LBO_W3, PT_SBO);
@@ -220,18 +219,19 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   const int erow = (warp & 3) * 32 + lane;
   const int ecol = (warp >> 2) * 32;
   const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
-  // one half-epilogue: relu(acc[:, half*128 + ecol ..+32] + bias (+ score rows)) -> h tile
-  auto epilogue_to_h = [&](uint32_t tm_src, const float* bias, int half, bool add_scores) {
-    const int col_base = half * 128 + ecol;
+  // one half-epilogue: relu(acc[:, ecol..+32] + bias[col0 + ecol ..] (+ score rows)) -> the
+  // activation operand in TENSOR MEMORY (bf16 hi / lo pairs; TS-form UMMAs read it)
+  auto epilogue_to_h = [&](uint32_t tm_src, const float* bias, int col0, bool add_scores) {
     float va[32];
-    umma::tmem_ld32(tm_src + tlane + col_base, va);
+    umma::tmem_ld32(tm_src + tlane + ecol, va);
     umma::tmem_ld_wait();
+    uint32_t hh[16], hl[16];
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       float v[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e] = va[cc + e];
-      const int col = col_base + cc;
+      const int col = col0 + ecol + cc;
       if (MULTI && add_scores) {
         const float sc = row_sc[erow], sn = row_sn[erow];
         const float* wc = w1 + (size_t)row_rc[erow] * PT_H + col;
@@ -246,22 +246,17 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
         }
       }
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        float x[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = fmaxf(v[g * 8 + e] + bias[col + g * 8 + e], 0.f);
-        uint4 h, l;
-        umma::split_bf16x2(x[0], x[1], h.x, l.x);
-        umma::split_bf16x2(x[2], x[3], h.y, l.y);
-        umma::split_bf16x2(x[4], x[5], h.z, l.z);
-        umma::split_bf16x2(x[6], x[7], h.w, l.w);
-        // chunk index inside the 128-column half
-        const uint32_t off = (uint32_t)((ecol + cc + g * 8) >> 3) * PT_LBO_A + (uint32_t)erow * 16;
-        *reinterpret_cast<uint4*>(h_hi + off) = h;
-        *reinterpret_cast<uint4*>(h_lo + off) = l;
-      }
+      for (int e = 0; e < 8; ++e)
+        umma::split_bf16x2(fmaxf(v[2 * e] + bias[col + 2 * e], 0.f),
+                           fmaxf(v[2 * e + 1] + bias[col + 2 * e + 1], 0.f),
+                           hh[(cc >> 1) + e], hl[(cc >> 1) + e]);
     }
-    umma::fence_smem_to_async();
+    const uint32_t c0 = (uint32_t)(ecol >> 1);
+    umma::tmem_st8(tm_hh + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hh[0]));
+    umma::tmem_st8(tm_hh + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hh[8]));
+    umma::tmem_st8(tm_hl + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hl[0]));
+    umma::tmem_st8(tm_hl + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hl[8]));
+    umma::tmem_st_wait();
     umma::tc_fence_before();
     __syncthreads();
   };
@@ -342,18 +337,19 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
     umma::tc_fence_before();
     __syncthreads();
 
-    // ---- layer 1 ------------------------------------------------------------------
-    if (t == 0) {
-      umma::tc_fence_after();
-      umma::mma_bf16x3(tm_l1, d_a1h, d_a1l, d_b1h, d_b1l, 0, 0, idesc256, 0);
-      umma::mma_commit(done);
-    }
-    wait_done();
-
-    // ---- layer 2, two K halves ------------------------------------------------------
+    // ---- layers 1 + 2, per 128-column half of the hidden layer ---------------------------
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      epilogue_to_h(tm_l1, bias1, half, true);
+      if (t == 0) {
+        umma::tc_fence_after();
+        // layer 1, output columns [128*half, +128): rows 128*half.. of the B1 tile
+        umma::mma_bf16x3(tm_l1, d_a1h, d_a1l, d_b1h, d_b1l, 0, half * (128 * 16 >> 4), idesc128, 0);
+        umma::mma_commit(done);
+      }
+      // UMMAs complete in order: this also covers the layer-2 UMMAs of the previous half,
+      // so the activation operand may be overwritten
+      wait_done();
+      epilogue_to_h(tm_l1, bias1, half * 128, true);
       if (t == 0) {
         umma::tc_fence_after();
 #pragma unroll 1
@@ -361,12 +357,14 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
           const uint32_t g = mma_k++, s = g % PT_RING;
           umma::mbar_wait(&full[s], (g / PT_RING) & 1);
           umma::tc_fence_after();
-          const uint32_t ksr = ((uint32_t)ksl + ring.k0) & 7u;   // k-step this stage holds
-          umma::mma_bf16x3(tm_l2, d_hh, d_hl, d_ringh, d_ringl, ksr * (2 * PT_LBO_A >> 4),
-                           s * (PT_STAGE >> 4), idesc256, (half | ksl) != 0);
+          const uint32_t boff = s * (PT_STAGE >> 4);
+          const uint32_t acc = (half | ksl) != 0;
+          umma::mma_bf16_ts(tm_l2, tm_hl + ksl * 8, d_ringh + boff, idesc256, acc);
+          umma::mma_bf16_ts(tm_l2, tm_hh + ksl * 8, d_ringl + boff, idesc256, 1);
+          umma::mma_bf16_ts(tm_l2, tm_hh + ksl * 8, d_ringh + boff, idesc256, 1);
           umma::mma_commit(&empty[s]);   // slot s is free once these UMMAs have run
         }
-        umma::mma_commit(done);
+        if (half == 1) umma::mma_commit(done);
       } else if (t == 32) {
         // W2 producer (its own thread, so the UMMA issuer never waits on a completion:
         // the commit -> mbarrier latency would otherwise sit on the issue path of every
@@ -375,24 +373,26 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
         load_target += 8;
         ring.fill(load_target);
       }
-      wait_done();
     }
+    wait_done();   // layer 2 complete
 
     // ---- layer 3, two K halves ------------------------------------------------------
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
-      epilogue_to_h(tm_l2, bias2, half, false);
+      epilogue_to_h(tm_l2 + half * 128, bias2, half * 128, false);
       if (t == 0) {
         umma::tc_fence_after();
 #pragma unroll
         for (int ksl = 0; ksl < 8; ++ksl) {
-          const int kc = (half * 8 + ksl) * 2;   // chunk index into W3^T
-          umma::mma_bf16x3(tm_l3, d_hh, d_hl, d_b3h, d_b3l, ksl * (2 * PT_LBO_A >> 4),
-                           kc * (PT_LBO_W3 >> 4), idesc32, (half | ksl) != 0);
+          const uint32_t boff = (uint32_t)((half * 8 + ksl) * 2) * (PT_LBO_W3 >> 4);
+          const uint32_t acc = (half | ksl) != 0;
+          umma::mma_bf16_ts(tm_l3, tm_hl + ksl * 8, d_b3h + boff, idesc32, acc);
+          umma::mma_bf16_ts(tm_l3, tm_hh + ksl * 8, d_b3l + boff, idesc32, 1);
+          umma::mma_bf16_ts(tm_l3, tm_hh + ksl * 8, d_b3h + boff, idesc32, 1);
         }
         umma::mma_commit(done);
       }
-      wait_done();
+      wait_done();   // also frees the activation operand for the next half / tile
     }
 
     // ---- output: relu(acc + b3) -> pw_out[p, 32] ---------------------------------------
