@@ -1,9 +1,9 @@
 """Per-class loss weights (reference nms_net/class_weights.py:12-23).
 
 The expected weight mass is `1 - pos_weight` for background and `pos_weight`
-spread evenly over the foreground classes; index 0 is background.  The
-reference counts classes through imdb.tools.get_class_counts (data plumbing,
-out of scope), so the counts are an argument here.
+spread evenly over the foreground classes; index 0 is background.  Counts come
+from imdb.tools.get_class_counts like in the reference (or from a precomputed
+`class_counts` entry of the imdb dict).
 """
 import numpy as np
 
@@ -22,5 +22,9 @@ def class_equal_weights_from_counts(class_counts, num_classes=None):
 
 
 def class_equal_weights(imdb):
-    """Same call as the reference when the imdb dict carries `class_counts`."""
-    return class_equal_weights_from_counts(imdb['class_counts'], imdb['num_classes'])
+    """class_weights.py:12-23."""
+    counts = imdb.get('class_counts')
+    if counts is None:
+        from gossipnet_b200.imdb.tools import get_class_counts
+        counts = get_class_counts(imdb)
+    return class_equal_weights_from_counts(counts, imdb['num_classes'])

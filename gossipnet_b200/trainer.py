@@ -193,9 +193,22 @@ class Trainer(object):
         return n_images
 
     def step(self, batches, lr):
-        res = self.forward_backward(batches)
+        """One optimizer step on this rank's images (possibly none: a rank whose
+        shard of a small step is empty still joins the all-reduce)."""
+        if len(batches) == 0:
+            self.gradbuf.zero_()
+            res = {'num_images': 0, 'loss_out': None}
+        else:
+            res = self.forward_backward(batches)
         res['images_in_step'] = self.apply_gradients(lr)
         return res
+
+    def regularization_loss(self):
+        """weight_decay * sum(W^2) / 2 over the regularised weights: the term
+        tf.contrib.losses.get_total_loss() adds to the data loss (train.py:237).
+        Display only; the update applies its gradient inside the optimizer kernel."""
+        flat = self.eng.flat
+        return float(0.5 * torch.sum(self.decay * flat * flat).item())
 
     # ------------------------------------------------------- checkpoint / resume
     def state_dict(self):

@@ -10,6 +10,6 @@ import sys
 _impl = importlib.import_module('gossipnet_b200.nms_net')
 for _sub in ('config', 'class_weights', 'matching_module', 'roi_pooling_layer',
              'roi_pooling_layer.roi_pooling_op', 'roi_pooling_layer.roi_pooling_op_grad',
-             'network'):
+             'network', 'dataset', 'tools'):
     sys.modules['nms_net.' + _sub] = importlib.import_module('gossipnet_b200.nms_net.' + _sub)
 sys.modules[__name__] = _impl
