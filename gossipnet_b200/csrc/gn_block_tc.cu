@@ -23,6 +23,7 @@
 // W1^T / W2^T (hi and lo) stay resident in shared memory for the CTA's lifetime.
 // The phases of one CTA are sequential; two CTAs are resident per SM (92 KB smem,
 // 128 TMEM columns each) so one CTA's UMMAs overlap the other's CUDA-core phases.
+#include <cstdlib>
 #include "gn_common.cuh"
 #include "gn_umma.cuh"
 
@@ -377,7 +378,9 @@ static int launch_block_pair(const char* name, bool hl, const float* pw, int w, 
     return GN_ERR_CUDA;
   }
   int grid = gn::ceil_div(capacity, gn::TC_TILE);
-  const int cap = 2 * gn::sm_count();
+  int per_sm = 2;
+  if (const char* e = getenv("GN_PAIR_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : 2;   // experiments only
+  const int cap = per_sm * gn::sm_count();
   if (grid > cap) grid = cap;
   const float* fp = static_cast<const float*>(feats);
   const float* np = static_cast<const float*>(nfeats);

@@ -1,35 +1,35 @@
 // Pair features on the tensor cores: geometry (A4) + the 3-layer pair-feature
 // MLP (A5) width -> 256 -> 256 -> 32 with ReLU after every layer, fused.
 //
-// Tile = 128 pairs (the M of one tcgen05.mma), one persistent CTA per SM.
+// Tile = 128 pairs (the M of one tcgen05.mma), one persistent warp-specialised CTA per SM
+// (pwfeat_pipe_kernel below: epilogue / MMA / W2-producer / geometry warps, mbarrier
+// hand-offs, the hidden layers processed in 64-column quarters).
 //   geometry : one thread per pair computes the 9 hand-crafted features in fp32
 //              (pair_geometry, same rounding as the reference) and writes a K=16
-//              bf16 hi/lo operand row;
-//   layer 1  : [128 x 16] x [16 x 256]  (1 k-step x 3 UMMAs, N = 256) -> TMEM [0,256)
+//              bf16 hi/lo operand row, one tile ahead of the tensor core;
+//   layer 1  : [128 x 16] x [16 x 64] per quarter (3 UMMAs) -> a 64-column accumulator;
 //              single class: K rows = [c_score, n_score, 7 geometry]; multi class:
 //              the one-hot score block degenerates to two weight-row gathers that
 //              the epilogue adds in fp32 (K rows = 7 geometry only);
-//   layer 2  : [128 x 256] x [256 x 256] (16 k-steps x 3 UMMAs) -> TMEM [256,512).
-//              W2 (256 KB as bf16 hi+lo) does not fit next to the activations, so it
-//              is streamed per k-step (16 KB) from a pre-split operand image in
-//              global memory (L2 resident) through a 4-stage cp.async.bulk ring
-//              (mbarrier complete_tx / tcgen05.commit) that runs ahead of the UMMAs
-//              across the epilogue phases;
-//   layer 3  : [128 x 256] x [256 x 32] -> TMEM [0,32) (layer-1 columns are dead).
-// The activation operand tile holds 128 of the 256 K columns at a time, so each of
-// layers 2 and 3 runs as two (epilogue-half, 8 k-step) rounds.  Only pw_out[P,32]
-// goes back to HBM; the [P,256] activations never leave the SM.
+//   layer 2  : [128 x 256] x [256 x 256] (16 k-steps x 3 UMMAs, A operand in tensor
+//              memory) -> TMEM [256,512).  W2 (256 KB as bf16 hi+lo) does not fit next
+//              to the activations, so it is streamed per k-step (16 KB) from a pre-split
+//              operand image in global memory (L2 resident) through a cp.async.bulk ring
+//              (mbarrier complete_tx / tcgen05.commit);
+//   layer 3  : [128 x 256] x [256 x 32] -> the first 32 columns of the layer-2 accumulator,
+//              again quarter by quarter as the epilogue drains it.
+// Only pw_out[P,32] goes back to HBM (whole 128-byte rows through a padded staging tile);
+// the [P,256] activations never leave the SM.
 // bf16x3: every fp32 operand is split into bf16 hi + lo and each product is
 // a_lo*b_hi + a_hi*b_lo + a_hi*b_hi with fp32 accumulation (gn_umma.cuh).
+// Measured per-tile timeline and what bounds each phase: profiles/r1_tc_kernels.md.
 #include "gn_pairfeat.cuh"
 #include "gn_umma.cuh"
 
 namespace gn {
 
 constexpr int PT_TILE = 128;
-constexpr int PT_THREADS = 512;   // 16 warps: 4 TMEM lane quadrants x 4 column groups
 constexpr int PT_H = 256, PT_O = 32;
-constexpr int PT_RING = 6;
 constexpr uint32_t PT_SBO = 128;
 constexpr uint32_t PT_LBO_A = PT_TILE * 16;      // activation / A1 chunk pitch (2048)
 constexpr uint32_t PT_LBO_W = PT_H * 16;         // 256-row weight chunk pitch (4096)
@@ -46,16 +46,6 @@ constexpr uint32_t PT_IMG_B1 = PT_IMG_W2 + PT_W2_COPIES * 16 * PT_STAGE;   // hi
 constexpr uint32_t PT_IMG_B3 = PT_IMG_B1 + 2 * 2 * PT_LBO_W; // hi 16 KB, lo 16 KB
 constexpr uint32_t PT_IMG_BYTES = PT_IMG_B3 + 2 * 32 * PT_LBO_W3;
 
-// shared memory map
-constexpr uint32_t PS_RING = 0;                                   // PT_RING x 16 KB
-constexpr uint32_t PS_B1 = PS_RING + PT_RING * PT_STAGE;          // 16 KB
-constexpr uint32_t PS_B3 = PS_B1 + 2 * 2 * PT_LBO_W;              // 32 KB
-constexpr uint32_t PS_A1 = PS_B3 + 2 * 32 * PT_LBO_W3;            // hi 4 KB + lo 4 KB
-constexpr uint32_t PS_BIAS = PS_A1 + 2 * 2 * PT_LBO_A;            // b1[256] b2[256] b3[32]
-constexpr uint32_t PS_ROW = PS_BIAS + (2 * PT_H + PT_O) * 4;      // sc[128] sn[128] rc[128] rn[128]
-constexpr uint32_t PS_BAR = PS_ROW + 4 * PT_TILE * 4;             // full[R] empty[R] done
-constexpr uint32_t PS_BYTES = PS_BAR + 16 * 8;
-static_assert(PS_BYTES <= 227 * 1024, "pair MLP tile exceeds shared memory");
 
 // ---------------------------------------------------------------------------------
 // weight preparation: fp32 [in,out] -> bf16 hi/lo K-major operand images
@@ -112,35 +102,60 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(umma::smem_u32(bar)) : "memory");
 }
 
-struct PtRing {
-  uint64_t* full;
-  uint64_t* empty;
-  uint32_t ring_smem;
-  const unsigned char* w2img;
-  uint32_t loads_issued, total_loads;
-  uint32_t k0;   // per-CTA rotation of the k-step order inside each K half (spreads the
-                 // CTAs over the L2 lines of the W2 image instead of all hitting the same one)
+// ---------------------------------------------------------------------------------
+// Pipelined version: warp-specialised roles, the hidden layer processed in four
+// 64-column quarters with double-buffered layer-1 accumulators and activation operands,
+// so the epilogue of quarter q+1 runs while the layer-2 UMMAs of quarter q do.
+//
+//   warps 0-15  epilogue : TMEM lane quadrant = warp % 4, 16 of a quarter's 64 columns
+//   warp  16    MMA      : one thread issues every tcgen05.mma / commit
+//   warp  17    producer : one thread streams W2 k-steps through the cp.async.bulk ring
+//   warps 18-21 geometry : one thread per pair, one tile ahead (A1 double-buffered)
+//
+// TMEM (512 columns): L1 accumulators 2 x 64 | activation operands H[2] (K = 64 each:
+// 32 columns bf16 hi + 32 lo) | layer-2 accumulator 256 (its first 32 columns are reused
+// as the layer-3 accumulator once the first quarter has been drained).
+// Hand-offs are mbarriers: a1_full/a1_empty (geometry <-> MMA), l1_done (MMA -> epilogue),
+// h_full/h_empty (epilogue <-> MMA), acc2_done, acc3_done, tab_free (epilogue -> geometry).
+// Every operand-buffer production p uses H[p % 2]; it may start once consumption p - 2 has
+// completed (tcgen05.commit -> h_empty).
+// ---------------------------------------------------------------------------------
+constexpr int PP_EPI_WARPS = 16;
+constexpr int PP_WARP_MMA = 16, PP_WARP_LOAD = 17, PP_WARP_GEO = 18;
+constexpr int PP_THREADS = (PP_WARP_GEO + 4) * 32;   // 704
+constexpr int PP_Q = 64;                              // hidden columns per quarter
+constexpr int PP_RING = 8;                            // W2 k-step stages in flight
+constexpr uint32_t PP_OUT_PITCH = 144;                // output staging row pitch (bytes): 128 + 16,
+                                                      // so 8 consecutive rows hit 8 distinct 16-byte bank groups
 
-  // issue every W2 k-step load up to (exclusive) index `upto`
-  __device__ __forceinline__ void fill(uint32_t upto) {
-    while (loads_issued < upto && loads_issued < total_loads) {
-      const uint32_t i = loads_issued, s = i % PT_RING;
-      if (i >= PT_RING) umma::mbar_wait(&empty[s], ((i / PT_RING) - 1) & 1);
-      bulk_g2s(ring_smem + s * PT_STAGE, w2img + (size_t)((i & 8u) | (((i & 7u) + k0) & 7u)) * PT_STAGE, PT_STAGE, &full[s]);
-      ++loads_issued;
-    }
-  }
-};
+constexpr uint32_t PQ_RING = 0;
+constexpr uint32_t PQ_B1 = PQ_RING + PP_RING * PT_STAGE;
+constexpr uint32_t PQ_B3 = PQ_B1 + 2 * 2 * PT_LBO_W;
+constexpr uint32_t PQ_A1 = PQ_B3 + 2 * 32 * PT_LBO_W3;            // 2 buffers x (hi 4 KB + lo 4 KB)
+constexpr uint32_t PQ_BIAS = PQ_A1 + 2 * 2 * 2 * PT_LBO_A;
+constexpr uint32_t PQ_ROW = PQ_BIAS + (2 * PT_H + PT_O) * 4;      // 2 x (sc, sn, rc, rn)[128]
+constexpr uint32_t PQ_OUT = PQ_ROW + 2 * 4 * PT_TILE * 4;          // output staging tile
+constexpr uint32_t PQ_BAR = PQ_OUT + PT_TILE * PP_OUT_PITCH;
+constexpr int PQ_NBAR = 2 * PP_RING + 14;
+constexpr uint32_t PQ_BYTES = PQ_BAR + PQ_NBAR * 8;
+static_assert(PQ_BYTES <= 227 * 1024, "pipelined pair MLP exceeds shared memory");
+
+#ifdef PP_TRACE
+__device__ long long pp_trace[64];
+#define PP_TR(i) do { if (blockIdx.x == 0 && it == 2) pp_trace[i] = clock64(); } while (0)
+#else
+#define PP_TR(i) do { } while (0)
+#endif
 
 template <bool MULTI>
-__global__ void __launch_bounds__(PT_THREADS, 1)
-pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ scores,
-                 const int32_t* __restrict__ classes, const int32_t* __restrict__ pair_c,
-                 const int32_t* __restrict__ pair_n, const float* __restrict__ pair_iou,
-                 const int32_t* __restrict__ num_pairs, int capacity, int num_classes, float mult,
-                 const float* __restrict__ w1, const float* __restrict__ b1,
-                 const float* __restrict__ b2, const float* __restrict__ b3,
-                 const unsigned char* __restrict__ img, float* __restrict__ pw_out) {
+__global__ void __launch_bounds__(PP_THREADS, 1)
+pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ scores,
+                   const int32_t* __restrict__ classes, const int32_t* __restrict__ pair_c,
+                   const int32_t* __restrict__ pair_n, const float* __restrict__ pair_iou,
+                   const int32_t* __restrict__ num_pairs, int capacity, int num_classes, float mult,
+                   const float* __restrict__ w1, const float* __restrict__ b1,
+                   const float* __restrict__ b2, const float* __restrict__ b3,
+                   const unsigned char* __restrict__ img, float* __restrict__ pw_out) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -149,34 +164,44 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   if ((int)blockIdx.x >= num_tiles) return;
   const int my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-  unsigned char* a1_hi = smem + PS_A1;
-  unsigned char* a1_lo = a1_hi + 2 * PT_LBO_A;
-  float* bias1 = reinterpret_cast<float*>(smem + PS_BIAS);
+  float* bias1 = reinterpret_cast<float*>(smem + PQ_BIAS);
   float* bias2 = bias1 + PT_H;
   float* bias3 = bias2 + PT_H;
-  float* row_sc = reinterpret_cast<float*>(smem + PS_ROW);
-  float* row_sn = row_sc + PT_TILE;
-  int* row_rc = reinterpret_cast<int*>(row_sn + PT_TILE);
-  int* row_rn = row_rc + PT_TILE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + PS_BAR);
-  uint64_t* empty = full + PT_RING;
-  uint64_t* done = empty + PT_RING;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + PQ_BAR);
+  uint64_t* full = bars;                       // [RING] W2 stage landed
+  uint64_t* empty = full + PP_RING;            // [RING] W2 stage consumed
+  uint64_t* a1_full = empty + PP_RING;         // [2]
+  uint64_t* a1_empty = a1_full + 2;            // [2]
+  uint64_t* l1_done = a1_empty + 2;            // [2]
+  uint64_t* h_full = l1_done + 2;              // [2]
+  uint64_t* h_empty = h_full + 2;              // [2]
+  uint64_t* tab_free = h_empty + 2;            // [2]
+  uint64_t* acc2_done = tab_free + 2;          // [1]
+  uint64_t* acc3_done = acc2_done + 1;         // [1]
 
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
   if (t == 0) {
-    for (int s = 0; s < PT_RING; ++s) {
+    for (int s = 0; s < PP_RING; ++s) {
       umma::mbar_init(&full[s], 1);
       umma::mbar_init(&empty[s], 1);
     }
-    umma::mbar_init(done, 1);
+    for (int b = 0; b < 2; ++b) {
+      umma::mbar_init(&a1_full[b], 4);
+      umma::mbar_init(&a1_empty[b], 1);
+      umma::mbar_init(&l1_done[b], 1);
+      umma::mbar_init(&h_full[b], PP_EPI_WARPS);
+      umma::mbar_init(&h_empty[b], 1);
+      umma::mbar_init(&tab_free[b], PP_EPI_WARPS);
+    }
+    umma::mbar_init(acc2_done, 1);
+    umma::mbar_init(acc3_done, 1);
     umma::fence_barrier_init();
   }
-  // resident operands: B1, B3 (already split, copied verbatim), biases
-  for (int i = t; i < (int)(2 * 2 * PT_LBO_W) / 16; i += PT_THREADS)
-    reinterpret_cast<uint4*>(smem + PS_B1)[i] = __ldg(reinterpret_cast<const uint4*>(img + PT_IMG_B1) + i);
-  for (int i = t; i < (int)(2 * 32 * PT_LBO_W3) / 16; i += PT_THREADS)
-    reinterpret_cast<uint4*>(smem + PS_B3)[i] = __ldg(reinterpret_cast<const uint4*>(img + PT_IMG_B3) + i);
-  for (int i = t; i < PT_H; i += PT_THREADS) {
+  for (int i = t; i < (int)(2 * 2 * PT_LBO_W) / 16; i += PP_THREADS)
+    reinterpret_cast<uint4*>(smem + PQ_B1)[i] = __ldg(reinterpret_cast<const uint4*>(img + PT_IMG_B1) + i);
+  for (int i = t; i < (int)(2 * 32 * PT_LBO_W3) / 16; i += PP_THREADS)
+    reinterpret_cast<uint4*>(smem + PQ_B3)[i] = __ldg(reinterpret_cast<const uint4*>(img + PT_IMG_B3) + i);
+  for (int i = t; i < PT_H; i += PP_THREADS) {
     bias1[i] = __ldg(b1 + i);
     bias2[i] = __ldg(b2 + i);
   }
@@ -187,234 +212,289 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
   umma::tc_fence_after();
 
   const uint32_t tmem = tmem_base_s;
-  // TMEM map: layer-1 accumulator of one 128-column half [0,128) (layer-3 accumulator
-  // [0,32) later), activation operand hi [128,192) + lo [192,256) (128 K elements, two
-  // bf16 per column), layer-2 accumulator [256,512)
-  const uint32_t tm_l1 = tmem, tm_hh = tmem + 128, tm_hl = tmem + 192, tm_l2 = tmem + PT_H, tm_l3 = tmem;
-  const uint32_t idesc128 = umma::idesc_bf16_f32(PT_TILE, 128);
-  const uint32_t idesc256 = umma::idesc_bf16_f32(PT_TILE, PT_H);
-  const uint32_t idesc32 = umma::idesc_bf16_f32(PT_TILE, PT_O);
-  const uint32_t s_ring = umma::smem_u32(smem + PS_RING);
-  const uint32_t s_a1h = umma::smem_u32(a1_hi), s_a1l = umma::smem_u32(a1_lo);
-  const uint32_t s_b1h = umma::smem_u32(smem + PS_B1), s_b1l = s_b1h + 2 * PT_LBO_W;
-  const uint32_t s_b3h = umma::smem_u32(smem + PS_B3), s_b3l = s_b3h + 32 * PT_LBO_W3;
+  const uint32_t tm_l1 = tmem;              // L1 accumulator buffers: +0, +64
+  const uint32_t tm_h = tmem + 128;         // H[b] at +64 b: hi 32 columns, lo 32 columns
+  const uint32_t tm_l2 = tmem + 256;        // layer-2 accumulator (256), layer-3 in its first 32
 
-  // kernel-lifetime operand descriptors; the issue loops only add start-address offsets
-  const uint64_t d_a1h = umma::smem_desc(s_a1h, PT_LBO_A, PT_SBO), d_a1l = umma::smem_desc(s_a1l, PT_LBO_A, PT_SBO);
-  const uint64_t d_b1h = umma::smem_desc(s_b1h, PT_LBO_W, PT_SBO), d_b1l = umma::smem_desc(s_b1l, PT_LBO_W, PT_SBO);
-  const uint64_t d_ringh = umma::smem_desc(s_ring, PT_LBO_W, PT_SBO);
-  const uint64_t d_ringl = umma::smem_desc(s_ring + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
-  const uint64_t d_b3h = umma::smem_desc(s_b3h, PT_LBO_W3, PT_SBO), d_b3l = umma::smem_desc(s_b3l, PT_LBO_W3, PT_SBO);
-
-  PtRing ring{full, empty, s_ring,
-              img + PT_IMG_W2 + (size_t)(blockIdx.x % PT_W2_COPIES) * 16 * PT_STAGE, 0u, (uint32_t)my_tiles * 16u,
-              0u};   // rotation off: results stay independent of the tile -> CTA mapping
-  uint32_t mma_k = 0;     // W2 k-steps consumed so far (thread 0 only)
-  uint32_t done_par = 0;  // parity of the next `done` completion (all threads)
-  uint32_t load_target = PT_RING;   // W2 k-steps requested so far (producer thread only)
-  if (t == 32) ring.fill(load_target);
-
-  // epilogue mapping: TMEM lane quadrant = warp % 4; within a 128-column half the
-  // warp owns columns [32 * (warp / 4), +32)
-  const int erow = (warp & 3) * 32 + lane;
-  const int ecol = (warp >> 2) * 32;
-  const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
-  // one half-epilogue: relu(acc[:, ecol..+32] + bias[col0 + ecol ..] (+ score rows)) -> the
-  // activation operand in TENSOR MEMORY (bf16 hi / lo pairs; TS-form UMMAs read it)
-  auto epilogue_to_h = [&](uint32_t tm_src, const float* bias, int col0, bool add_scores) {
-    float va[32];
-    umma::tmem_ld32(tm_src + tlane + ecol, va);
-    umma::tmem_ld_wait();
-    uint32_t hh[16], hl[16];
-#pragma unroll
-    for (int cc = 0; cc < 32; cc += 16) {
-      float v[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = va[cc + e];
-      const int col = col0 + ecol + cc;
-      if (MULTI && add_scores) {
-        const float sc = row_sc[erow], sn = row_sn[erow];
-        const float* wc = w1 + (size_t)row_rc[erow] * PT_H + col;
-        const float* wn = w1 + (size_t)row_rn[erow] * PT_H + col;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const float4 a = ldg4(wc + g * 4), b = ldg4(wn + g * 4);
-          v[g * 4 + 0] += sc * a.x + sn * b.x;
-          v[g * 4 + 1] += sc * a.y + sn * b.y;
-          v[g * 4 + 2] += sc * a.z + sn * b.z;
-          v[g * 4 + 3] += sc * a.w + sn * b.w;
-        }
-      }
+  if (warp < PP_EPI_WARPS) {
+    // =========================== epilogue warps =====================================
+    const int quad = warp & 3, cg = warp >> 2;
+    const int erow = quad * 32 + lane;
+    const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+    uint32_t prod = 0;
+    // relu(v + bias) of this thread's 16 columns -> H[prod % 2] (bf16 hi | lo), then hand over
+    auto produce = [&](float (&v)[16], const float* bias16) {
+      uint32_t hh[8], hl[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e)
-        umma::split_bf16x2(fmaxf(v[2 * e] + bias[col + 2 * e], 0.f),
-                           fmaxf(v[2 * e + 1] + bias[col + 2 * e + 1], 0.f),
-                           hh[(cc >> 1) + e], hl[(cc >> 1) + e]);
+        umma::split_bf16x2(fmaxf(v[2 * e] + bias16[2 * e], 0.f),
+                           fmaxf(v[2 * e + 1] + bias16[2 * e + 1], 0.f), hh[e], hl[e]);
+      const uint32_t b = prod & 1u, u = prod >> 1;
+      if (u >= 1) umma::mbar_wait(&h_empty[b], (u - 1) & 1u);
+      umma::tc_fence_after();
+      const uint32_t dst = tm_h + b * 64 + tlane + (uint32_t)cg * 8;
+      umma::tmem_st8(dst, hh);
+      umma::tmem_st8(dst + 32, hl);
+      umma::tmem_st_wait();
+      umma::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&h_full[b]);
+      ++prod;
+    };
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int tb = it & 1;
+      const float* row_sc = reinterpret_cast<const float*>(smem + PQ_ROW) + tb * 4 * PT_TILE;
+      const float* row_sn = row_sc + PT_TILE;
+      const int* row_rc = reinterpret_cast<const int*>(row_sn + PT_TILE);
+      const int* row_rn = row_rc + PT_TILE;
+      // ---- layer-1 quarters -> H ------------------------------------------------------
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t n = 2u * (uint32_t)it + (uint32_t)(q >> 1);
+        umma::mbar_wait(&l1_done[q & 1], n & 1u);
+        umma::tc_fence_after();
+        if (t == 0) PP_TR(32 + 2 * q);
+        float v[16];
+        umma::tmem_ld16(tm_l1 + (uint32_t)(q & 1) * 64 + tlane + (uint32_t)cg * 16, v);
+        umma::tmem_ld_wait();
+        const int col = q * PP_Q + cg * 16;
+        if (MULTI) {
+          const float sc = row_sc[erow], sn = row_sn[erow];
+          const float* wc = w1 + (size_t)row_rc[erow] * PT_H + col;
+          const float* wn = w1 + (size_t)row_rn[erow] * PT_H + col;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 a = ldg4(wc + g * 4), b = ldg4(wn + g * 4);
+            v[g * 4 + 0] += sc * a.x + sn * b.x;
+            v[g * 4 + 1] += sc * a.y + sn * b.y;
+            v[g * 4 + 2] += sc * a.z + sn * b.z;
+            v[g * 4 + 3] += sc * a.w + sn * b.w;
+          }
+        }
+        produce(v, bias1 + col);
+        if (t == 0) PP_TR(33 + 2 * q);
+      }
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&tab_free[tb]);   // score tables of this tile are dead
+      // ---- layer-2 accumulator quarters -> H --------------------------------------------
+      umma::mbar_wait(acc2_done, (uint32_t)it & 1u);
+      umma::tc_fence_after();
+      if (t == 0) PP_TR(40);
+#pragma unroll 1
+      for (int q = 0; q < 4; ++q) {
+        float v[16];
+        const int col = q * PP_Q + cg * 16;
+        umma::tmem_ld16(tm_l2 + tlane + (uint32_t)col, v);
+        umma::tmem_ld_wait();
+        produce(v, bias2 + col);
+        if (t == 0) PP_TR(41 + q);
+      }
+      // ---- output: relu(acc3 + b3) -> pw_out[p, 32]; this warp owns 8 columns -------------
+      umma::mbar_wait(acc3_done, (uint32_t)it & 1u);
+      umma::tc_fence_after();
+      if (t == 0) PP_TR(45);
+      {
+        // this thread's 8 columns of its row -> padded staging tile; then every warp writes
+        // whole 128-byte rows (a row-per-thread store would cost one L1 wavefront per lane)
+        float v[8];
+        umma::tmem_ld8(tm_l2 + tlane + (uint32_t)cg * 8, v);
+        umma::tmem_ld_wait();
+        if (t == 0) PP_TR(47);
+        const float* bb = bias3 + cg * 8;
+        unsigned char* stage = smem + PQ_OUT;
+        float4* dst = reinterpret_cast<float4*>(stage + erow * PP_OUT_PITCH + cg * 32);
+        dst[0] = make_float4(fmaxf(v[0] + bb[0], 0.f), fmaxf(v[1] + bb[1], 0.f),
+                             fmaxf(v[2] + bb[2], 0.f), fmaxf(v[3] + bb[3], 0.f));
+        dst[1] = make_float4(fmaxf(v[4] + bb[4], 0.f), fmaxf(v[5] + bb[5], 0.f),
+                             fmaxf(v[6] + bb[6], 0.f), fmaxf(v[7] + bb[7], 0.f));
+        asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int idx = i * (PP_EPI_WARPS * 32) + t;       // 1024 chunks of 16 bytes
+          const int r = idx >> 3, ch = idx & 7;
+          const int p = tile * PT_TILE + r;
+          const float4 x = *reinterpret_cast<const float4*>(stage + r * PP_OUT_PITCH + ch * 16);
+          if (p < P) *reinterpret_cast<float4*>(pw_out + (size_t)p * PT_O + ch * 4) = x;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");   // staging reusable
+      }
+      if (t == 0) PP_TR(46);
+      umma::tc_fence_before();   // the next production's arrive orders these loads before the
+                                 // UMMAs that overwrite the accumulator
     }
-    const uint32_t c0 = (uint32_t)(ecol >> 1);
-    umma::tmem_st8(tm_hh + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hh[0]));
-    umma::tmem_st8(tm_hh + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hh[8]));
-    umma::tmem_st8(tm_hl + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hl[0]));
-    umma::tmem_st8(tm_hl + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hl[8]));
-    umma::tmem_st_wait();
-    umma::tc_fence_before();
-    __syncthreads();
-  };
-  auto wait_done = [&]() {
-    umma::mbar_wait(done, done_par);
-    done_par ^= 1;
-    umma::tc_fence_after();
-  };
-
-  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int p0 = tile * PT_TILE;
-
-    // ---- geometry -> A1 (K = 16): two threads per pair -------------------------------
-    // role 0 (t < 128): iou and the three distances; role 1 (128 <= t < 256): the three
-    // log ratios, the scores and the zero padding.  Each stores its own bf16 hi / lo
-    // elements of the operand row (single class: [sc sn | iou xd yd l2 | wd hd] [ad 0..];
-    // multi class: [iou xd yd l2 | wd hd ad 0] [0..]).
-    if (t < 2 * PT_TILE) {
-      const int row = t & (PT_TILE - 1), role = t >> 7;
-      const int p = p0 + row;
+  } else if (warp == PP_WARP_MMA) {
+    // =============================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc64 = umma::idesc_bf16_f32(PT_TILE, PP_Q);
+      const uint32_t idesc256 = umma::idesc_bf16_f32(PT_TILE, PT_H);
+      const uint32_t idesc32 = umma::idesc_bf16_f32(PT_TILE, PT_O);
+      const uint32_t s_ring = umma::smem_u32(smem + PQ_RING);
+      const uint32_t s_a1 = umma::smem_u32(smem + PQ_A1);
+      const uint32_t s_b1h = umma::smem_u32(smem + PQ_B1), s_b1l = s_b1h + 2 * PT_LBO_W;
+      const uint32_t s_b3h = umma::smem_u32(smem + PQ_B3), s_b3l = s_b3h + 32 * PT_LBO_W3;
+      const uint64_t d_b1h = umma::smem_desc(s_b1h, PT_LBO_W, PT_SBO), d_b1l = umma::smem_desc(s_b1l, PT_LBO_W, PT_SBO);
+      const uint64_t d_ringh = umma::smem_desc(s_ring, PT_LBO_W, PT_SBO);
+      const uint64_t d_ringl = umma::smem_desc(s_ring + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
+      const uint64_t d_b3h = umma::smem_desc(s_b3h, PT_LBO_W3, PT_SBO), d_b3l = umma::smem_desc(s_b3l, PT_LBO_W3, PT_SBO);
+      uint32_t cons = 0, ring_k = 0;
+      // layer 1 of quarter q of the tile whose A1 sits in buffer ab -> L1 accumulator q % 2
+      auto issue_l1 = [&](int ab, int q) {
+        const uint64_t d_ah = umma::smem_desc(s_a1 + (uint32_t)ab * (4 * PT_LBO_A), PT_LBO_A, PT_SBO);
+        const uint64_t d_al = umma::smem_desc(s_a1 + (uint32_t)ab * (4 * PT_LBO_A) + 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
+        umma::mma_bf16x3(tm_l1 + (uint32_t)(q & 1) * 64, d_ah, d_al, d_b1h, d_b1l, 0,
+                         (uint32_t)q * (PP_Q * 16 >> 4), idesc64, 0);
+        umma::mma_commit(&l1_done[q & 1]);
+      };
+      umma::mbar_wait(&a1_full[0], 0);
+      umma::tc_fence_after();
+      issue_l1(0, 0);
+      issue_l1(0, 1);
+#pragma unroll 1
+      for (int it = 0; it < my_tiles; ++it) {
+        const int ab = it & 1;
+        PP_TR(0);
+        // ---- layer 2: quarter q of K as soon as its operand is there -------------------
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t hb = cons & 1u;
+          umma::mbar_wait(&h_full[hb], (cons >> 1) & 1u);
+          umma::tc_fence_after();
+          PP_TR(1 + 2 * q);
+          const uint32_t a_hi = tm_h + hb * 64, a_lo = a_hi + 32;
+#pragma unroll 1
+          for (int ksl = 0; ksl < 4; ++ksl) {
+            const uint32_t g = ring_k++, s = g % PP_RING;
+#ifndef PP_NORING
+            umma::mbar_wait(&full[s], (g / PP_RING) & 1u);
+#endif
+            umma::tc_fence_after();
+            const uint32_t boff = s * (PT_STAGE >> 4);
+            const uint32_t acc = (q | ksl) != 0;
+            umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_ringh + boff, idesc256, acc);
+            umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringl + boff, idesc256, 1);
+            umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringh + boff, idesc256, 1);
+            umma::mma_commit(&empty[s]);
+          }
+          umma::mma_commit(&h_empty[hb]);
+          PP_TR(2 + 2 * q);
+          ++cons;
+          if (q < 2) {
+            issue_l1(ab, q + 2);
+            if (q == 1) umma::mma_commit(&a1_empty[ab]);   // A1[ab] has been read for the last time
+          }
+        }
+        umma::mma_commit(acc2_done);
+        // ---- layer 3 ------------------------------------------------------------------------
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t hb = cons & 1u;
+          umma::mbar_wait(&h_full[hb], (cons >> 1) & 1u);
+          umma::tc_fence_after();
+          PP_TR(10 + 2 * q);
+          const uint32_t a_hi = tm_h + hb * 64, a_lo = a_hi + 32;
+#pragma unroll
+          for (int ksl = 0; ksl < 4; ++ksl) {
+            const uint32_t boff = (uint32_t)((q * 4 + ksl) * 2) * (PT_LBO_W3 >> 4);
+            const uint32_t acc = (q | ksl) != 0;
+            umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_b3h + boff, idesc32, acc);
+            umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3l + boff, idesc32, 1);
+            umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3h + boff, idesc32, 1);
+          }
+          umma::mma_commit(&h_empty[hb]);
+          ++cons;
+        }
+        umma::mma_commit(acc3_done);
+        PP_TR(20);
+        // ---- the next tile's first two layer-1 quarters queue up behind layer 3 ---------------
+        if (it + 1 < my_tiles) {
+          const int nb = (it + 1) & 1;
+          umma::mbar_wait(&a1_full[nb], (uint32_t)((it + 1) >> 1) & 1u);
+          umma::tc_fence_after();
+          issue_l1(nb, 0);
+          issue_l1(nb, 1);
+        }
+      }
+    }
+  } else if (warp == PP_WARP_LOAD) {
+    // ============================== W2 producer =========================================
+    if (lane == 0) {
+      const uint32_t s_ring = umma::smem_u32(smem + PQ_RING);
+      uint32_t total = (uint32_t)my_tiles * 16u;
+#ifdef PP_NORING
+      total = 0;
+#endif
+      for (uint32_t i = 0; i < total; ++i) {
+        const uint32_t s = i % PP_RING;
+        if (i >= PP_RING) umma::mbar_wait(&empty[s], ((i / PP_RING) - 1) & 1u);
+        bulk_g2s(s_ring + s * PT_STAGE, img + PT_IMG_W2 + (size_t)((blockIdx.x % PT_W2_COPIES) * 16 + (i & 15u)) * PT_STAGE, PT_STAGE, &full[s]);
+      }
+    }
+  } else {
+    // ================================ geometry ============================================
+    const int row = (warp - PP_WARP_GEO) * 32 + lane;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int ab = it & 1;
+      const uint32_t u = (uint32_t)it >> 1;
+      const int p = tile * PT_TILE + row;
       const bool live = p < P;
       int c = 0, n = 0;
       float4 cbx = make_float4(0.f, 0.f, 1.f, 1.f), nbx = cbx;
+      float iou = 0.f, sc = 0.f, sn = 0.f;
+      int rc = 0, rn = 0;
       if (live) {
         c = __ldg(pair_c + p);
         n = __ldg(pair_n + p);
+        iou = __ldg(pair_iou + p);
         cbx = ldg4(dets + (size_t)c * 4);
         nbx = ldg4(dets + (size_t)n * 4);
-      }
-      __nv_bfloat16* hi0 = reinterpret_cast<__nv_bfloat16*>(a1_hi + row * 16);
-      __nv_bfloat16* lo0 = reinterpret_cast<__nv_bfloat16*>(a1_lo + row * 16);
-      auto put2 = [&](int e, float x0, float x1) {      // elements e, e+1 of chunk 0
-        uint32_t h, l;
-        umma::split_bf16x2(x0, x1, h, l);
-        *reinterpret_cast<uint32_t*>(hi0 + e) = h;
-        *reinterpret_cast<uint32_t*>(lo0 + e) = l;
-      };
-      if (role == 0) {
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
-        if (live) pair_geometry_dist(cbx, nbx, __ldg(pair_iou + p), mult, g);
-        const int e0 = MULTI ? 0 : 2;
-        put2(e0, g[0], g[1]);
-        put2(e0 + 2, g[2], g[3]);
-      } else {
-        float g[3] = {0.f, 0.f, 0.f};
-        float sc = 0.f, sn = 0.f;
-        int rc = 0, rn = 0;
-        if (live) {
-          pair_geometry_logs(cbx, nbx, mult, g);
-          sc = __fmul_rn(__ldg(scores + c), mult);
-          sn = __fmul_rn(__ldg(scores + n), mult);
-          if (MULTI) {
-            rc = __ldg(classes + c) - 1;               // one-based classes (network.py:413-419)
-            rn = num_classes + __ldg(classes + n) - 1;
-          }
-        }
-        uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        sc = __fmul_rn(__ldg(scores + c), mult);
+        sn = __fmul_rn(__ldg(scores + n), mult);
         if (MULTI) {
-          row_sc[row] = sc; row_sn[row] = sn; row_rc[row] = rc; row_rn[row] = rn;
-          put2(4, g[0], g[1]);
-          put2(6, g[2], 0.f);
-          *reinterpret_cast<uint4*>(a1_hi + PT_LBO_A + row * 16) = z;
-          *reinterpret_cast<uint4*>(a1_lo + PT_LBO_A + row * 16) = z;
-        } else {
-          put2(0, sc, sn);
-          put2(6, g[0], g[1]);
-          uint32_t h, l;
-          umma::split_bf16x2(g[2], 0.f, h, l);
-          uint4 zh = z, zl = z;
-          zh.x = h;
-          zl.x = l;
-          *reinterpret_cast<uint4*>(a1_hi + PT_LBO_A + row * 16) = zh;
-          *reinterpret_cast<uint4*>(a1_lo + PT_LBO_A + row * 16) = zl;
+          rc = __ldg(classes + c) - 1;               // one-based classes (network.py:413-419)
+          rn = num_classes + __ldg(classes + n) - 1;
         }
       }
-    }
-    umma::fence_smem_to_async();
-    umma::tc_fence_before();
-    __syncthreads();
-
-    // ---- layers 1 + 2, per 128-column half of the hidden layer ---------------------------
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      if (t == 0) {
-        umma::tc_fence_after();
-        // layer 1, output columns [128*half, +128): rows 128*half.. of the B1 tile
-        umma::mma_bf16x3(tm_l1, d_a1h, d_a1l, d_b1h, d_b1l, 0, half * (128 * 16 >> 4), idesc128, 0);
-        umma::mma_commit(done);
+      float g[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (live) {
+        pair_geometry_dist(cbx, nbx, iou, mult, g);
+        pair_geometry_logs(cbx, nbx, mult, g + 4);
       }
-      // UMMAs complete in order: this also covers the layer-2 UMMAs of the previous half,
-      // so the activation operand may be overwritten
-      wait_done();
-      epilogue_to_h(tm_l1, bias1, half * 128, true);
-      if (t == 0) {
-        umma::tc_fence_after();
-#pragma unroll 1
-        for (int ksl = 0; ksl < 8; ++ksl) {
-          const uint32_t g = mma_k++, s = g % PT_RING;
-          umma::mbar_wait(&full[s], (g / PT_RING) & 1);
-          umma::tc_fence_after();
-          const uint32_t boff = s * (PT_STAGE >> 4);
-          const uint32_t acc = (half | ksl) != 0;
-          umma::mma_bf16_ts(tm_l2, tm_hl + ksl * 8, d_ringh + boff, idesc256, acc);
-          umma::mma_bf16_ts(tm_l2, tm_hh + ksl * 8, d_ringl + boff, idesc256, 1);
-          umma::mma_bf16_ts(tm_l2, tm_hh + ksl * 8, d_ringh + boff, idesc256, 1);
-          umma::mma_commit(&empty[s]);   // slot s is free once these UMMAs have run
-        }
-        if (half == 1) umma::mma_commit(done);
-      } else if (t == 32) {
-        // W2 producer (its own thread, so the UMMA issuer never waits on a completion:
-        // the commit -> mbarrier latency would otherwise sit on the issue path of every
-        // k-step).  Refill every slot this round frees; the last wait resolves with the
-        // round's last UMMA.
-        load_target += 8;
-        ring.fill(load_target);
+      uint4 h0, l0, h1 = make_uint4(0u, 0u, 0u, 0u), l1 = h1;
+      if (MULTI) {      // [iou xd yd l2 | wd hd ad 0] [0 ...]
+        umma::split_bf16x2(g[0], g[1], h0.x, l0.x);
+        umma::split_bf16x2(g[2], g[3], h0.y, l0.y);
+        umma::split_bf16x2(g[4], g[5], h0.z, l0.z);
+        umma::split_bf16x2(g[6], 0.f, h0.w, l0.w);
+      } else {          // [sc sn | iou xd yd l2 | wd hd] [ad 0 ...]
+        umma::split_bf16x2(sc, sn, h0.x, l0.x);
+        umma::split_bf16x2(g[0], g[1], h0.y, l0.y);
+        umma::split_bf16x2(g[2], g[3], h0.z, l0.z);
+        umma::split_bf16x2(g[4], g[5], h0.w, l0.w);
+        umma::split_bf16x2(g[6], 0.f, h1.x, l1.x);
       }
-    }
-    wait_done();   // layer 2 complete
-
-    // ---- layer 3, two K halves ------------------------------------------------------
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      epilogue_to_h(tm_l2 + half * 128, bias2, half * 128, false);
-      if (t == 0) {
-        umma::tc_fence_after();
-#pragma unroll
-        for (int ksl = 0; ksl < 8; ++ksl) {
-          const uint32_t boff = (uint32_t)((half * 8 + ksl) * 2) * (PT_LBO_W3 >> 4);
-          const uint32_t acc = (half | ksl) != 0;
-          umma::mma_bf16_ts(tm_l3, tm_hl + ksl * 8, d_b3h + boff, idesc32, acc);
-          umma::mma_bf16_ts(tm_l3, tm_hh + ksl * 8, d_b3l + boff, idesc32, 1);
-          umma::mma_bf16_ts(tm_l3, tm_hh + ksl * 8, d_b3h + boff, idesc32, 1);
-        }
-        umma::mma_commit(done);
+      if (u >= 1) {
+        umma::mbar_wait(&a1_empty[ab], (u - 1) & 1u);
+        umma::mbar_wait(&tab_free[ab], (u - 1) & 1u);
       }
-      wait_done();   // also frees the activation operand for the next half / tile
-    }
-
-    // ---- output: relu(acc + b3) -> pw_out[p, 32] ---------------------------------------
-    if (warp < 4) {
-      const int p = p0 + erow;
-#pragma unroll
-      for (int cc = 0; cc < PT_O; cc += 16) {
-        float v[16];
-        umma::tmem_ld16(tm_l3 + tlane + cc, v);
-        umma::tmem_ld_wait();
-        if (p < P) {
-          float* dst = pw_out + (size_t)p * PT_O + cc;
-#pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<float4*>(dst + g * 4) = make_float4(
-                fmaxf(v[g * 4 + 0] + bias3[cc + g * 4 + 0], 0.f), fmaxf(v[g * 4 + 1] + bias3[cc + g * 4 + 1], 0.f),
-                fmaxf(v[g * 4 + 2] + bias3[cc + g * 4 + 2], 0.f), fmaxf(v[g * 4 + 3] + bias3[cc + g * 4 + 3], 0.f));
-        }
+      unsigned char* a_hi = smem + PQ_A1 + ab * (4 * PT_LBO_A);
+      unsigned char* a_lo = a_hi + 2 * PT_LBO_A;
+      *reinterpret_cast<uint4*>(a_hi + row * 16) = h0;
+      *reinterpret_cast<uint4*>(a_lo + row * 16) = l0;
+      *reinterpret_cast<uint4*>(a_hi + PT_LBO_A + row * 16) = h1;
+      *reinterpret_cast<uint4*>(a_lo + PT_LBO_A + row * 16) = l1;
+      if (MULTI) {
+        float* t_sc = reinterpret_cast<float*>(smem + PQ_ROW) + ab * 4 * PT_TILE;
+        t_sc[row] = sc;
+        t_sc[PT_TILE + row] = sn;
+        reinterpret_cast<int*>(t_sc)[2 * PT_TILE + row] = rc;
+        reinterpret_cast<int*>(t_sc)[3 * PT_TILE + row] = rn;
       }
+      umma::fence_smem_to_async();
+      __syncwarp();
+      if (lane == 0) umma::mbar_arrive(&a1_full[ab]);
     }
-    umma::tc_fence_before();
-    __syncthreads();   // TMEM [0,32) and the row tables are free for the next tile
   }
 
   umma::tc_fence_before();
@@ -423,6 +503,12 @@ pwfeat_tc_kernel(const float* __restrict__ dets, const float* __restrict__ score
 }
 
 }  // namespace gn
+
+#ifdef PP_TRACE
+extern "C" int gn_pwfeat_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, gn::pp_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int64_t gn_pwfeat_prep_bytes(void) { return (int64_t)gn::PT_IMG_BYTES; }
 
@@ -455,17 +541,17 @@ extern "C" int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const i
   if (grid > sms) grid = sms;
   cudaError_t e;
   if (num_classes > 1) {
-    e = cudaFuncSetAttribute(gn::pwfeat_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)gn::PS_BYTES);
+    e = cudaFuncSetAttribute(gn::pwfeat_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gn::PQ_BYTES);
     if (e == cudaSuccess)
-      gn::pwfeat_tc_kernel<true><<<grid, gn::PT_THREADS, gn::PS_BYTES, s>>>(
+      gn::pwfeat_pipe_kernel<true><<<grid, gn::PP_THREADS, gn::PQ_BYTES, s>>>(
           dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,
           multiplier, w1, b1, b2, b3, img, pw_out);
   } else {
-    e = cudaFuncSetAttribute(gn::pwfeat_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)gn::PS_BYTES);
+    e = cudaFuncSetAttribute(gn::pwfeat_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)gn::PQ_BYTES);
     if (e == cudaSuccess)
-      gn::pwfeat_tc_kernel<false><<<grid, gn::PT_THREADS, gn::PS_BYTES, s>>>(
+      gn::pwfeat_pipe_kernel<false><<<grid, gn::PP_THREADS, gn::PQ_BYTES, s>>>(
           dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,
           multiplier, w1, b1, b2, b3, img, pw_out);
   }
