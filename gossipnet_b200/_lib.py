@@ -44,6 +44,11 @@ SIGNATURES = {
     'gn_block_pair_fwd_hl': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                              c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_void_p, c_void_p],
+    'gn_predict_collapse': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'gn_rowdot_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],
+    'gn_block_pair_fwd_pipe': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                               c_void_p],
     'gn_block_pair_image_bytes': [],
     'gn_block_det_image_bytes': [],
     'gn_prepare_operands': [c_void_p, c_void_p, c_int, c_void_p, c_void_p],

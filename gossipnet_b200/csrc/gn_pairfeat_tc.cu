@@ -230,7 +230,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         umma::split_bf16x2(fmaxf(v[2 * e] + bias16[2 * e], 0.f),
                            fmaxf(v[2 * e + 1] + bias16[2 * e + 1], 0.f), hh[e], hl[e]);
       const uint32_t b = prod & 1u, u = prod >> 1;
-      if (u >= 1) umma::mbar_wait(&h_empty[b], (u - 1) & 1u);
+      if (u >= 1) umma::mbar_wait_relaxed(&h_empty[b], (u - 1) & 1u);
       umma::tc_fence_after();
       const uint32_t dst = tm_h + b * 64 + tlane + (uint32_t)cg * 8;
       umma::tmem_st8(dst, hh);
@@ -252,7 +252,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
         const uint32_t n = 2u * (uint32_t)it + (uint32_t)(q >> 1);
-        umma::mbar_wait(&l1_done[q & 1], n & 1u);
+        umma::mbar_wait_relaxed(&l1_done[q & 1], n & 1u);
         umma::tc_fence_after();
         if (t == 0) PP_TR(32 + 2 * q);
         float v[16];
@@ -278,7 +278,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(&tab_free[tb]);   // score tables of this tile are dead
       // ---- layer-2 accumulator quarters -> H --------------------------------------------
-      umma::mbar_wait(acc2_done, (uint32_t)it & 1u);
+      umma::mbar_wait_relaxed(acc2_done, (uint32_t)it & 1u);
       umma::tc_fence_after();
       if (t == 0) PP_TR(40);
 #pragma unroll 1
@@ -291,7 +291,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         if (t == 0) PP_TR(41 + q);
       }
       // ---- output: relu(acc3 + b3) -> pw_out[p, 32]; this warp owns 8 columns -------------
-      umma::mbar_wait(acc3_done, (uint32_t)it & 1u);
+      umma::mbar_wait_relaxed(acc3_done, (uint32_t)it & 1u);
       umma::tc_fence_after();
       if (t == 0) PP_TR(45);
       {
@@ -426,7 +426,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
 #endif
       for (uint32_t i = 0; i < total; ++i) {
         const uint32_t s = i % PP_RING;
-        if (i >= PP_RING) umma::mbar_wait(&empty[s], ((i / PP_RING) - 1) & 1u);
+        if (i >= PP_RING) umma::mbar_wait_relaxed(&empty[s], ((i / PP_RING) - 1) & 1u);
         bulk_g2s(s_ring + s * PT_STAGE, img + PT_IMG_W2 + (size_t)((blockIdx.x % PT_W2_COPIES) * 16 + (i & 15u)) * PT_STAGE, PT_STAGE, &full[s]);
       }
     }
@@ -475,8 +475,8 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         umma::split_bf16x2(g[6], 0.f, h1.x, l1.x);
       }
       if (u >= 1) {
-        umma::mbar_wait(&a1_empty[ab], (u - 1) & 1u);
-        umma::mbar_wait(&tab_free[ab], (u - 1) & 1u);
+        umma::mbar_wait_relaxed(&a1_empty[ab], (u - 1) & 1u);
+        umma::mbar_wait_relaxed(&tab_free[ab], (u - 1) & 1u);
       }
       unsigned char* a_hi = smem + PQ_A1 + ab * (4 * PT_LBO_A);
       unsigned char* a_lo = a_hi + 2 * PT_LBO_A;

@@ -20,6 +20,10 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#ifndef GN_MBAR_SLEEP_NS
+#define GN_MBAR_SLEEP_NS 40
+#endif
+
 namespace gn {
 namespace umma {
 
@@ -50,6 +54,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spin > (1u << 26)) __trap();
 }
 
+// The same wait for warps that are NOT on the tensor-core issue path: back off between
+// polls, so that 20-odd waiting warps do not take the issue slots the single UMMA-issuing
+// thread of a warp-specialised kernel needs (measured: 75-100 cycles per tcgen05.mma issue
+// with hot spin loops around it, profiles/r1_tc_kernels.md).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t spin = 0;; ++spin) {
+    __nanosleep(GN_MBAR_SLEEP_NS);
+    if (mbar_try_wait(bar, parity)) return;
+    if (spin > (1u << 24)) __trap();
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -81,7 +81,12 @@ class GnetEngine(object):
         # the pair kernel (+14 us in the det kernel): 'ab' halves the shared-memory
         # traffic but doubles the random L2 gather bytes per pair (2 x 256 B fp32 rows
         # instead of 2 x 128 B), whose latency lands in the epilogue.  Kept selectable.
-        self.pair_mode = 'hl'
+        # 'pipe': the 'hl' arithmetic as a warp-specialised pipeline (gn_block_pipe.cu), the
+        # shipped variant.
+        self.pair_mode = 'pipe'
+        # the predict head's hidden layers are linear (network.py:263): apply it as one folded
+        # affine map instead of three FC launches (False: the staged FCs)
+        self.collapse_predict = True
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name, shape, dtype=torch.float32):
@@ -201,7 +206,7 @@ class GnetEngine(object):
         block b, reduce_dim and (pw_fc1[32:64] | pw_fc1[64:96])^T of block b+1].
         pair_mode 'hl': pair image = [pw_fc1^T (K = 96), pw_fc2^T]; det image without the
         last part."""
-        key = 'wimg_' + self.pair_mode
+        key = 'wimg_' + ('ab' if self.pair_mode == 'ab' else 'hl')
         if key in self._ws:
             return self._ws[key]
         lib = ops._lib.load()
@@ -287,6 +292,9 @@ class GnetEngine(object):
             if ab_mode:
                 ops.block_pair_fwd_ab(pw, inter, pair_c, pair_n, num_pairs, cap,
                                       p[s + 'pw_fc2/biases'], wimg, pooled)
+            elif self.pair_mode == 'pipe':
+                ops.block_pair_fwd_pipe(pw, inter, pair_c, pair_n, num_pairs, cap,
+                                        p[s + 'pw_fc1/biases'], p[s + 'pw_fc2/biases'], wimg, pooled)
             else:
                 ops.block_pair_fwd(pw, inter, inter, pair_c, pair_n, num_pairs, cap,
                                    None, p[s + 'pw_fc1/biases'], None, p[s + 'pw_fc2/biases'],
@@ -302,6 +310,8 @@ class GnetEngine(object):
         """A8: two LINEAR layers then the logit (network.py:257-273)."""
         g = self.g
         T = feats.shape[0]
+        if self.use_fused and self.collapse_predict:
+            return self._predict_collapsed(feats)
         x = feats
         for i in range(1, g['num_predict_fc']):
             x = self._fc(x, 'gnet/predict/fc%d/fully_connected' % i, False,
@@ -309,6 +319,26 @@ class GnetEngine(object):
         out = self._fc(x, 'gnet/predict/logits/fully_connected', False,
                        out=self._buf('logits', (T, 1)))
         return out.view(-1)
+
+    def _predict_collapsed(self, feats):
+        """The head's hidden layers are linear, so it is ONE affine map: fold the chain
+        (every forward: parameters move during training), then one dot product per row."""
+        g = self.g
+        if 'pred_table' not in self._ws:
+            names = ['gnet/predict/fc%d/fully_connected' % i for i in range(1, g['num_predict_fc'])]
+            names.append('gnet/predict/logits/fully_connected')
+            rows = []
+            for nm in names:
+                w, b = self.layout[nm + '/weights'], self.layout[nm + '/biases']
+                rows.append([w.offset, b.offset, w.shape[0], w.shape[1]])
+            self._ws['pred_table'] = torch.tensor(rows, dtype=torch.int32, device=self.device)
+            self._ws['pred_maxdim'] = max(max(r[2], r[3]) for r in rows)
+        table, md = self._ws['pred_table'], self._ws['pred_maxdim']
+        d = feats.shape[1]
+        w_eff = self._buf('pred_weff', (d,))
+        b_eff = self._buf('pred_beff', (1,))
+        ops.predict_collapse(self.flat, table, md, self._buf('pred_scratch', (2 * md,)), w_eff, b_eff)
+        return ops.rowdot_fwd(feats, w_eff, b_eff, self._buf('logits', (feats.shape[0],)))
 
     def forward(self, dets, scores, classes, img_off):
         """dets[T,4] f32, scores[T] f32, classes[T] i32, img_off[B+1] i32 (all

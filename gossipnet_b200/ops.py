@@ -242,6 +242,35 @@ def block_det_fwd_img(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out=None
               T, d, 64, 32, _stream())
 
 
+def predict_collapse(flat, table, max_dim, scratch, w_eff, b_eff):
+    """Fold the linear predict head into (w_eff, b_eff) (see gn_predict_collapse)."""
+    f32 = torch.float32
+    _lib.call('gn_predict_collapse', _chk(flat, f32, 'flat'), _chk(table, torch.int32, 'table'),
+              table.shape[0], int(max_dim), _chk(scratch, f32, 'scratch'), _chk(w_eff, f32, 'w_eff'),
+              _chk(b_eff, f32, 'b_eff'), _stream())
+
+
+def rowdot_fwd(x, w, b, out):
+    """out[r] = x[r] . w + b[0]."""
+    f32 = torch.float32
+    _lib.call('gn_rowdot_fwd', _chk(x, f32, 'x'), x.stride(0), _chk(w, f32, 'w'), _chk(b, f32, 'b'),
+              _chk(out, f32, 'out'), x.shape[0], x.shape[1], _stream())
+    return out
+
+
+def block_pair_fwd_pipe(pw, feats_hl, pair_c, pair_n, num_pairs, capacity, b1, b2, wimg, pooled):
+    """Pipelined pair stage (see gn_block_pair_fwd_pipe): bf16 (hi | lo) reduced-feature
+    rows [num_dets, 2r], prepared weight image; pooled must be zero-filled."""
+    f32 = torch.float32
+    _lib.call('gn_block_pair_fwd_pipe', _chk(pw, f32, 'pw'), pw.shape[1],
+              _chk(feats_hl, torch.bfloat16, 'feats_hl'), _chk(feats_hl, torch.bfloat16, 'nfeats_hl'),
+              feats_hl.shape[1] // 2, _chk(pair_c, torch.int32, 'pair_c'),
+              _chk(pair_n, torch.int32, 'pair_n'), _chk(num_pairs, torch.int32, 'num_pairs'),
+              int(capacity), _chk(b1, f32, 'b1'), _chk(b2, f32, 'b2'),
+              _chk(wimg, torch.uint8, 'wimg'), b2.numel(), _chk(pooled, f32, 'pooled'), _stream())
+    return pooled
+
+
 def block_pair_fwd_ab(pw, ab, pair_c, pair_n, num_pairs, capacity, b2, wimg, pooled):
     """Pair stage on per-detection halves AB[T, 2f] (see gn_block_pair_fwd_ab)."""
     f32 = torch.float32

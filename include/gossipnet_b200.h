@@ -167,6 +167,25 @@ int gn_block_pair_fwd_hl(const float* pw, int w, const void* feats_hl,
                          const float* w1, const float* b1, const float* w2,
                          const float* b2, const void* wimg, int f, float* pooled,
                          gn_stream_t stream);
+/* Predict head (A8, network.py:257-273): its hidden layers have activation_fn=None, so the
+ * chain collapses to one affine map.  gn_predict_collapse folds the n_layers FCs described by
+ * table (n_layers x 4 int32: weight offset, bias offset, in, out into flat_params; last out
+ * must be 1) into w_eff[in_0] and b_eff[1] (scratch: 2 * max_dim floats); gn_rowdot_fwd
+ * computes y[r] = x[r, :k] . w + b[0], one warp per row. */
+int gn_predict_collapse(const float* flat_params, const int32_t* table, int n_layers,
+                        int max_dim, float* scratch, float* w_eff, float* b_eff,
+                        gn_stream_t stream);
+int gn_rowdot_fwd(const float* x, int ldx, const float* w, const float* b, float* y, int rows,
+                  int k, gn_stream_t stream);
+/* gn_block_pair_fwd_pipe: the same pair stage (same operands as gn_block_pair_fwd_hl with
+ * a prepared weight image, same results bit for bit) as a warp-specialised pipeline: one
+ * persistent CTA per SM with fill / MMA / two epilogue warp groups and three tiles in
+ * flight (csrc/gn_block_pipe.cu).  This is the variant the engine ships. */
+int gn_block_pair_fwd_pipe(const float* pw, int w, const void* feats_hl,
+                           const void* nfeats_hl, int r, const int32_t* pair_c,
+                           const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                           const float* b1, const float* b2, const void* wimg, int f,
+                           float* pooled, gn_stream_t stream);
 /* Prepared operand images.  Splitting / transposing the fp32 weights into the bf16
  * hi / lo K-major tiles inside every CTA of every launch is redundant work; with
  *   gn_prepare_operands(flat_params, table, entries, image)

@@ -38,7 +38,7 @@ def check_against(net, ref, with_loss=True):
 
 
 @pytest.mark.parametrize('name', CASES)
-@pytest.mark.parametrize('fused', ['ab', 'hl', False])
+@pytest.mark.parametrize('fused', ['pipe', 'ab', 'hl', False])
 def test_forward_matches_reference_golden(name, fused):
     g, num_classes, layout, flat, img = setup_case(name)
     net = Gnet(num_classes, class_weights=g['class_weights'], params=flat)
@@ -129,3 +129,16 @@ def test_imfeats_is_rejected_loudly():
     cfg.gnet.imfeats = True
     with pytest.raises(NotImplementedError):
         Gnet(1)
+
+
+def test_collapsed_predict_head_matches_staged_layers():
+    """The linear predict head folded into one affine map (gn_predict_collapse +
+    gn_rowdot_fwd) against the three staged FC launches (network.py:257-273)."""
+    load_experiment('coco_person', num_blocks=3)
+    net = Gnet(1)
+    img = synthetic.make_image(500, 1, image_index=2)
+    net.engine.collapse_predict = True
+    folded = net(img).cpu().numpy().copy()
+    net.engine.collapse_predict = False
+    staged = net(img).cpu().numpy()
+    assert rel_err(folded, staged) < 5e-6
