@@ -254,3 +254,40 @@ extern "C" int gn_roi_pool_bwd(int batch, int height, int width, int channels,
   GN_CHECK_LAUNCH("gn_roi_pool_bwd");
   return GN_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// Detection boxes -> Fast R-CNN rois for the image-feature head (network.py:78-100,
+// enlarge_windows + to_frcn_coords): every box grows by `padding` times its size on each
+// side around its centre, batch index 0:
+//   cx = (x1 + x2) / 2, nw2 = (x2 - x1) * (0.5 + padding)  ->  (0, cx - nw2, cy - nh2, cx + nw2, cy + nh2)
+// float32 ops in the reference's order.
+// ---------------------------------------------------------------------------------
+namespace gn {
+__global__ void frcn_boxes_kernel(const float* __restrict__ dets, int n, float half_plus_pad,
+                                  float batch_index, float* __restrict__ rois) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 d = ldg4(dets + (size_t)i * 4);
+  const float w = __fsub_rn(d.z, d.x), h = __fsub_rn(d.w, d.y);
+  const float cx = __fdiv_rn(__fadd_rn(d.x, d.z), 2.0f), cy = __fdiv_rn(__fadd_rn(d.y, d.w), 2.0f);
+  const float nw2 = __fmul_rn(w, half_plus_pad), nh2 = __fmul_rn(h, half_plus_pad);
+  float* r = rois + (size_t)i * 5;
+  r[0] = batch_index;
+  r[1] = __fsub_rn(cx, nw2);
+  r[2] = __fsub_rn(cy, nh2);
+  r[3] = __fadd_rn(cx, nw2);
+  r[4] = __fadd_rn(cy, nh2);
+}
+}  // namespace gn
+
+extern "C" int gn_frcn_boxes(const float* dets, int num_dets, float padding, int batch_index,
+                             float* rois, gn_stream_t stream) {
+  GN_REQUIRE(num_dets >= 0, "gn_frcn_boxes: negative size");
+  if (num_dets == 0) return GN_OK;
+  GN_REQUIRE(dets && rois, "gn_frcn_boxes: null pointer");
+  GN_REQUIRE(((uintptr_t)dets & 15) == 0, "gn_frcn_boxes: dets must be 16-byte aligned");
+  gn::frcn_boxes_kernel<<<gn::ceil_div(num_dets, 256), 256, 0, (cudaStream_t)stream>>>(
+      dets, num_dets, (float)(0.5 + (double)padding), (float)batch_index, rois);
+  GN_CHECK_LAUNCH("gn_frcn_boxes");
+  return GN_OK;
+}

@@ -84,6 +84,22 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src
       ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// shared -> global bulk copy (bulk async-group completion): issue, commit, then wait until
+// the source shared memory has been read (…_read) or the copies are complete.
+__device__ __forceinline__ void bulk_copy_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_group_read0() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_group0() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ---- TMEM ---------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address
 // is written to *dst_smem.

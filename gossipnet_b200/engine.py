@@ -46,6 +46,11 @@ class GnetEngine(object):
             'num_block_pw_fc', 'num_block_fc', 'num_predict_fc', 'predict_fc_dim',
             'neighbor_feats', 'num_pwfeat_fc', 'pwfeat_dim', 'pwfeat_narrow_dim',
             'pw_feat_multiplyer'))
+        # image-feature head (network.py:223-240): ROI-pooled crops of a feature map
+        self.imfeats = bool(g.imfeats)
+        self.imfeat_dim = int(g.imfeat_dim)
+        self.crop = (int(cfg.imfeat_crop_height), int(cfg.imfeat_crop_width))
+        self.imfeat_stride = 16          # get_resnet: output_stride=16 (network.py:57,63)
         self.normalize_loss = bool(cfg.train.normalize_loss)
         self.loss_multiplyer = float(cfg.train.loss_multiplyer)
         self.layout, self.total = P.param_layout(num_classes, cfg)
@@ -340,18 +345,51 @@ class GnetEngine(object):
         ops.predict_collapse(self.flat, table, md, self._buf('pred_scratch', (2 * md,)), w_eff, b_eff)
         return ops.rowdot_fwd(feats, w_eff, b_eff, self._buf('logits', (feats.shape[0],)))
 
-    def forward(self, dets, scores, classes, img_off):
+    def image_features(self, dets, img_off_host, imfeats, out):
+        """Start features from the image (network.py:103-119, 223-240): boxes enlarged by
+        half their size -> ROI max pooling of each image's feature map [1,H,W,C] (stride 16)
+        -> flatten -> [FC imfeat_dim, relu ->] FC shortcut_dim, relu.  Returns
+        (start_feat, roifeats[T,ph,pw,C], det_imfeats, frcn_boxes[T,5])."""
+        T = dets.shape[0]
+        if len(imfeats) != len(img_off_host) - 1:
+            raise ValueError('one feature map per image expected (%d maps, %d images)'
+                             % (len(imfeats), len(img_off_host) - 1))
+        rois = ops.frcn_boxes(dets, 0.5, 0, out=self._buf('frcn_rois', (T, 5)))
+        ph, pw_ = self.crop
+        tops = []
+        for i, fm in enumerate(imfeats):
+            d0, d1 = int(img_off_host[i]), int(img_off_host[i + 1])
+            top, _ = ops.roi_pool_fwd(fm, rois[d0:d1], ph, pw_, 1.0 / self.imfeat_stride)
+            tops.append(top)
+        roifeats = tops[0] if len(tops) == 1 else torch.cat(tops)
+        x = roifeats.reshape(T, -1)
+        scope = 'gnet/reduce_imfeats/fully_connected'
+        if self.imfeat_dim > 0:
+            x = self._fc(x, scope, True, out=self._buf('det_imfeats', (T, self.imfeat_dim)))
+            scope += '_1'
+        return self._fc(x, scope, True, out=out), roifeats, x, rois
+
+    def forward(self, dets, scores, classes, img_off, imfeats=None, img_off_host=None):
         """dets[T,4] f32, scores[T] f32, classes[T] i32, img_off[B+1] i32 (all
         CUDA) -> dict(prediction[T], row_ptr, num_pairs, pair_c, pair_n,
         pair_iou, pw_feats, feats, [block_feats]).  Returned tensors are views
-        of the engine's workspace: valid until the next forward."""
+        of the engine's workspace: valid until the next forward.  With
+        cfg.gnet.imfeats, `imfeats` is the list of per-image feature maps."""
         T = dets.shape[0]
         g = self.g
         row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = self.neighbors(dets, img_off)
         pw = self.pair_features(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, cap)
         d = g['shortcut_dim']
         feats = self._buf('feats0', (T, d))
-        feats.zero_()  # network.py:241-246
+        im = None
+        if self.imfeats:
+            if imfeats is None:
+                raise ValueError('cfg.gnet.imfeats is set: forward() needs the feature maps')
+            if img_off_host is None:
+                img_off_host = img_off.cpu().numpy()
+            feats, *im = self.image_features(dets, img_off_host, imfeats, feats)
+        else:
+            feats.zero_()  # network.py:241-246
         block_feats = [feats.clone()] if self.keep_block_feats else None
         if self.fused_det and self.use_fused and self.use_tensor_cores and g['num_blocks'] > 0:
             feats = self._blocks_fused(feats, pair_c, pair_n, num_pairs, cap, pw, block_feats)
@@ -366,6 +404,8 @@ class GnetEngine(object):
                    pair_n=pair_n, pair_iou=pair_iou, pw_feats=pw, feats=feats, capacity=cap)
         if self.keep_block_feats:
             res['block_feats'] = block_feats
+        if im is not None:
+            res['roifeats'], res['det_imfeats'], res['frcn_boxes'] = im
         return res
 
     # -------------------------------------------------------------- matching, loss

@@ -103,6 +103,9 @@ _DEFAULTS = {
         'imfeats': False,
         'load_imfeats': False,
         'imfeat_dim': -1,
+        # channels of the feature map fed as `imfeats` (ResNet-101 block3/unit_22 = 1024);
+        # not a reference key: there the width comes from the ResNet graph itself
+        'imfeat_channels': 1024,
         'neighbor_feats': False,
         'num_pwfeat_fc': 0,
         'pwfeat_dim': 256,

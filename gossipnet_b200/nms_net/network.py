@@ -16,8 +16,11 @@ Differences that are deliberate:
   * `det_det_iou` (dense N x N) and `neighbor_pair_idxs` ([P,2] int64) are
     materialised only when read: the hot path keeps the neighbor graph as a
     CSR + int32 pair list and never writes the dense matrix;
-  * image features (`cfg.gnet.imfeats`, ResNet-101) are out of scope
-    (SURVEY.md §2 row 4): constructing such a Gnet raises.
+  * image features (`cfg.gnet.imfeats`): the head of network.py:223-240 (enlarged
+    boxes -> roi_pool -> flatten -> FC -> FC as block-0 features) is here; the
+    ResNet-101 that produces the feature map is not, so the
+    batch carries the stride-16 feature map itself as `imfeats` [1,H,W,C] where
+    the reference's carries the `image`.
 """
 import numpy as np
 import torch
@@ -78,7 +81,11 @@ class Gnet(object):
                 'gt_crowd': (bool_, [None]),
                 'gt_classes': (int32, [None]),
             })
-        if cfg.gnet.imfeats or cfg.gnet.load_imfeats:
+        if cfg.gnet.imfeats:
+            # the reference feeds `image` through ResNet-101 (network.py:52-75); here the
+            # batch carries that network's stride-16 output map
+            batch_spec['imfeats'] = (float32, [1, None, None, cfg.gnet.imfeat_channels])
+        elif cfg.gnet.load_imfeats:
             batch_spec['image'] = (float32, [None, None, None, 3])
         return batch_spec
 
@@ -87,10 +94,6 @@ class Gnet(object):
         self.num_classes = num_classes
         self.multiclass = num_classes > 1
         self.weight_reg = weight_reg
-        if cfg.gnet.imfeats:
-            raise NotImplementedError(
-                'cfg.gnet.imfeats (ResNet-101 image features) is outside the B200 hot path; '
-                'roi_pool itself is available in nms_net.roi_pooling_layer')
         if reuse:
             if self.name not in _SCOPES:
                 raise ValueError('Gnet(reuse=True) before any Gnet was built '
@@ -118,7 +121,8 @@ class Gnet(object):
     def _clear(self):
         for k in ('prediction', 'labels', 'weights', 'det_gt_matching', 'loss', 'loss_normed',
                   'loss_unnormed', 'det_anno_iou', 'pw_feats', 'block_feats', 'num_dets',
-                  'dets_boxdata', 'gt_boxdata'):
+                  'dets_boxdata', 'gt_boxdata', 'imfeats', 'roifeats', 'det_imfeats',
+                  'frcn_boxes'):
             setattr(self, k, None)
         self._lazy = {}
 
@@ -163,8 +167,18 @@ class Gnet(object):
         with_gt = all(b.get('gt_boxes') is not None for b in batches)
         io = self._pack(batches, self.device, with_gt)
         eng = self.engine
+        imfeats = None
+        if eng.imfeats:
+            if any(b.get('imfeats') is None for b in batches):
+                raise NotImplementedError(
+                    'cfg.gnet.imfeats: every image needs its stride-16 feature map as '
+                    '`imfeats` [1,H,W,C]; computing it from `image` (ResNet-101) is not part '
+                    'of this package')
+            imfeats = [_as_dev(b['imfeats'], float32, self.device) for b in batches]
+            io['imfeats'] = imfeats
         while True:
-            res = eng.forward(io['dets'], io['det_scores'], io['det_classes'], io['img_off'])
+            res = eng.forward(io['dets'], io['det_scores'], io['det_classes'], io['img_off'],
+                              imfeats=imfeats, img_off_host=io['img_off_host'])
             if with_gt:
                 res.update(eng.matching_and_loss(
                     res['prediction'], io['dets'], io['det_classes'], io['img_off'],
@@ -198,6 +212,10 @@ class Gnet(object):
         self.block_feats = res['block_feats']
         self._pairs = (res['pair_c'][:P].clone(), res['pair_n'][:P].clone())
         self.dets_boxdata = self._xyxy_to_boxdata(self.dets)
+        if 'roifeats' in res:
+            self.imfeats = res['imfeats'][0]
+            self.roifeats, self.frcn_boxes = res['roifeats'], res['frcn_boxes'].clone()
+            self.det_imfeats = res['det_imfeats'].clone()
         if 'labels' in res:
             for k in ('gt_boxes', 'gt_crowd', 'gt_classes'):
                 setattr(self, k, res[k])

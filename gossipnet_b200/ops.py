@@ -399,6 +399,16 @@ def _roi_args(bottom_data, bottom_rois):
         raise ValueError('rois must be [num_rois, 5] (batch_idx, x1, y1, x2, y2)')
 
 
+def frcn_boxes(dets, padding=0.5, batch_index=0, out=None):
+    """dets[N,4] -> rois[N,5] = (batch_index, enlarged box) (network.py:78-100)."""
+    n = dets.shape[0]
+    if out is None:
+        out = torch.empty((n, 5), dtype=torch.float32, device=dets.device)
+    _lib.call('gn_frcn_boxes', _chk(dets, torch.float32, 'dets'), n, float(padding), int(batch_index),
+              _chk(out, torch.float32, 'rois'), _stream())
+    return out
+
+
 def roi_pool_fwd(bottom_data, bottom_rois, pooled_height, pooled_width, spatial_scale):
     _roi_args(bottom_data, bottom_rois)
     if pooled_height < 0:      # roi_pooling_op.cc:64-73

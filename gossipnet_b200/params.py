@@ -32,12 +32,11 @@ def raw_pairfeat_width(num_classes):
 
 
 def param_layout(num_classes, cfg):
-    """Ordered name -> ParamEntry for the no-imfeats Gnet."""
+    """Ordered name -> ParamEntry.  With cfg.gnet.imfeats the image-feature head
+    (`network.py:223-240`, scope gnet/reduce_imfeats: flattened ROI features ->
+    [imfeat_dim ->] shortcut_dim) is included; the ResNet that produces the
+    feature map is not part of this package."""
     g = cfg.gnet
-    if g.imfeats:
-        raise NotImplementedError(
-            'cfg.gnet.imfeats needs ResNet-101 image features, which are out '
-            'of scope (SURVEY.md §2 row 4)')
     entries = OrderedDict()
     off = [0]
 
@@ -58,6 +57,13 @@ def param_layout(num_classes, cfg):
         add_fc('gnet/pw_feats/fc%d' % g.num_pwfeat_fc, width,
                g.pwfeat_narrow_dim, True)
         width = g.pwfeat_narrow_dim
+    if g.imfeats:
+        n_in = cfg.imfeat_crop_height * cfg.imfeat_crop_width * g.imfeat_channels
+        scope = 'gnet/reduce_imfeats/fully_connected'
+        if g.imfeat_dim > 0:
+            add_fc(scope, n_in, g.imfeat_dim, True)
+            n_in, scope = g.imfeat_dim, scope + '_1'      # TF's second default scope name
+        add_fc(scope, n_in, g.shortcut_dim, True)
     for b in range(1, g.num_blocks + 1):
         s = 'gnet/block%d/' % b
         add_fc(s + 'reduce_dim', g.shortcut_dim, g.reduced_dim, True)

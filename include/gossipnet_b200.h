@@ -314,6 +314,12 @@ int gn_adam_step(float* params, const float* grads, float* m, float* v, const fl
 int gn_momentum_step(float* params, const float* grads, float* accum, const float* decay,
                      int64_t n, float lr, float momentum, float grad_scale, gn_stream_t stream);
 
+/* gn_frcn_boxes: detection boxes -> rois of the image-feature head (network.py:78-100,
+ * enlarge_windows + to_frcn_coords): rois[i] = (batch_index, cx - w (0.5 + padding),
+ * cy - h (0.5 + padding), cx + w (0.5 + padding), cy + h (0.5 + padding)), float32 ops in the
+ * reference's order (bit-exact). */
+int gn_frcn_boxes(const float* dets, int num_dets, float padding, int batch_index, float* rois,
+                  gn_stream_t stream);
 /* ---- RoiPool / RoiPoolGrad ----------------------------------
  * Replace the RoiPool / RoiPoolGrad ops (nms_net/roi_pooling_layer/roi_pooling_op.cc:
  * 35-54 op definitions, :128-187 / :374-449 CPU semantics; python names

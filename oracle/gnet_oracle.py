@@ -207,6 +207,37 @@ def loss(prediction, labels, weights, assignment, gt_crowd, gt_classes,
 
 
 # --------------------------------------------------------------------------
+# image-feature head
+# --------------------------------------------------------------------------
+
+def enlarge_windows(boxdata, padding=0.5):
+    """network.py:78-87: each box grown by `padding` of its size on every side."""
+    x1, y1, w, h, x2, y2, _ = boxdata
+    cx = (x1 + x2) / F32(2.0)
+    cy = (y1 + y2) / F32(2.0)
+    nw2 = w * F32(0.5 + padding)
+    nh2 = h * F32(0.5 + padding)
+    return np.concatenate([cx - nw2, cy - nh2, cx + nw2, cy + nh2], axis=1).astype(F32)
+
+
+def image_features(dets_boxdata, imfeats, params, cfg, stride=16):
+    """network.py:103-119 (crop_windows: enlarged boxes, batch index 0, roi_pool at
+    1/stride) and :223-240 (flatten -> [FC imfeat_dim relu ->] FC shortcut_dim relu).
+    `imfeats` is the [1,H,W,C] map the reference gets from ResNet-101."""
+    from oracle import roi_pool_oracle
+    boxes = enlarge_windows(dets_boxdata)
+    frcn = np.concatenate([np.zeros((boxes.shape[0], 1), dtype=F32), boxes], axis=1)
+    roifeats, _ = roi_pool_oracle.roi_pool(imfeats, frcn, cfg.imfeat_crop_height,
+                                           cfg.imfeat_crop_width, 1.0 / stride)
+    x = roifeats.reshape(roifeats.shape[0], -1)
+    scope = 'gnet/reduce_imfeats/fully_connected'
+    if cfg.gnet.imfeat_dim > 0:
+        x = fc(x, params, scope, relu=True)
+        scope += '_1'
+    return fc(x, params, scope, relu=True), roifeats, x, frcn
+
+
+# --------------------------------------------------------------------------
 # whole forward
 # --------------------------------------------------------------------------
 
@@ -231,7 +262,12 @@ def gnet_forward(image, params, cfg, num_classes, matching_fn=None,
                             pairs, num_classes, g.pw_feat_multiplyer)
     pw = pw_feats_fc(pw_raw, params, cfg) if g.num_pwfeat_fc > 0 else pw_raw
 
-    feats = np.zeros((n, g.shortcut_dim), dtype=F32)
+    if g.imfeats:
+        feats, roifeats, det_imfeats, frcn_boxes = image_features(
+            dets_boxdata, np.asarray(image['imfeats'], dtype=F32), params, cfg)
+        out.update(roifeats=roifeats, det_imfeats=det_imfeats, frcn_boxes=frcn_boxes)
+    else:
+        feats = np.zeros((n, g.shortcut_dim), dtype=F32)
     block_feats = [feats]
     for b in range(1, g.num_blocks + 1):
         feats = block(b, feats, pair_c, pair_n, pw, params, cfg)

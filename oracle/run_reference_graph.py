@@ -34,7 +34,17 @@ CASES = [
     ('person_n120_b16', 'coco_person', 1, 120, 16, 3),
     ('multiclass_n150_b3', 'coco_multiclass', 80, 150, 3, 1),
     ('default_rawpw_n60_b2', None, 1, 60, 2, 5),           # num_pwfeat_fc = 0 (reference default)
+    # image-feature head (network.py:223-240): cfg.gnet.imfeats with a synthetic stride-16
+    # feature map standing in for ResNet-101's block3/unit_22 output (C = 24 channels)
+    ('imfeats_n50_b2', 'coco_person', 1, 50, 2, 7),
 ]
+IMFEAT_CHANNELS, IMFEAT_DIM = 24, 40
+
+
+def synthetic_feature_map(channels, image_index):
+    """[1, 38, 63, C] float32: the stride-16 map of the 600 x 1000 synthetic canvas."""
+    rs = np.random.RandomState(9000 + image_index)
+    return rs.normal(0.0, 1.0, (1, 38, 63, channels)).astype(np.float32)
 
 
 def _load_by_path(name, path):
@@ -71,8 +81,20 @@ def main(out_dir):
             return tf.T(lab), tf.T(w), tf.T(asg)
 
     tf.OP_LIBRARIES['det_matching.so'] = _MatchingLib()
-    tf.OP_LIBRARIES['roi_pooling.so'] = type('RoiLib', (), {'roi_pool': None,
-                                                            'roi_pool_grad': None})()
+    from oracle import roi_pool_oracle
+
+    class _RoiLib(object):
+        """roi_pooling.so stand-in: the reference's own roi_pooling_op.cc (CPU kernel),
+        compiled unmodified into oracle/_ref."""
+        roi_pool_grad = None
+
+        @staticmethod
+        def roi_pool(data, rois, pooled_height, pooled_width, spatial_scale):
+            top, arg = roi_pool_oracle.ref_roi_pool(tf._v(data), tf._v(rois), pooled_height,
+                                                    pooled_width, spatial_scale)
+            return tf.T(top), tf.T(arg)
+
+    tf.OP_LIBRARIES['roi_pooling.so'] = _RoiLib()
     if not det_matching_oracle.have_reference_build():
         det_matching_oracle.build()
 
@@ -99,6 +121,12 @@ def main(out_dir):
             our_config.cfg_from_file(path)
         ref_cfg.gnet.num_blocks = num_blocks
         our_config.cfg.gnet.num_blocks = num_blocks
+        with_imfeats = name.startswith('imfeats')
+        if with_imfeats:
+            for c in (ref_cfg, our_config.cfg):
+                c.gnet.imfeats = True
+                c.gnet.imfeat_dim = IMFEAT_DIM
+            our_config.cfg.gnet.imfeat_channels = IMFEAT_CHANNELS
 
         layout, total = P.param_layout(num_classes, our_config.cfg)
         flat = P.init_flat(layout, total, our_config.cfg, seed=1000 + img_idx)
@@ -109,6 +137,11 @@ def main(out_dir):
         img = synthetic.make_image(n_dets, num_classes, seed=42, image_index=img_idx)
         cw = np.linspace(0.5, 1.5, num_classes + 1).astype(np.float32)
         batch = dict((k, tf.T(v)) for k, v in img.items())
+        if with_imfeats:
+            # ResNet-101 is not run: get_resnet hands back the synthetic map at stride 16
+            fmap = synthetic_feature_map(IMFEAT_CHANNELS, img_idx)
+            batch['image'] = tf.T(np.zeros((1, 600, 1000, 3), dtype=np.float32))
+            ref_network.get_resnet = lambda image, reuse: (tf.T(fmap), 16, [], {})
         net = ref_network.Gnet(num_classes, class_weights=cw, batch=batch)
 
         used = sorted(v.name[:-2] for v in net.trainable_variables)
@@ -130,6 +163,10 @@ def main(out_dir):
             det_gt_matching=tf._v(net.det_gt_matching),
             loss=tf._v(net.loss), loss_normed=tf._v(net.loss_normed),
             loss_unnormed=tf._v(net.loss_unnormed))
+        if with_imfeats:
+            out.update(imfeats=fmap, roifeats=tf._v(net.roifeats), frcn_boxes=tf._v(net.frcn_boxes),
+                       det_imfeats=tf._v(net.det_imfeats), block0_feats=tf._v(net.block_feats[0]),
+                       imfeat_dim=np.int32(IMFEAT_DIM), imfeat_channels=np.int32(IMFEAT_CHANNELS))
         if n_dets > 150:   # keep the fixtures small: drop the big dense tensors
             for k in ('det_det_iou', 'pw_feats', 'block1_feats', 'last_feats'):
                 out[k + '_sum'] = np.float64(np.sum(out[k], dtype=np.float64))

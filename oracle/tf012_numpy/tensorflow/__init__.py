@@ -35,6 +35,19 @@ def reset():
     del _scope[:]
     del _created[:]
     del _losses[:]
+    _default_names.clear()
+
+
+_default_names = {}     # (enclosing scope, default name) -> uses so far
+
+
+def unique_default_scope(default_name):
+    """tf.variable_scope(None, default_name=...): `fully_connected`, then
+    `fully_connected_1`, ... within one enclosing scope."""
+    key = (current_scope(), default_name)
+    n = _default_names.get(key, 0)
+    _default_names[key] = n + 1
+    return default_name if n == 0 else '%s_%d' % (default_name, n)
 
 
 class T(object):

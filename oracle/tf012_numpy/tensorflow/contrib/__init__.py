@@ -21,7 +21,7 @@ class _Layers(object):
         `<scope>/weights`, `<scope>/biases`, default scope `fully_connected`."""
         if activation_fn is None and 'activation_fn' not in kwargs:
             pass
-        with tf.variable_scope(scope or 'fully_connected'):
+        with tf.variable_scope(scope or tf.unique_default_scope('fully_connected')):
             prefix = tf.current_scope()
             w = tf.get_param(prefix + '/weights')
             b = tf.get_param(prefix + '/biases')

@@ -52,6 +52,11 @@ def test_forward_matches_reference_golden(name, fused):
         assert rel_err(net.block_feats[1].cpu().numpy(), g['block1_feats']) < 2e-5
         assert rel_err(net.block_feats[-1].cpu().numpy(), g['last_feats']) < LOGIT_TOL
         assert np.array_equal(net.det_det_iou.cpu().numpy(), g['det_det_iou'])
+    if 'imfeats' in g:      # image-feature head: boxes and ROI pooling bit-exact, FCs to tolerance
+        assert np.array_equal(net.frcn_boxes.cpu().numpy(), g['frcn_boxes'])
+        assert np.array_equal(net.roifeats.cpu().numpy(), g['roifeats'])
+        assert rel_err(net.det_imfeats.cpu().numpy(), g['det_imfeats']) < 2e-5
+        assert rel_err(net.block_feats[0].cpu().numpy(), g['block0_feats']) < 2e-5
 
 
 @pytest.mark.parametrize('n,blocks,exp,C', [(300, 2, 'coco_person', 1),       # BASELINE configs[0]
@@ -125,10 +130,29 @@ def test_static_block_matches_oracle():
     assert rel_err(out.cpu().numpy(), net.block_feats[2].cpu().numpy()) < 3e-5
 
 
-def test_imfeats_is_rejected_loudly():
+def test_imfeats_needs_the_feature_map():
+    """cfg.gnet.imfeats: the head runs on a feature map in the batch; an `image` alone
+    (ResNet-101 is not part of this package) is rejected loudly."""
+    load_experiment('coco_person', num_blocks=1)
     cfg.gnet.imfeats = True
+    cfg.gnet.imfeat_channels = 8
+    cfg.gnet.imfeat_dim = 16
+    net = Gnet(1)
+    assert 'gnet/reduce_imfeats/fully_connected_1/weights' in net.state_dict()
+    assert 'imfeats' in Gnet.get_batch_spec(1) and 'image' not in Gnet.get_batch_spec(1)
+    img = synthetic.make_image(30, 1)
     with pytest.raises(NotImplementedError):
-        Gnet(1)
+        net(dict(img, image=np.zeros((1, 600, 1000, 3), dtype=np.float32)))
+    fmap = np.random.RandomState(0).normal(size=(1, 38, 63, 8)).astype(np.float32)
+    pred = net(dict(img, imfeats=fmap))
+    assert pred.shape == (30,) and net.roifeats.shape == (30, 7, 7, 8)
+    assert net.det_imfeats.shape == (30, 16) and net.block_feats[0].shape == (30, 128)
+    # two images in one call == one at a time
+    img2 = synthetic.make_image(41, 1, image_index=3)
+    fmap2 = np.random.RandomState(1).normal(size=(1, 20, 30, 8)).astype(np.float32)
+    both = net.run_batch([dict(img, imfeats=fmap), dict(img2, imfeats=fmap2)])['prediction'].cpu().numpy().copy()
+    assert np.array_equal(both[:30], pred.cpu().numpy())
+    assert np.array_equal(both[30:], net(dict(img2, imfeats=fmap2)).cpu().numpy())
 
 
 def test_collapsed_predict_head_matches_staged_layers():

@@ -22,11 +22,17 @@ def setup_case(name):
     if exp:
         load_experiment(exp)
     cfg.gnet.num_blocks = int(g['num_blocks'])
+    if 'imfeats' in g:          # image-feature head: synthetic stride-16 map in the fixture
+        cfg.gnet.imfeats = True
+        cfg.gnet.imfeat_dim = int(g['imfeat_dim'])
+        cfg.gnet.imfeat_channels = int(g['imfeat_channels'])
     num_classes = int(g['num_classes'])
     layout, total = P.param_layout(num_classes, cfg)
     flat = P.init_flat(layout, total, cfg, seed=int(g['param_seed']))
     img = synthetic.make_image(int(g['n_dets']), num_classes, seed=42,
                                image_index=int(g['image_index']))
+    if 'imfeats' in g:
+        img['imfeats'] = g['imfeats']
     return g, num_classes, layout, flat, img
 
 
@@ -55,6 +61,11 @@ def test_oracle_matches_reference_execution(name, oracle_built):
         assert rel_err(out['block_feats'][-1], g['last_feats']) < 1e-6
     else:
         assert abs(np.sum(out['det_det_iou'], dtype=np.float64) - g['det_det_iou_sum']) < 1e-6
+    if 'imfeats' in g:
+        assert np.array_equal(out['frcn_boxes'], g['frcn_boxes'])
+        assert np.array_equal(out['roifeats'], g['roifeats'])       # C restatement == reference op
+        assert rel_err(out['det_imfeats'], g['det_imfeats']) < 1e-6
+        assert rel_err(out['block_feats'][0], g['block0_feats']) < 1e-6
     assert rel_err(out['prediction'], g['prediction']) < 1e-6
     for k in ('loss', 'loss_normed', 'loss_unnormed'):
         assert abs(float(out[k]) - float(g[k])) <= 1e-6 * max(1.0, abs(float(g[k]))), k
