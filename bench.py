@@ -195,6 +195,10 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at the
+        # VERSION debug level some launch environments set
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     cfg = setup_cfg(args.blocks)
     peaks = {}

@@ -159,6 +159,17 @@ class Gnet(object):
                        gt_classes=cat('gt_classes', int32), gt_off_host=gt_off_host)
         return out
 
+    def _pack_imfeats(self, batches):
+        """Per-image feature maps [1,H,W,C] on the device (None without cfg.gnet.imfeats)."""
+        if not self.engine.imfeats:
+            return None
+        if any(b.get('imfeats') is None for b in batches):
+            raise NotImplementedError(
+                'cfg.gnet.imfeats: every image needs its stride-16 feature map as '
+                '`imfeats` [1,H,W,C]; computing it from `image` (ResNet-101) is not part '
+                'of this package')
+        return [_as_dev(b['imfeats'], float32, self.device) for b in batches]
+
     # ----------------------------------------------------------------------- run
     def run_batch(self, batches, want_grad=False):
         """Forward (+ matching and loss when every image carries gt_*) for a list
@@ -167,15 +178,7 @@ class Gnet(object):
         with_gt = all(b.get('gt_boxes') is not None for b in batches)
         io = self._pack(batches, self.device, with_gt)
         eng = self.engine
-        imfeats = None
-        if eng.imfeats:
-            if any(b.get('imfeats') is None for b in batches):
-                raise NotImplementedError(
-                    'cfg.gnet.imfeats: every image needs its stride-16 feature map as '
-                    '`imfeats` [1,H,W,C]; computing it from `image` (ResNet-101) is not part '
-                    'of this package')
-            imfeats = [_as_dev(b['imfeats'], float32, self.device) for b in batches]
-            io['imfeats'] = imfeats
+        imfeats = io['imfeats'] = self._pack_imfeats(batches)
         while True:
             res = eng.forward(io['dets'], io['det_scores'], io['det_classes'], io['img_off'],
                               imfeats=imfeats, img_off_host=io['img_off_host'])

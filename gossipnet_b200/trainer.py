@@ -97,7 +97,26 @@ class Trainer(object):
         pw = pw_acts[-1]
         w, r, f = pw.shape[1], g['reduced_dim'], g['pairfeat_dim']
 
-        feats = torch.zeros((T, g['shortcut_dim']), dtype=torch.float32, device=eng.device)
+        im_acts, im_scopes = None, []
+        if eng.imfeats:
+            # image-feature head (network.py:223-240); the feature maps are inputs of the
+            # step (the ResNet that makes them is not part of this package), so the gradient
+            # stops at the ROI-pooled features
+            start, roifeats, _, _ = eng.image_features(
+                dets, io['img_off_host'], net._pack_imfeats(batches),
+                torch.empty((T, g['shortcut_dim']), dtype=torch.float32, device=eng.device))
+            x0 = roifeats.reshape(T, -1)
+            scope = 'gnet/reduce_imfeats/fully_connected'
+            im_acts = [x0]
+            if eng.imfeat_dim > 0:
+                im_acts.append(self._fc(x0, scope, True))
+                im_scopes.append(scope)
+                scope += '_1'
+            im_scopes.append(scope)
+            feats = self._fc(im_acts[-1], scope, True)
+            im_acts.append(feats)
+        else:
+            feats = torch.zeros((T, g['shortcut_dim']), dtype=torch.float32, device=eng.device)
         tape = []
         for b in range(1, g['num_blocks'] + 1):
             s = 'gnet/block%d/' % b
@@ -158,15 +177,23 @@ class Trainer(object):
             ops.gather_concat_bwd(dh, w, r, pair_c, pair_n, row_ptr, T, num_pairs, cap, dpw,
                                   dred, dnred)
             ops.relu_mask(dred, red)
-            dx = self._fc_bwd(feats_in, dred, s + 'reduce_dim', need_dx=b > 1)
+            first_needs_dx = b > 1 or im_acts is not None
+            dx = self._fc_bwd(feats_in, dred, s + 'reduce_dim', need_dx=first_needs_dx)
             if g['neighbor_feats']:
                 ops.relu_mask(dnred, nred)
-                dxn = self._fc_bwd(feats_in, dnred, s + 'reduce_dim_neighbor', need_dx=b > 1)
+                dxn = self._fc_bwd(feats_in, dnred, s + 'reduce_dim_neighbor',
+                                   need_dx=first_needs_dx)
                 if dxn is not None:
                     ops.add_inplace(dfeats, dxn)
-            # block 1's input is the constant zero start feature (network.py:241-246)
+            # without image features block 1's input is the constant zero start feature
+            # (network.py:241-246) and nothing flows further
             if dx is not None:
                 ops.add_inplace(dfeats, dx)
+        if im_acts is not None:       # dfeats = d loss / d start features
+            d = dfeats
+            for i in range(len(im_scopes), 0, -1):
+                ops.relu_mask(d, im_acts[i])
+                d = self._fc_bwd(im_acts[i - 1], d, im_scopes[i - 1], need_dx=i > 1)
         # pair-feature MLP: sum of the gradients of all blocks; raw features are constants
         d = dpw
         for i in range(g['num_pwfeat_fc'], 0, -1):

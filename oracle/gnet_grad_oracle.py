@@ -25,8 +25,11 @@ def _fc(x, p, scope, relu):
     return np.maximum(y, 0.0) if relu else y
 
 
-def forward(params, cfg, pairs, pw_raw, n_dets, keep=False):
-    """float64 forward from the (constant) raw pair features to the logits."""
+def forward(params, cfg, pairs, pw_raw, n_dets, keep=False, roi_x0=None):
+    """float64 forward from the (constant) raw pair features to the logits.
+    `roi_x0` [n_dets, ph*pw*C]: flattened ROI-pooled image features (constants of the
+    step) for cfg.gnet.imfeats - the start features are then their reduce_imfeats FCs
+    (network.py:223-240) instead of zeros."""
     g = cfg.gnet
     p = dict((k, np.asarray(v, dtype=F64)) for k, v in params.items())
     pc, pn = pairs[:, 0], pairs[:, 1]
@@ -35,6 +38,17 @@ def forward(params, cfg, pairs, pw_raw, n_dets, keep=False):
         acts['pw'].append(_fc(acts['pw'][-1], p, 'gnet/pw_feats/fc%d' % i, True))
     pw = acts['pw'][-1]
     feats = np.zeros((n_dets, g.shortcut_dim), dtype=F64)
+    acts['im'], acts['im_scopes'] = None, []
+    if roi_x0 is not None:
+        scope = 'gnet/reduce_imfeats/fully_connected'
+        acts['im'] = [np.asarray(roi_x0, dtype=F64)]
+        if g.imfeat_dim > 0:
+            acts['im'].append(_fc(acts['im'][-1], p, scope, True))
+            acts['im_scopes'].append(scope)
+            scope += '_1'
+        acts['im'].append(_fc(acts['im'][-1], p, scope, True))
+        acts['im_scopes'].append(scope)
+        feats = acts['im'][-1]
     starts = np.flatnonzero(np.diff(np.concatenate([[-1], pc])) != 0)
     blocks = []
     for b in range(1, g.num_blocks + 1):
@@ -75,10 +89,11 @@ def reg_loss(params, layout, weight_decay):
                for e in layout.values() if e.regularized)
 
 
-def gradients(params, cfg, pairs, pw_raw, n_dets, labels, weights):
+def gradients(params, cfg, pairs, pw_raw, n_dets, labels, weights, roi_x0=None):
     """d data_loss / d theta for every parameter (float64 dict), plus the logits."""
     g = cfg.gnet
-    pred, (p, acts, blocks, pa, starts) = forward(params, cfg, pairs, pw_raw, n_dets, keep=True)
+    pred, (p, acts, blocks, pa, starts) = forward(params, cfg, pairs, pw_raw, n_dets, keep=True,
+                                                  roi_x0=roi_x0)
     pc, pn = pairs[:, 0], pairs[:, 1]
     grads = dict((k, np.zeros_like(v)) for k, v in p.items())
 
@@ -124,6 +139,11 @@ def gradients(params, cfg, pairs, pw_raw, n_dets, labels, weights):
         dfeats = dpre + fc_bwd(feats_in, dred * (red > 0), s + 'reduce_dim')
         if g.neighbor_feats:
             dfeats = dfeats + fc_bwd(feats_in, dnred * (nred > 0), s + 'reduce_dim_neighbor')
+    if acts['im'] is not None:      # dfeats = d loss / d start features
+        d = dfeats
+        for i in range(len(acts['im_scopes']), 0, -1):
+            d = d * (acts['im'][i] > 0)
+            d = fc_bwd(acts['im'][i - 1], d, acts['im_scopes'][i - 1])
     d = dpw
     for i in range(g.num_pwfeat_fc, 0, -1):
         d = d * (acts['pw'][i] > 0)

@@ -19,12 +19,16 @@ pytestmark = pytest.mark.gpu
 
 def oracle_grad_for(img, flat, layout, num_classes, labels, weights):
     bd = go.xyxy_to_boxdata(img['dets'])
+    x0 = None
+    if cfg.gnet.imfeats:     # ROI-pooled crops are constants of the step
+        _, roifeats, _, _ = go.image_features(bd, img['imfeats'], P.views(layout, flat), cfg)
+        x0 = roifeats.reshape(roifeats.shape[0], -1)
     m = go.iou(bd, bd)
     pairs = go.neighbor_pairs(m, cfg.gnet.neighbor_thresh)
     raw = go.geometry_feats(bd, m, img['det_scores'], img['det_classes'], pairs, num_classes,
                             cfg.gnet.pw_feat_multiplyer)
     grads, _ = gg.gradients(P.views(layout, flat.astype(np.float64)), cfg, pairs, raw,
-                            img['dets'].shape[0], labels, weights)
+                            img['dets'].shape[0], labels, weights, roi_x0=x0)
     out = np.zeros(flat.shape[0])
     for e in layout.values():
         out[e.offset:e.offset + e.size] = grads[e.name].reshape(-1)
@@ -52,6 +56,18 @@ def grad_check(num_classes, imgs, tol=2e-3):
         scale = max(np.max(np.abs(b)), 1e-6)
         assert np.max(np.abs(a - b)) / scale < tol, (e.name, np.max(np.abs(a - b)) / scale)
     return tr, res
+
+
+def test_gradients_with_image_feature_head(oracle_built):
+    load_experiment('coco_person', num_blocks=2)
+    cfg.gnet.imfeats = True
+    cfg.gnet.imfeat_channels, cfg.gnet.imfeat_dim = 16, 48
+    imgs = []
+    for i, n in enumerate((120, 75)):
+        img = synthetic.make_image(n, 1, image_index=i)
+        img['imfeats'] = np.random.RandomState(40 + i).normal(size=(1, 38, 63, 16)).astype(np.float32)
+        imgs.append(img)
+    grad_check(1, imgs)
 
 
 def test_gradients_coco_person_two_blocks():

@@ -40,12 +40,20 @@ def setup(n=14, seed=3):
     return layout, flat, params, pairs, raw, labels, weights, n
 
 
-def check(neighbor_feats, normalize):
+def check(neighbor_feats, normalize, imfeats=False):
     tiny_cfg(neighbor_feats)
     cfg.train.normalize_loss = normalize
     cfg.train.loss_multiplyer = 1.7
+    x0 = None
+    if imfeats:      # image-feature head on 2x2x3 ROI crops, one hidden layer
+        cfg.gnet.imfeats = True
+        cfg.gnet.imfeat_channels, cfg.gnet.imfeat_dim = 3, 5
+        cfg.imfeat_crop_height = cfg.imfeat_crop_width = 2
     layout, flat, params, pairs, raw, labels, weights, n = setup()
-    grads, pred = gg.gradients(params, cfg, pairs, raw, n, labels, weights)
+    if imfeats:
+        x0 = np.random.RandomState(5).normal(0, 1, (n, 12))
+        assert 'gnet/reduce_imfeats/fully_connected_1/weights' in layout
+    grads, pred = gg.gradients(params, cfg, pairs, raw, n, labels, weights, roi_x0=x0)
     rs = np.random.RandomState(0)
     worst = 0.0
     for e in layout.values():
@@ -54,9 +62,9 @@ def check(neighbor_feats, normalize):
             h = 1e-6
             old = flat[i]
             flat[i] = old + h
-            lp = gg.data_loss(gg.forward(params, cfg, pairs, raw, n), labels, weights, cfg)
+            lp = gg.data_loss(gg.forward(params, cfg, pairs, raw, n, roi_x0=x0), labels, weights, cfg)
             flat[i] = old - h
-            lm = gg.data_loss(gg.forward(params, cfg, pairs, raw, n), labels, weights, cfg)
+            lm = gg.data_loss(gg.forward(params, cfg, pairs, raw, n, roi_x0=x0), labels, weights, cfg)
             flat[i] = old
             num = (lp - lm) / (2 * h)
             ana = grads[e.name].reshape(-1)[i - e.offset]
@@ -70,6 +78,10 @@ def test_gradients_match_finite_differences():
 
 def test_gradients_with_neighbor_feats_and_normalized_loss():
     check(neighbor_feats=True, normalize=True)
+
+
+def test_gradients_with_image_feature_head():
+    check(neighbor_feats=False, normalize=False, imfeats=True)
 
 
 def test_forward_matches_float32_oracle():
