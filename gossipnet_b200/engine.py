@@ -345,6 +345,20 @@ class GnetEngine(object):
         ops.predict_collapse(self.flat, table, md, self._buf('pred_scratch', (2 * md,)), w_eff, b_eff)
         return ops.rowdot_fwd(feats, w_eff, b_eff, self._buf('logits', (feats.shape[0],)))
 
+    def _empty_result(self):
+        """A batch without a single detection (every image empty): nothing to launch."""
+        dev, f32, i32 = self.device, torch.float32, torch.int32
+        zero = torch.zeros(1, dtype=i32, device=dev)
+        self._last_num_pairs, self._last_capacity = zero, max(self.capacity, 1)
+        e = lambda shape, dt=f32: torch.empty(shape, dtype=dt, device=dev)
+        res = dict(prediction=e((0,)), row_ptr=zero, num_pairs=zero, pair_c=e((0,), i32),
+                   pair_n=e((0,), i32), pair_iou=e((0,)), pw_feats=e((0, self.pw_width)),
+                   feats=e((0, self.g['shortcut_dim'])), capacity=0)
+        if self.keep_block_feats:
+            res['block_feats'] = [e((0, self.g['shortcut_dim']))
+                                  for _ in range(self.g['num_blocks'] + 1)]
+        return res
+
     def image_features(self, dets, img_off_host, imfeats, out):
         """Start features from the image (network.py:103-119, 223-240): boxes enlarged by
         half their size -> ROI max pooling of each image's feature map [1,H,W,C] (stride 16)
@@ -377,6 +391,8 @@ class GnetEngine(object):
         cfg.gnet.imfeats, `imfeats` is the list of per-image feature maps."""
         T = dets.shape[0]
         g = self.g
+        if T == 0:
+            return self._empty_result()
         row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = self.neighbors(dets, img_off)
         pw = self.pair_features(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, cap)
         d = g['shortcut_dim']

@@ -182,7 +182,7 @@ class Gnet(object):
         while True:
             res = eng.forward(io['dets'], io['det_scores'], io['det_classes'], io['img_off'],
                               imfeats=imfeats, img_off_host=io['img_off_host'])
-            if with_gt:
+            if with_gt and io['dets'].shape[0] > 0:
                 res.update(eng.matching_and_loss(
                     res['prediction'], io['dets'], io['det_classes'], io['img_off'],
                     io['img_off_host'], io['gt_boxes'], io['gt_crowd'], io['gt_classes'],
