@@ -44,6 +44,9 @@ SIGNATURES = {
     'gn_block_pair_fwd_hl': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                              c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int, c_void_p, c_void_p],
+    'gn_neighbor_count_masks': [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p],
+    'gn_neighbor_fill_masks': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, c_void_p],
     'gn_frcn_boxes': [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p],
     'gn_predict_collapse': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'gn_rowdot_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],

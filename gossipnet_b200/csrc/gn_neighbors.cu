@@ -87,6 +87,126 @@ neighbor_kernel(const float* __restrict__ dets, const int32_t* __restrict__ img_
   }
 }
 
+
+// ---------------------------------------------------------------------------------
+// Mask variant (the shipped path): the count pass decides  iou >= thresh  WITHOUT the IEEE
+// division for all but borderline pairs and leaves one 32-bit hit mask per (row, 32
+// columns of its image); the fill pass touches only the hits (P << N^2) and computes the
+// exact IoU value there.  The decision is bit-identical to thresholding fl(inter / union):
+// with t = thresh * union (one rounding, 2^-24) and d = 2^-20,
+//     inter >= t (1 + d)  =>  inter/union > thresh (1 + 2^-21)  =>  fl(inter/union) >= thresh
+//     inter <= t (1 - d)  =>  inter/union < thresh (1 - 2^-21)  =>  fl(inter/union) <  thresh
+// (rounding is monotonic and both bounds are several ulps away from thresh); the band in
+// between takes the exact division.  Mask word w of row r covers columns lo + 32 w .. + 31
+// of r's own image [lo, hi); `stride` words per row (>= ceil(largest image / 32)).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool iou_at_least(const Box& a, const Box& b, float thresh) {
+  const float inter = box_intersection(a, b);
+  const float uni = __fsub_rn(__fadd_rn(a.area, b.area), inter);
+  const float t = __fmul_rn(thresh, uni);
+  const float hi = __fmul_rn(t, 1.0f + 9.5367431640625e-07f);   // 1 + 2^-20
+  const float lo = __fmul_rn(t, 1.0f - 9.5367431640625e-07f);
+  if (thresh > 0.f && uni > 0.f) {
+    if (inter >= hi) return true;
+    if (inter <= lo) return false;
+  }
+  return box_iou(a, b) >= thresh;      // borderline, thresh <= 0 or a degenerate box: exact test
+}
+
+__global__ void __launch_bounds__(NB_THREADS)
+neighbor_mask_kernel(const float* __restrict__ dets, const int32_t* __restrict__ img_off,
+                     int num_images, int num_dets, float thresh, int stride,
+                     int32_t* __restrict__ degree, uint32_t* __restrict__ masks) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int row0 = blockIdx.x * NB_ROWS_PER_CTA + warp * NB_ROWS_PER_WARP;
+  if (row0 >= num_dets) return;
+  Box rb[NB_ROWS_PER_WARP];
+  int lo[NB_ROWS_PER_WARP], hi[NB_ROWS_PER_WARP], cnt[NB_ROWS_PER_WARP];
+#pragma unroll
+  for (int i = 0; i < NB_ROWS_PER_WARP; ++i) {
+    const int r = row0 + i;
+    cnt[i] = 0;
+    lo[i] = hi[i] = -1;
+    rb[i] = Box{0.f, 0.f, 0.f, 0.f, 0.f};
+    if (r < num_dets) {
+      const int img = find_image(img_off, num_images, r);
+      lo[i] = __ldg(img_off + img);
+      hi[i] = __ldg(img_off + img + 1);
+      rb[i] = make_box(ldg4(dets + (size_t)r * 4));
+    }
+  }
+  // rows of one image are contiguous: walk the (at most 4) images the warp's rows touch, so
+  // every row's mask words are aligned to its own image start
+  int i0 = 0;
+  while (i0 < NB_ROWS_PER_WARP && lo[i0] >= 0) {
+    const int seg_lo = lo[i0], seg_hi = hi[i0];
+    int i1 = i0;
+    while (i1 < NB_ROWS_PER_WARP && lo[i1] == seg_lo) ++i1;
+    for (int c0 = seg_lo, w = 0; c0 < seg_hi; c0 += 32, ++w) {
+      const int c = c0 + lane;
+      const bool in_range = c < seg_hi;
+      const Box cb = make_box(in_range ? ldg4(dets + (size_t)c * 4) : make_float4(0.f, 0.f, 1.f, 1.f));
+#pragma unroll
+      for (int i = 0; i < NB_ROWS_PER_WARP; ++i) {
+        if (i < i0 || i >= i1) continue;          // warp uniform
+        const bool hit = in_range && iou_at_least(rb[i], cb, thresh);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0 && w < stride) masks[(size_t)(row0 + i) * stride + w] = mask;
+        cnt[i] += __popc(mask);
+      }
+    }
+    i0 = i1;
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NB_ROWS_PER_WARP; ++i)
+      if (row0 + i < num_dets) degree[row0 + i] = cnt[i];
+  }
+}
+
+// one warp per row: lane l takes mask words l, l + 32, ...; ordered positions from a warp
+// prefix sum of the popcounts; the exact IoU only for the set bits
+__global__ void __launch_bounds__(NB_THREADS)
+neighbor_fill_mask_kernel(const float* __restrict__ dets, const int32_t* __restrict__ img_off,
+                          int num_images, int num_dets, const int32_t* __restrict__ row_ptr,
+                          int capacity, const uint32_t* __restrict__ masks, int stride,
+                          int32_t* __restrict__ pair_c, int32_t* __restrict__ pair_n,
+                          float* __restrict__ pair_iou) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
+  if (r >= num_dets) return;
+  const int img = find_image(img_off, num_images, r);
+  const int lo = __ldg(img_off + img), hi = __ldg(img_off + img + 1);
+  const Box rb = make_box(ldg4(dets + (size_t)r * 4));
+  int base = __ldg(row_ptr + r);
+  const int words = min((hi - lo + 31) >> 5, stride);
+  for (int w0 = 0; w0 < words; w0 += 32) {
+    const int w = w0 + lane;
+    unsigned m = w < words ? __ldg(masks + (size_t)r * stride + w) : 0u;
+    const int n = __popc(m);
+    int incl = n;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    int pos = base + incl - n;
+    base += __shfl_sync(0xffffffffu, incl, 31);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int c = lo + (w << 5) + b;
+      if (pos < capacity) {
+        pair_c[pos] = r;
+        pair_n[pos] = c;
+        pair_iou[pos] = box_iou(rb, make_box(ldg4(dets + (size_t)c * 4)));
+      }
+      ++pos;
+    }
+  }
+}
+
 // Single-CTA exclusive scan with a running carry: out[0..n] (out[n] = total).
 // n is at most a few hundred thousand detections, the scan is latency-bound and
 // a single pass over L2-resident data; one CTA of 1024 threads x 4 items.
@@ -181,5 +301,38 @@ extern "C" int gn_neighbor_fill(const float* dets, const int32_t* img_off, int n
       dets, img_off, num_images, num_dets, thresh, row_ptr, capacity, nullptr, pair_c, pair_n,
       pair_iou, overflow);
   GN_CHECK_LAUNCH("gn_neighbor_fill");
+  return GN_OK;
+}
+
+extern "C" int gn_neighbor_count_masks(const float* dets, const int32_t* img_off, int num_images,
+                                       int num_dets, float thresh, int stride_words,
+                                       int32_t* degree, uint32_t* masks, gn_stream_t stream) {
+  GN_REQUIRE(num_images >= 0 && num_dets >= 0 && stride_words > 0, "gn_neighbor_count_masks: bad size");
+  if (num_dets == 0) return GN_OK;
+  GN_REQUIRE(dets && img_off && degree && masks, "gn_neighbor_count_masks: null pointer");
+  GN_REQUIRE(num_images > 0, "gn_neighbor_count_masks: detections without images");
+  GN_REQUIRE(((uintptr_t)dets & 15) == 0, "gn_neighbor_count_masks: dets must be 16-byte aligned");
+  const int grid = gn::ceil_div(num_dets, gn::NB_ROWS_PER_CTA);
+  gn::neighbor_mask_kernel<<<grid, gn::NB_THREADS, 0, (cudaStream_t)stream>>>(
+      dets, img_off, num_images, num_dets, thresh, stride_words, degree, masks);
+  GN_CHECK_LAUNCH("gn_neighbor_count_masks");
+  return GN_OK;
+}
+
+extern "C" int gn_neighbor_fill_masks(const float* dets, const int32_t* img_off, int num_images,
+                                      int num_dets, const int32_t* row_ptr, int capacity,
+                                      const uint32_t* masks, int stride_words, int32_t* pair_c,
+                                      int32_t* pair_n, float* pair_iou, gn_stream_t stream) {
+  GN_REQUIRE(num_images >= 0 && num_dets >= 0 && capacity >= 0 && stride_words > 0,
+             "gn_neighbor_fill_masks: bad size");
+  if (num_dets == 0) return GN_OK;
+  GN_REQUIRE(dets && img_off && row_ptr && masks && pair_c && pair_n && pair_iou,
+             "gn_neighbor_fill_masks: null pointer");
+  GN_REQUIRE(num_images > 0, "gn_neighbor_fill_masks: detections without images");
+  const int grid = gn::ceil_div(num_dets, gn::NB_THREADS / 32);
+  gn::neighbor_fill_mask_kernel<<<grid, gn::NB_THREADS, 0, (cudaStream_t)stream>>>(
+      dets, img_off, num_images, num_dets, row_ptr, capacity, masks, stride_words, pair_c, pair_n,
+      pair_iou);
+  GN_CHECK_LAUNCH("gn_neighbor_fill_masks");
   return GN_OK;
 }

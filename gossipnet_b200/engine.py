@@ -92,6 +92,9 @@ class GnetEngine(object):
         # the predict head's hidden layers are linear (network.py:263): apply it as one folded
         # affine map instead of three FC launches (False: the staged FCs)
         self.collapse_predict = True
+        # neighbor build through per-row hit masks (division-free threshold test in the count
+        # pass, exact IoU only for the hits in the fill pass); False: both passes recompute
+        self.use_neighbor_masks = True
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name, shape, dtype=torch.float32):
@@ -118,12 +121,23 @@ class GnetEngine(object):
         return p
 
     # -------------------------------------------------------------------- forward
-    def neighbors(self, dets, img_off):
-        """A3. -> (row_ptr[T+1], num_pairs_dev[1], pair_c, pair_n, pair_iou, capacity)."""
+    def neighbors(self, dets, img_off, max_img=None):
+        """A3. -> (row_ptr[T+1], num_pairs_dev[1], pair_c, pair_n, pair_iou, capacity).
+        `max_img` = detections of the largest image (host int): sizes the per-row hit masks
+        of the mask variant; None reads it back from img_off (one sync)."""
         T = dets.shape[0]
         degree = self._buf('degree', (T,), torch.int32)
         row_ptr = self._buf('row_ptr', (T + 1,), torch.int32)
-        ops.neighbor_count(dets, img_off, self.g['neighbor_thresh'], degree)
+        masks = None
+        if self.use_neighbor_masks:
+            if max_img is None:
+                max_img = int((img_off[1:] - img_off[:-1]).max().item())
+            stride = max(1, (int(max_img) + 31) // 32)
+            # the dense-proposal stress image (N = 10 000) needs 313 words x 10 000 rows = 12.5 MB
+            masks = self._buf('nb_masks', (T, stride), torch.int32)
+            ops.neighbor_count_masks(dets, img_off, self.g['neighbor_thresh'], stride, degree, masks)
+        else:
+            ops.neighbor_count(dets, img_off, self.g['neighbor_thresh'], degree)
         ops.exclusive_scan(degree, row_ptr)
         num_pairs = row_ptr[T:T + 1]
         cap = self._ensure_capacity(num_pairs, T)
@@ -136,8 +150,12 @@ class GnetEngine(object):
         pair_c = self._buf('pair_c', (cap,), torch.int32)
         pair_n = self._buf('pair_n', (cap,), torch.int32)
         pair_iou = self._buf('pair_iou', (cap,), torch.float32)
-        ops.neighbor_fill(dets, img_off, self.g['neighbor_thresh'], row_ptr, cap, pair_c, pair_n,
-                          pair_iou, None)
+        if masks is not None:
+            ops.neighbor_fill_masks(dets, img_off, row_ptr, cap, masks, masks.shape[1], pair_c,
+                                    pair_n, pair_iou)
+        else:
+            ops.neighbor_fill(dets, img_off, self.g['neighbor_thresh'], row_ptr, cap, pair_c,
+                              pair_n, pair_iou, None)
         self._last_num_pairs, self._last_capacity = num_pairs, cap
         return row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap
 
@@ -383,7 +401,8 @@ class GnetEngine(object):
             scope += '_1'
         return self._fc(x, scope, True, out=out), roifeats, x, rois
 
-    def forward(self, dets, scores, classes, img_off, imfeats=None, img_off_host=None):
+    def forward(self, dets, scores, classes, img_off, imfeats=None, img_off_host=None,
+                max_img=None):
         """dets[T,4] f32, scores[T] f32, classes[T] i32, img_off[B+1] i32 (all
         CUDA) -> dict(prediction[T], row_ptr, num_pairs, pair_c, pair_n,
         pair_iou, pw_feats, feats, [block_feats]).  Returned tensors are views
@@ -393,7 +412,9 @@ class GnetEngine(object):
         g = self.g
         if T == 0:
             return self._empty_result()
-        row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = self.neighbors(dets, img_off)
+        if max_img is None and img_off_host is not None:
+            max_img = int(np.max(np.diff(np.asarray(img_off_host))))
+        row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = self.neighbors(dets, img_off, max_img)
         pw = self.pair_features(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, cap)
         d = g['shortcut_dim']
         feats = self._buf('feats0', (T, d))

@@ -65,6 +65,26 @@ def neighbor_count(dets, img_off, thresh, degree=None):
     return degree
 
 
+def neighbor_count_masks(dets, img_off, thresh, stride_words, degree, masks):
+    """Count pass of the mask variant: degree[T] + hit masks [T, stride_words] (uint32 as int32)."""
+    _lib.call('gn_neighbor_count_masks', _chk(dets, torch.float32, 'dets'),
+              _chk(img_off, torch.int32, 'img_off'), img_off.numel() - 1, dets.shape[0],
+              float(thresh), int(stride_words), _chk(degree, torch.int32, 'degree'),
+              _chk(masks, torch.int32, 'masks'), _stream())
+    return degree, masks
+
+
+def neighbor_fill_masks(dets, img_off, row_ptr, capacity, masks, stride_words, pair_c, pair_n,
+                        pair_iou):
+    _lib.call('gn_neighbor_fill_masks', _chk(dets, torch.float32, 'dets'),
+              _chk(img_off, torch.int32, 'img_off'), img_off.numel() - 1, dets.shape[0],
+              _chk(row_ptr, torch.int32, 'row_ptr'), int(capacity), _chk(masks, torch.int32, 'masks'),
+              int(stride_words), _chk(pair_c, torch.int32, 'pair_c'),
+              _chk(pair_n, torch.int32, 'pair_n'), _chk(pair_iou, torch.float32, 'pair_iou'),
+              _stream())
+    return pair_c, pair_n, pair_iou
+
+
 def exclusive_scan(x, out=None):
     n = x.numel()
     if out is None:

@@ -25,6 +25,7 @@ class InferenceSession(object):
         self.device = net.device
         self.use_graph = use_graph
         self._shape = None
+        self._max_img = 0
         self._graph = None
         self.stream = torch.cuda.Stream(device=self.device)
         self.launches_per_forward = None
@@ -47,7 +48,8 @@ class InferenceSession(object):
         self._graph = None
 
     def _forward(self):
-        res = self.engine.forward(self.d_dets, self.d_scores, self.d_cls, self.d_off)
+        res = self.engine.forward(self.d_dets, self.d_scores, self.d_cls, self.d_off,
+                                  max_img=self._max_img)
         self._pred, self._num_pairs, self._cap = res['prediction'], res['num_pairs'], res['capacity']
 
     def _prepare(self):
@@ -79,7 +81,11 @@ class InferenceSession(object):
         img_off[B+1] i32 -> new scores (logits) [T] f32 (a view of the pinned
         result buffer, valid until the next run)."""
         T, B = int(dets.shape[0]), int(img_off.shape[0]) - 1
-        if self._shape != (T, B):
+        # the captured graph is specific to (T, B) and to the mask stride of the neighbor
+        # build, i.e. to the size of the largest image (rounded up to 32 detections)
+        max_img = (int(np.max(np.diff(img_off))) + 31) // 32 * 32 if B > 0 else 0
+        if self._shape != (T, B) or max_img != self._max_img:
+            self._max_img = max_img
             self._alloc(T, B)
         self.h_dets.numpy()[...] = dets
         self.h_scores.numpy()[...] = det_scores

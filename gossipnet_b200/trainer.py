@@ -83,11 +83,13 @@ class Trainer(object):
             self.gradbuf.zero_()
 
         # ---- forward, keeping activations (unfused CUDA pieces) ---------------------
-        row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dets, img_off)
+        max_img = int(np.max(np.diff(io['img_off_host'])))
+        row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dets, img_off, max_img)
         P = int(num_pairs.item())
         if P > cap:   # grow and redo the fill
             eng.capacity = int(P * 1.25) + 256
-            row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dets, img_off)
+            row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dets, img_off,
+                                                                              max_img)
         cls = classes if eng.multiclass else None
         raw = ops.pair_geometry(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
                                 eng.num_classes, g['pw_feat_multiplyer'])

@@ -61,6 +61,20 @@ int gn_iou_dense(const float* a, const float* b, const uint8_t* crowd,
                  const int32_t* a_cls, const int32_t* b_cls,
                  int batch, int n, int m, float* out, gn_stream_t stream);
 
+/* Mask variant of the neighbor build (shipped path).  gn_neighbor_count_masks decides
+ * iou >= thresh without the IEEE division except for borderline pairs (bit-identical decision,
+ * see gn_neighbors.cu) and writes, next to degree[], one 32-bit hit mask per (row, 32 columns
+ * of the row's image): masks[row * stride_words + w] covers columns img_lo + 32 w .. + 31;
+ * stride_words >= ceil(largest image / 32).  gn_neighbor_fill_masks expands the masks into
+ * pair_c / pair_n / pair_iou (exact IoU, computed for the hits only), same order and values
+ * as gn_neighbor_fill. */
+int gn_neighbor_count_masks(const float* dets, const int32_t* img_off, int num_images,
+                            int num_dets, float thresh, int stride_words, int32_t* degree,
+                            uint32_t* masks, gn_stream_t stream);
+int gn_neighbor_fill_masks(const float* dets, const int32_t* img_off, int num_images,
+                           int num_dets, const int32_t* row_ptr, int capacity,
+                           const uint32_t* masks, int stride_words, int32_t* pair_c,
+                           int32_t* pair_n, float* pair_iou, gn_stream_t stream);
 /* ---- A3: neighbor build ----------------------------------------------------
  * Replaces tf.where(det_det_iou >= cfg.gnet.neighbor_thresh)
  * (nms_net/network.py:192-195).  IoU is recomputed from the boxes (same

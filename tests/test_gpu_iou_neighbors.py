@@ -69,12 +69,25 @@ def test_batched_iou_matches_per_image():
         assert np.array_equal(bits(got[i]), bits(ref))
 
 
-def build_pairs(dets_list, thresh=0.2):
+def build_pairs(dets_list, thresh=0.2, masks=False):
     n = [d.shape[0] for d in dets_list]
     off = np.zeros(len(n) + 1, np.int32)
     np.cumsum(n, out=off[1:])
     dets = dev(np.concatenate(dets_list).reshape(-1, 4))
     img_off = dev(off)
+    if masks:      # the shipped variant: division-free count pass + per-row hit masks
+        T = int(off[-1])
+        stride = max(1, (max(n) + 31) // 32)
+        degree = torch.empty(T, dtype=torch.int32, device='cuda')
+        hit = torch.full((T, stride), -1, dtype=torch.int32, device='cuda')
+        ops.neighbor_count_masks(dets, img_off, thresh, stride, degree, hit)
+        row_ptr = ops.exclusive_scan(degree)
+        P = int(row_ptr[-1].item())
+        pc = torch.empty(P, dtype=torch.int32, device='cuda')
+        pn = torch.empty(P, dtype=torch.int32, device='cuda')
+        pi = torch.empty(P, dtype=torch.float32, device='cuda')
+        ops.neighbor_fill_masks(dets, img_off, row_ptr, P, hit, stride, pc, pn, pi)
+        return off, row_ptr.cpu().numpy(), pc.cpu().numpy(), pn.cpu().numpy(), pi.cpu().numpy()
     degree = ops.neighbor_count(dets, img_off, thresh)
     row_ptr = ops.exclusive_scan(degree)
     P = int(row_ptr[-1].item())
@@ -87,12 +100,13 @@ def build_pairs(dets_list, thresh=0.2):
     return off, row_ptr.cpu().numpy(), pc.cpu().numpy(), pn.cpu().numpy(), pi.cpu().numpy()
 
 
+@pytest.mark.parametrize('masks', [False, True])
 @pytest.mark.parametrize('sizes', [[1], [40], [300], [1000], [17, 1, 255, 64, 3], [1000] * 4,
-                                   [2000], [0, 5, 0, 7]])
-def test_neighbor_lists_bit_exact(sizes):
+                                   [2000], [0, 5, 0, 7], [3, 2, 1, 1, 1, 6, 33, 2]])
+def test_neighbor_lists_bit_exact(sizes, masks):
     dets_list = [synthetic.make_image(max(n, 1), 1, image_index=i)['dets'][:n]
                  for i, n in enumerate(sizes)]
-    off, row_ptr, pc, pn, pi = build_pairs(dets_list)
+    off, row_ptr, pc, pn, pi = build_pairs(dets_list, masks=masks)
     want_c, want_n, want_iou = [], [], []
     for i, d in enumerate(dets_list):
         bd = go.xyxy_to_boxdata(d)
@@ -127,10 +141,31 @@ def test_threshold_edge_inclusive_on_gpu():
         found = np.array([[0, 0, 12, 10], [8, 0, 20, 10]], F32)  # inter 40, union 200
     m = go.iou(go.xyxy_to_boxdata(found), go.xyxy_to_boxdata(found))
     assert m[0, 1] == thr
-    _, _, pc, pn, _ = build_pairs([found])
-    assert list(zip(pc.tolist(), pn.tolist())) == [(0, 0), (0, 1), (1, 0), (1, 1)]
-    _, _, pc, pn, _ = build_pairs([found], thresh=float(np.nextafter(thr, F32(1))))
-    assert list(zip(pc.tolist(), pn.tolist())) == [(0, 0), (1, 1)]
+    for masks in (False, True):     # the division-free test must agree on the exact edge
+        _, _, pc, pn, _ = build_pairs([found], masks=masks)
+        assert list(zip(pc.tolist(), pn.tolist())) == [(0, 0), (0, 1), (1, 0), (1, 1)]
+        _, _, pc, pn, _ = build_pairs([found], thresh=float(np.nextafter(thr, F32(1))), masks=masks)
+        assert list(zip(pc.tolist(), pn.tolist())) == [(0, 0), (1, 1)]
+
+
+def test_division_free_threshold_agrees_near_the_edge():
+    """Pairs engineered to land within a few ulps of the threshold on both sides: the mask
+    variant (fast accept / reject + exact fallback) equals thresholding the dense IoU."""
+    rs = np.random.RandomState(3)
+    boxes = []
+    for _ in range(400):
+        w, h = rs.uniform(20, 200, 2)
+        # two boxes of equal size shifted along x so that iou = (w - s) / (w + s) ~ 0.2
+        s = w * (1 - 0.2) / (1 + 0.2) * (1 + rs.uniform(-3e-7, 3e-7))
+        x, y = rs.uniform(0, 500, 2)
+        boxes += [[x, y, x + w, y + h], [x + s, y, x + s + w, y + h]]
+    d = np.array(boxes, F32)
+    for thresh in (0.2, float(np.nextafter(F32(0.2), F32(1))), float(np.nextafter(F32(0.2), F32(0)))):
+        off, _, pc, pn, pi = build_pairs([d], thresh=thresh, masks=True)
+        m = go.iou(go.xyxy_to_boxdata(d), go.xyxy_to_boxdata(d))
+        want = np.argwhere(m >= F32(thresh))
+        assert np.array_equal(np.stack([pc, pn], axis=1), want)
+        assert np.array_equal(bits(pi), bits(m[want[:, 0], want[:, 1]]))
 
 
 def test_fill_reports_overflow_and_stays_in_bounds():
