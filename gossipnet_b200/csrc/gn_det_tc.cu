@@ -37,7 +37,14 @@ constexpr uint32_t DT_OFF_A = DT_OFF_WABL + 4 * DT_D * 16;           // 81920 = 
 constexpr uint32_t DT_A_BYTES = 2 * 16 * DT_LBO_A;                   // K up to 128, hi + lo
 constexpr uint32_t DT_OFF_BIAS = DT_OFF_A + DT_A_BYTES;              // b_fc1[64] b_fc2[128] b_rd[32] b_ab[64]
 constexpr uint32_t DT_OFF_BAR = DT_OFF_BIAS + (DT_F + DT_D + DT_R + DT_F) * 4;
-constexpr uint32_t DT_SMEM = DT_OFF_BAR + 16;   // two mbarriers: UMMA completion, weight image
+// feats tile staging [128 rows][128 fp32], row pitch 512 + 16 bytes: the shortcut operand
+// comes in and the block output leaves as whole 512-byte rows (one warp instruction = one
+// row = 4 L1 wavefronts) and is transposed to / from the row-per-thread epilogue layout
+// through shared memory (16-byte accesses at a 528-byte pitch are conflict free).  A
+// row-per-thread LDG / STG costs one wavefront per lane: 8 192 wavefront cycles per tile.
+constexpr uint32_t DT_STAGE_PITCH = DT_D * 4 + 16;
+constexpr uint32_t DT_OFF_STAGE = (DT_OFF_BAR + 16 + 127) / 128 * 128;
+constexpr uint32_t DT_SMEM = DT_OFF_STAGE + DT_TILE * DT_STAGE_PITCH;   // two mbarriers before it
 static_assert(DT_SMEM <= 227 * 1024, "det tile exceeds shared memory");
 
 // transpose + split w[k_total, n_total] (fp32, [in,out]) into K-major hi/lo tiles
@@ -143,6 +150,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
     umma::fence_barrier_init();
   }
   uint64_t* wbar = bar + 1;
+  unsigned char* stage = smem + DT_OFF_STAGE;
   if (wimg != nullptr) {
     // operand image from gn_prepare_operands, laid out like the shared-memory weight
     // region [fc1^T hi|lo, fc2^T hi|lo, rd^T hi|lo] (64 KB): two bulk copies
@@ -239,23 +247,35 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
         dt_gemm<DT_F / 16>(tm2, d_ah, d_al, d_w2h, d_w2l, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
         umma::mma_commit(bar);
       }
-      // the shortcut operand (this thread's 64 columns of feats_in) is fetched while the
-      // fc2 UMMAs run: 16 x 16 bytes in flight per thread, latency paid once
-      float4 resid[16];
+      // the shortcut tile (feats_in rows) is fetched while the fc2 UMMAs run: every warp
+      // instruction reads one whole 512-byte row (16 rows per warp, all in flight), then the
+      // rows go to the staging tile for the row-per-thread epilogue
+      {
+        float4 rowv[16];
 #pragma unroll
-      for (int g = 0; g < 16; ++g)
-        resid[g] = live ? ldg4(feats_in + (size_t)grow * DT_D + ehalf * 64 + g * 4)
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = 0; g < 16; ++g) {
+          const int r = g * 8 + warp;
+          rowv[g] = (row0 + r < num_dets) ? ldg4(feats_in + (size_t)(row0 + r) * DT_D + lane * 4)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int g = 0; g < 16; ++g)
+          *reinterpret_cast<float4*>(stage + (g * 8 + warp) * DT_STAGE_PITCH + lane * 16) = rowv[g];
+      }
+      __syncthreads();
+      float* srow = reinterpret_cast<float*>(stage + erow * DT_STAGE_PITCH) + ehalf * 64;
       umma::mbar_wait(bar, par);
       par ^= 1;
       umma::tc_fence_after();
-      // ---- feats_out = relu(feats_in + acc + b_fc2) -> global, and -> A (K = 128) ------
+      // ---- feats_out = relu(feats_in + acc + b_fc2) -> staging (in place), and -> A (K = 128)
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {
         const int col0 = ehalf * 64 + cc;
         float v[16];
         umma::tmem_ld16(tm2 + tlane + col0, v);
-        const float4* res = resid + (cc >> 2);
+        float4 res[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) res[g] = *reinterpret_cast<const float4*>(srow + cc + g * 4);
         umma::tmem_ld_wait();
         float x[16];
 #pragma unroll
@@ -265,12 +285,10 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
           x[g * 4 + 2] = fmaxf(res[g].z + (v[g * 4 + 2] + bias2[col0 + g * 4 + 2]), 0.f);
           x[g * 4 + 3] = fmaxf(res[g].w + (v[g * 4 + 3] + bias2[col0 + g * 4 + 3]), 0.f);
         }
-        if (live) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
-            *reinterpret_cast<float4*>(feats_out + (size_t)grow * DT_D + col0 + g * 4) =
-                make_float4(x[g * 4 + 0], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
-        }
+        for (int g = 0; g < 4; ++g)
+          *reinterpret_cast<float4*>(srow + cc + g * 4) =
+              make_float4(x[g * 4 + 0], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
         if (stage_b) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -291,6 +309,20 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       if (weights_pending) { umma::mbar_wait(wbar, 0); weights_pending = false; }
     }
 
+    // block output: staging rows -> feats_out, one whole 512-byte row per warp instruction
+    auto store_feats_tile = [&]() {
+#pragma unroll
+      for (int g = 0; g < 16; ++g) {
+        const int r = g * 8 + warp;
+        const float4 x = *reinterpret_cast<const float4*>(stage + r * DT_STAGE_PITCH + lane * 16);
+        if (row0 + r < num_dets)
+          *reinterpret_cast<float4*>(feats_out + (size_t)(row0 + r) * DT_D + lane * 4) = x;
+      }
+    };
+    if (stage_a && !stage_b) {
+      __syncthreads();
+      store_feats_tile();
+    }
     if (stage_b) {
       umma::fence_smem_to_async();
       umma::tc_fence_before();
@@ -300,6 +332,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
         dt_gemm<DT_D / 16>(tmr, d_ah, d_al, d_wrh, d_wrl, DT_R * 16, umma::idesc_bf16_f32(DT_TILE, DT_R));
         umma::mma_commit(bar);
       }
+      if (stage_a) store_feats_tile();      // while the reduce_dim UMMAs run
       umma::mbar_wait(bar, par);
       par ^= 1;
       umma::tc_fence_after();
