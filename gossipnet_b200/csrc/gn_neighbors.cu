@@ -100,17 +100,35 @@ neighbor_kernel(const float* __restrict__ dets, const int32_t* __restrict__ img_
 // between takes the exact division.  Mask word w of row r covers columns lo + 32 w .. + 31
 // of r's own image [lo, hi); `stride` words per row (>= ceil(largest image / 32)).
 // ---------------------------------------------------------------------------------
+// image that owns detection row r, found by the whole warp at once: the number of images
+// that end at or before r (one round of independent loads per 32 images, where the binary
+// search of find_image is a chain of dependent ones - the prologue of a warp that only owns
+// four rows must not cost as much as its main loop)
+__device__ __forceinline__ int find_image_warp(const int32_t* __restrict__ off, int num_images,
+                                               int r, int lane) {
+  int count = 0;
+  for (int base = 0; base < num_images; base += 32) {
+    const int idx = base + lane;
+    const bool ended = idx < num_images && __ldg(off + idx + 1) <= r;
+    count += __popc(__ballot_sync(0xffffffffu, ended));
+  }
+  return min(count, num_images - 1);
+}
+
 __device__ __forceinline__ bool iou_at_least(const Box& a, const Box& b, float thresh) {
   const float inter = box_intersection(a, b);
   const float uni = __fsub_rn(__fadd_rn(a.area, b.area), inter);
   const float t = __fmul_rn(thresh, uni);
   const float hi = __fmul_rn(t, 1.0f + 9.5367431640625e-07f);   // 1 + 2^-20
   const float lo = __fmul_rn(t, 1.0f - 9.5367431640625e-07f);
-  if (thresh > 0.f && uni > 0.f) {
-    if (inter >= hi) return true;
-    if (inter <= lo) return false;
+  bool hit = inter >= hi;
+  // borderline, thresh <= 0 or a degenerate box: the exact test.  The common path stays
+  // branch free: one warp vote, and the division only runs if some lane needs it.
+  const bool border = !(thresh > 0.f && uni > 0.f) || (inter > lo && inter < hi);
+  if (__any_sync(0xffffffffu, border)) {
+    if (border) hit = box_iou(a, b) >= thresh;
   }
-  return box_iou(a, b) >= thresh;      // borderline, thresh <= 0 or a degenerate box: exact test
+  return hit;
 }
 
 __global__ void __launch_bounds__(NB_THREADS)
@@ -129,34 +147,51 @@ neighbor_mask_kernel(const float* __restrict__ dets, const int32_t* __restrict__
     cnt[i] = 0;
     lo[i] = hi[i] = -1;
     rb[i] = Box{0.f, 0.f, 0.f, 0.f, 0.f};
+    const int img = find_image_warp(img_off, num_images, min(r, num_dets - 1), lane);
     if (r < num_dets) {
-      const int img = find_image(img_off, num_images, r);
       lo[i] = __ldg(img_off + img);
       hi[i] = __ldg(img_off + img + 1);
       rb[i] = make_box(ldg4(dets + (size_t)r * 4));
     }
   }
   // rows of one image are contiguous: walk the (at most 4) images the warp's rows touch, so
-  // every row's mask words are aligned to its own image start
-  int i0 = 0;
-  while (i0 < NB_ROWS_PER_WARP && lo[i0] >= 0) {
-    const int seg_lo = lo[i0], seg_hi = hi[i0];
-    int i1 = i0;
-    while (i1 < NB_ROWS_PER_WARP && lo[i1] == seg_lo) ++i1;
-    for (int c0 = seg_lo, w = 0; c0 < seg_hi; c0 += 32, ++w) {
+  // every row's mask words are aligned to its own image start.  All array indices are
+  // compile-time constants (dynamic ones would send lo / hi / rb to local memory).
+#pragma unroll
+  for (int s0 = 0; s0 < NB_ROWS_PER_WARP; ++s0) {
+    const bool starts = lo[s0] >= 0 && (s0 == 0 || lo[s0] != lo[s0 > 0 ? s0 - 1 : 0]);
+    if (!starts) continue;                          // warp uniform
+    const int seg_lo = lo[s0], seg_hi = hi[s0];
+    // lane (w % 32) keeps the mask of iteration w; every 32 iterations (and at the end) the
+    // warp writes 32 words of each row with one coalesced store
+    unsigned acc[NB_ROWS_PER_WARP] = {0u, 0u, 0u, 0u};
+    int w = 0;
+    for (int c0 = seg_lo; c0 < seg_hi; c0 += 32, ++w) {
       const int c = c0 + lane;
       const bool in_range = c < seg_hi;
       const Box cb = make_box(in_range ? ldg4(dets + (size_t)c * 4) : make_float4(0.f, 0.f, 1.f, 1.f));
 #pragma unroll
-      for (int i = 0; i < NB_ROWS_PER_WARP; ++i) {
-        if (i < i0 || i >= i1) continue;          // warp uniform
-        const bool hit = in_range && iou_at_least(rb[i], cb, thresh);
-        const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0 && w < stride) masks[(size_t)(row0 + i) * stride + w] = mask;
+      for (int i = s0; i < NB_ROWS_PER_WARP; ++i) {
+        if (lo[i] != seg_lo) continue;              // warp uniform
+        const bool over = iou_at_least(rb[i], cb, thresh);   // all lanes: it votes
+        const unsigned mask = __ballot_sync(0xffffffffu, in_range && over);
+        if ((w & 31) == lane) acc[i] = mask;
         cnt[i] += __popc(mask);
       }
+      if ((w & 31) == 31) {
+#pragma unroll
+        for (int i = s0; i < NB_ROWS_PER_WARP; ++i)
+          if (lo[i] == seg_lo && (w - 31 + lane) < stride)
+            masks[(size_t)(row0 + i) * stride + (w - 31) + lane] = acc[i];
+      }
     }
-    i0 = i1;
+    if ((w & 31) != 0) {
+      const int wbase = w & ~31;
+#pragma unroll
+      for (int i = s0; i < NB_ROWS_PER_WARP; ++i)
+        if (lo[i] == seg_lo && lane < (w & 31) && wbase + lane < stride)
+          masks[(size_t)(row0 + i) * stride + wbase + lane] = acc[i];
+    }
   }
   if (lane == 0) {
 #pragma unroll
@@ -176,7 +211,7 @@ neighbor_fill_mask_kernel(const float* __restrict__ dets, const int32_t* __restr
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (NB_THREADS / 32) + (threadIdx.x >> 5);
   if (r >= num_dets) return;
-  const int img = find_image(img_off, num_images, r);
+  const int img = find_image_warp(img_off, num_images, r, lane);
   const int lo = __ldg(img_off + img), hi = __ldg(img_off + img + 1);
   const Box rb = make_box(ldg4(dets + (size_t)r * 4));
   int base = __ldg(row_ptr + r);
