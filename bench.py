@@ -52,6 +52,9 @@ def parse():
                     help='budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'],
+                    help="arithmetic of the fused FC kernels: fp32 semantics (bf16x3, the "
+                         "headline) or plain bf16 operands (BASELINE configs[2]'s arithmetic)")
     return ap.parse_args()
 
 
@@ -60,11 +63,12 @@ def workload_name(n_dets, blocks):
             % (n_dets, blocks))
 
 
-def setup_cfg(blocks):
+def setup_cfg(blocks, precision='fp32'):
     from gossipnet_b200.nms_net.config import cfg, cfg_from_file, reset_cfg
     reset_cfg()
     cfg_from_file(os.path.join(ROOT, 'experiments', 'coco_person', 'conf.yaml'))
     cfg.gnet.num_blocks = blocks
+    cfg.gnet.compute_dtype = precision
     return cfg
 
 
@@ -200,7 +204,8 @@ def run_b200(args):
         if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
             os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    cfg = setup_cfg(args.blocks)
+    cfg = setup_cfg(args.blocks, args.precision)
+    bf16 = args.precision == 'bf16'
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -290,7 +295,7 @@ def run_b200(args):
                 ops.block_pair_fwd_pipe(res['pw_feats'], red, res['pair_c'], res['pair_n'],
                                         res['num_pairs'], res['capacity'],
                                         eng.p[s1 + 'pw_fc1/biases'], eng.p[s1 + 'pw_fc2/biases'],
-                                        wimg, pooled)
+                                        wimg, pooled, bf16=bf16)
                 b.record(stream)
                 stream.synchronize()
                 times.append(a.elapsed_time(b))
@@ -304,10 +309,11 @@ def run_b200(args):
                 'traffic': 378.9e6 * (P / 2486884.0),
                 'ms_per_launch': k_ms, 'launches_per_step': args.blocks,
                 'algorithmic_flops_per_launch': flops,
-                'peak_source': '%s bf16 sustained %.1f TF/s (kernel timed inside a long step). '
-                               'fp32 semantics via bf16x3: the kernel issues 3 tensor flops per '
-                               'algorithmic flop, so 0.333 is the ceiling of this fraction'
-                               % (peak_src, bf16_peak)}
+                'peak_source': '%s bf16 sustained %.1f TF/s (kernel timed inside a long step). %s'
+                               % (peak_src, bf16_peak,
+                                  'plain bf16 operands: one tensor flop per algorithmic flop' if bf16
+                                  else 'fp32 semantics via bf16x3: the kernel issues 3 tensor flops '
+                                       'per algorithmic flop, so 0.333 is the ceiling of this fraction')}
         # dense IoU kernel at the stress size (N=10000 -> 400 MB written, > L2)
         with torch.cuda.stream(stream):
             n_iou = 10000
@@ -358,10 +364,14 @@ def run_b200(args):
         print(json.dumps({
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if bf16 else 'f32',
+            'data': 'synthetic',
             'config': {'workload': workload_name(N, args.blocks),
-                       'arithmetic': 'fp32 in/out; FC GEMMs as bf16 hi/lo split products '
-                                     '(bf16x3) on tcgen05 with fp32 TMEM accumulation',
+                       'arithmetic': ('fp32 in/out; FC GEMMs with plain bf16 operands on tcgen05, '
+                                      'fp32 TMEM accumulation (--precision bf16; NOT the headline)'
+                                      if bf16 else
+                                      'fp32 in/out; FC GEMMs as bf16 hi/lo split products '
+                                      '(bf16x3) on tcgen05 with fp32 TMEM accumulation'),
                        'images_per_gpu_per_step': B, 'pairs_per_step_rank0': P,
                        'parallelism': 'images sharded over %d GPU(s), no data-path collective'
                                       % world,

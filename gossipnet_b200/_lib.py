@@ -47,6 +47,15 @@ SIGNATURES = {
     'gn_neighbor_count_masks': [c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p],
     'gn_neighbor_fill_masks': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p],
+    'gn_pwfeat_mlp_fwd_bf16': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    'gn_block_pair_fwd_pipe_bf16': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                               c_void_p],
+    'gn_block_det_fwd_img_bf16': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                             c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                             c_int, c_int, c_void_p],
     'gn_frcn_boxes': [c_void_p, c_int, c_float, c_int, c_void_p, c_void_p],
     'gn_predict_collapse': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'gn_rowdot_fwd': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p],

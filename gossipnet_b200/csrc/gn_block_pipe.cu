@@ -61,6 +61,10 @@ __device__ long long bp_trace[64];
 #define BP_TR(i) do { } while (0)
 #endif
 
+// X3 = true : fp32 semantics, every product as three bf16 UMMAs (hi*hi + hi*lo + lo*hi);
+// X3 = false: plain bf16 operands (the hi parts only) with fp32 accumulation - the "bf16"
+//             arithmetic BASELINE configs[2] names; a third of the UMMAs, half the fill.
+template <bool X3>
 __global__ void __launch_bounds__(BP_THREADS, 1)
 block_pair_pipe_kernel(const float* __restrict__ pw, const float* __restrict__ feats_hl,
                        const float* __restrict__ nfeats_hl, const int32_t* __restrict__ pair_c,
@@ -155,7 +159,7 @@ block_pair_pipe_kernel(const float* __restrict__ pw, const float* __restrict__ f
         pre[u][1] = pre[u][0];
         if (src != nullptr) {
           pre[u][0] = ldg4(src);
-          pre[u][1] = ldg4(src + (u < 2 ? 4 : 16));
+          if (X3 || u < 2) pre[u][1] = ldg4(src + (u < 2 ? 4 : 16));   // (the lo chunk of an hl row)
         }
       }
     };
@@ -188,10 +192,8 @@ block_pair_pipe_kernel(const float* __restrict__ pw, const float* __restrict__ f
           umma::split_bf16x2(v1.z, v1.w, h.w, l.w);
         }
         const uint32_t off = (uint32_t)(part * 4 + q) * BP_LBO_A + (uint32_t)row * 16;
-        {
-          *reinterpret_cast<uint4*>(a_hi + off) = h;
-          *reinterpret_cast<uint4*>(a_lo + off) = l;
-        }
+        *reinterpret_cast<uint4*>(a_hi + off) = h;
+        if (X3) *reinterpret_cast<uint4*>(a_lo + off) = l;
       }
       umma::fence_smem_to_async();
       __syncwarp();
@@ -217,9 +219,14 @@ block_pair_pipe_kernel(const float* __restrict__ pw, const float* __restrict__ f
         const uint64_t d_al = umma::smem_desc(sa + BP_CH1 * BP_LBO_A, BP_LBO_A, BP_SBO);
         const uint32_t d1 = tmem + (uint32_t)slot * 192;
 #pragma unroll
-        for (int ks = 0; ks < BP_K1 / 16; ++ks)
-          umma::mma_bf16x3(d1, d_ah, d_al, d_b1h, d_b1l, ks * (2 * BP_LBO_A >> 4),
-                           ks * (2 * BP_LBO_B >> 4), idesc, ks > 0);
+        for (int ks = 0; ks < BP_K1 / 16; ++ks) {
+          if (X3)
+            umma::mma_bf16x3(d1, d_ah, d_al, d_b1h, d_b1l, ks * (2 * BP_LBO_A >> 4),
+                             ks * (2 * BP_LBO_B >> 4), idesc, ks > 0);
+          else
+            umma::mma_bf16_ss(d1, d_ah + ks * (2 * BP_LBO_A >> 4), d_b1h + ks * (2 * BP_LBO_B >> 4),
+                              idesc, ks > 0);
+        }
         umma::mma_commit(&fc1_done[slot]);
         umma::mma_commit(&a_empty[slot]);
         { [[maybe_unused]] const int it = it_; BP_TR(3); }
@@ -238,9 +245,13 @@ block_pair_pipe_kernel(const float* __restrict__ pw, const float* __restrict__ f
 #pragma unroll
         for (int ks = 0; ks < BP_F / 16; ++ks) {
           const uint32_t boff = ks * (2 * BP_LBO_B >> 4);
-          umma::mma_bf16_ts(d2, hl + ks * 8, d_b2h + boff, idesc, ks > 0);
-          umma::mma_bf16_ts(d2, hh + ks * 8, d_b2l + boff, idesc, 1);
-          umma::mma_bf16_ts(d2, hh + ks * 8, d_b2h + boff, idesc, 1);
+          if (X3) {
+            umma::mma_bf16_ts(d2, hl + ks * 8, d_b2h + boff, idesc, ks > 0);
+            umma::mma_bf16_ts(d2, hh + ks * 8, d_b2l + boff, idesc, 1);
+            umma::mma_bf16_ts(d2, hh + ks * 8, d_b2h + boff, idesc, 1);
+          } else {
+            umma::mma_bf16_ts(d2, hh + ks * 8, d_b2h + boff, idesc, ks > 0);
+          }
         }
         umma::mma_commit(&fc2_done[slot]);
         BP_TR(1);
@@ -304,8 +315,10 @@ block_pair_pipe_kernel(const float* __restrict__ pw, const float* __restrict__ f
         const uint32_t c0 = (uint32_t)(ecol0 >> 1);
         umma::tmem_st8(tm_hh + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hh[0]));
         umma::tmem_st8(tm_hh + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hh[8]));
-        umma::tmem_st8(tm_hl + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hl[0]));
-        umma::tmem_st8(tm_hl + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hl[8]));
+        if (X3) {
+          umma::tmem_st8(tm_hl + tlane + c0, reinterpret_cast<const uint32_t(&)[8]>(hl[0]));
+          umma::tmem_st8(tm_hl + tlane + c0 + 8, reinterpret_cast<const uint32_t(&)[8]>(hl[8]));
+        }
         umma::tmem_st_wait();
       }
       umma::tc_fence_before();
@@ -374,12 +387,11 @@ extern "C" int gn_block_pair_trace(long long* host_out) {
 }
 #endif
 
-extern "C" int gn_block_pair_fwd_pipe(const float* pw, int w, const void* feats_hl,
-                                      const void* nfeats_hl, int r, const int32_t* pair_c,
-                                      const int32_t* pair_n, const int32_t* num_pairs,
-                                      int capacity, const float* b1, const float* b2,
-                                      const void* wimg, int f, float* pooled, gn_stream_t stream) {
-  const char* name = "gn_block_pair_fwd_pipe";
+static int launch_pair_pipe(const char* name, bool x3, const float* pw, int w, const void* feats_hl,
+                            const void* nfeats_hl, int r, const int32_t* pair_c,
+                            const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                            const float* b1, const float* b2, const void* wimg, int f,
+                            float* pooled, gn_stream_t stream) {
   GN_REQUIRE(capacity >= 0, "%s: negative capacity", name);
   if (w != gn::BP_W || r != gn::BP_R || f != gn::BP_F) {
     gn::set_error("%s: fused kernel is built for w=%d r=%d f=%d (got %d, %d, %d)", name,
@@ -391,8 +403,10 @@ extern "C" int gn_block_pair_fwd_pipe(const float* pw, int w, const void* feats_
                  pooled, "%s: null pointer", name);
   GN_REQUIRE((((uintptr_t)pw | (uintptr_t)feats_hl | (uintptr_t)nfeats_hl | (uintptr_t)wimg) & 15) == 0,
              "%s: pointers must be 16-byte aligned", name);
-  cudaError_t e = cudaFuncSetAttribute(gn::block_pair_pipe_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn::BP_SMEM);
+  const void* kern = x3 ? (const void*)gn::block_pair_pipe_kernel<true>
+                        : (const void*)gn::block_pair_pipe_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)gn::BP_SMEM);
   if (e != cudaSuccess) {
     gn::set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
     return GN_ERR_CUDA;
@@ -400,9 +414,33 @@ extern "C" int gn_block_pair_fwd_pipe(const float* pw, int w, const void* feats_
   int grid = gn::ceil_div(capacity, gn::BP_TILE);
   const int sms = gn::sm_count();
   if (grid > sms) grid = sms;
-  gn::block_pair_pipe_kernel<<<grid, gn::BP_THREADS, gn::BP_SMEM, (cudaStream_t)stream>>>(
-      pw, static_cast<const float*>(feats_hl), static_cast<const float*>(nfeats_hl), pair_c, pair_n,
-      num_pairs, capacity, b1, b2, static_cast<const unsigned char*>(wimg), pooled);
+  if (x3)
+    gn::block_pair_pipe_kernel<true><<<grid, gn::BP_THREADS, gn::BP_SMEM, (cudaStream_t)stream>>>(
+        pw, static_cast<const float*>(feats_hl), static_cast<const float*>(nfeats_hl), pair_c, pair_n,
+        num_pairs, capacity, b1, b2, static_cast<const unsigned char*>(wimg), pooled);
+  else
+    gn::block_pair_pipe_kernel<false><<<grid, gn::BP_THREADS, gn::BP_SMEM, (cudaStream_t)stream>>>(
+        pw, static_cast<const float*>(feats_hl), static_cast<const float*>(nfeats_hl), pair_c, pair_n,
+        num_pairs, capacity, b1, b2, static_cast<const unsigned char*>(wimg), pooled);
   GN_CHECK_LAUNCH(name);
   return GN_OK;
+}
+
+extern "C" int gn_block_pair_fwd_pipe(const float* pw, int w, const void* feats_hl,
+                                      const void* nfeats_hl, int r, const int32_t* pair_c,
+                                      const int32_t* pair_n, const int32_t* num_pairs,
+                                      int capacity, const float* b1, const float* b2,
+                                      const void* wimg, int f, float* pooled, gn_stream_t stream) {
+  return launch_pair_pipe("gn_block_pair_fwd_pipe", true, pw, w, feats_hl, nfeats_hl, r, pair_c,
+                          pair_n, num_pairs, capacity, b1, b2, wimg, f, pooled, stream);
+}
+
+extern "C" int gn_block_pair_fwd_pipe_bf16(const float* pw, int w, const void* feats_hl,
+                                           const void* nfeats_hl, int r, const int32_t* pair_c,
+                                           const int32_t* pair_n, const int32_t* num_pairs,
+                                           int capacity, const float* b1, const float* b2,
+                                           const void* wimg, int f, float* pooled,
+                                           gn_stream_t stream) {
+  return launch_pair_pipe("gn_block_pair_fwd_pipe_bf16", false, pw, w, feats_hl, nfeats_hl, r,
+                          pair_c, pair_n, num_pairs, capacity, b1, b2, wimg, f, pooled, stream);
 }

@@ -109,16 +109,23 @@ __device__ __forceinline__ void dt_load_tile(const float* __restrict__ src, int 
 }
 
 // bf16x3 GEMM: D[tmem] = A[128 x K] (smem) * B[N x K]^T (smem); issued by one thread
-template <int KSTEPS>
+// X3 = false: plain bf16 operands (hi parts only), one UMMA per k-step
+template <int KSTEPS, bool X3>
 __device__ __forceinline__ void dt_gemm(uint32_t tmem_d, uint64_t d_ah, uint64_t d_al,
                                         uint64_t d_bh, uint64_t d_bl, uint32_t lbo_b,
                                         uint32_t idesc) {
 #pragma unroll
-  for (int ks = 0; ks < KSTEPS; ++ks)
-    umma::mma_bf16x3(tmem_d, d_ah, d_al, d_bh, d_bl, ks * (2 * DT_LBO_A >> 4),
-                     ks * (2 * lbo_b >> 4), idesc, ks > 0);
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+    if (X3)
+      umma::mma_bf16x3(tmem_d, d_ah, d_al, d_bh, d_bl, ks * (2 * DT_LBO_A >> 4),
+                       ks * (2 * lbo_b >> 4), idesc, ks > 0);
+    else
+      umma::mma_bf16_ss(tmem_d, d_ah + ks * (2 * DT_LBO_A >> 4), d_bh + ks * (2 * lbo_b >> 4), idesc,
+                        ks > 0);
+  }
 }
 
+template <bool X3>
 __global__ void __launch_bounds__(DT_THREADS, 1)
 block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_in,
                     const float* __restrict__ w_fc1, const float* __restrict__ b_fc1,
@@ -211,7 +218,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       __syncthreads();
       if (t == 0) {
         umma::tc_fence_after();
-        dt_gemm<DT_F / 16>(tm1, d_ah, d_al, d_w1h, d_w1l, DT_F * 16, umma::idesc_bf16_f32(DT_TILE, DT_F));
+        dt_gemm<DT_F / 16, X3>(tm1, d_ah, d_al, d_w1h, d_w1l, DT_F * 16, umma::idesc_bf16_f32(DT_TILE, DT_F));
         umma::mma_commit(bar);
       }
       umma::mbar_wait(bar, par);
@@ -244,7 +251,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       __syncthreads();
       if (t == 0) {
         umma::tc_fence_after();
-        dt_gemm<DT_F / 16>(tm2, d_ah, d_al, d_w2h, d_w2l, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
+        dt_gemm<DT_F / 16, X3>(tm2, d_ah, d_al, d_w2h, d_w2l, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
         umma::mma_commit(bar);
       }
       // the shortcut tile (feats_in rows) is fetched while the fc2 UMMAs run: every warp
@@ -329,7 +336,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       __syncthreads();
       if (t == 0) {
         umma::tc_fence_after();
-        dt_gemm<DT_D / 16>(tmr, d_ah, d_al, d_wrh, d_wrl, DT_R * 16, umma::idesc_bf16_f32(DT_TILE, DT_R));
+        dt_gemm<DT_D / 16, X3>(tmr, d_ah, d_al, d_wrh, d_wrl, DT_R * 16, umma::idesc_bf16_f32(DT_TILE, DT_R));
         umma::mma_commit(bar);
       }
       if (stage_a) store_feats_tile();      // while the reduce_dim UMMAs run
@@ -389,7 +396,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
         __syncthreads();
         if (t == 0) {
           umma::tc_fence_after();
-          dt_gemm<DT_R / 16>(tm2, d_ah, d_al, d_wabh, d_wabl, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
+          dt_gemm<DT_R / 16, X3>(tm2, d_ah, d_al, d_wabh, d_wabl, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
           umma::mma_commit(bar);
         }
         umma::mbar_wait(bar, par);
@@ -426,7 +433,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
 
 }  // namespace gn
 
-static int launch_block_det(const char* name, float* pooled, const float* feats_in,
+static int launch_block_det(const char* name, bool x3, float* pooled, const float* feats_in,
                             const float* w_fc1, const float* b_fc1, const float* w_fc2,
                             const float* b_fc2, const float* w_rd, const float* b_rd,
                             const void* wimg, int has_a, int has_b, float* feats_out,
@@ -452,8 +459,10 @@ static int launch_block_det(const char* name, float* pooled, const float* feats_
   GN_REQUIRE((((uintptr_t)pooled | (uintptr_t)feats_in | (uintptr_t)feats_out |
                (uintptr_t)red_f32 | (uintptr_t)red_hl | (uintptr_t)wimg) & 15) == 0,
              "%s: pointers must be 16-byte aligned", name);
-  cudaError_t e = cudaFuncSetAttribute(gn::block_det_tc_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn::DT_SMEM);
+  const void* kern = x3 ? (const void*)gn::block_det_tc_kernel<true>
+                        : (const void*)gn::block_det_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)gn::DT_SMEM);
   if (e != cudaSuccess) {
     gn::set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
     return GN_ERR_CUDA;
@@ -461,10 +470,16 @@ static int launch_block_det(const char* name, float* pooled, const float* feats_
   int grid = gn::ceil_div(num_dets, gn::DT_TILE);
   const int sms = gn::sm_count();
   if (grid > sms) grid = sms;
-  gn::block_det_tc_kernel<<<grid, gn::DT_THREADS, gn::DT_SMEM, (cudaStream_t)stream>>>(
-      pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd,
-      static_cast<const unsigned char*>(wimg), feats_out, red_f32,
-      static_cast<__nv_bfloat16*>(red_hl), b_ab, ab_out, num_dets, has_a, has_b);
+  if (x3)
+    gn::block_det_tc_kernel<true><<<grid, gn::DT_THREADS, gn::DT_SMEM, (cudaStream_t)stream>>>(
+        pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd,
+        static_cast<const unsigned char*>(wimg), feats_out, red_f32,
+        static_cast<__nv_bfloat16*>(red_hl), b_ab, ab_out, num_dets, has_a, has_b);
+  else
+    gn::block_det_tc_kernel<false><<<grid, gn::DT_THREADS, gn::DT_SMEM, (cudaStream_t)stream>>>(
+        pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd,
+        static_cast<const unsigned char*>(wimg), feats_out, red_f32,
+        static_cast<__nv_bfloat16*>(red_hl), b_ab, ab_out, num_dets, has_a, has_b);
   GN_CHECK_LAUNCH(name);
   return GN_OK;
 }
@@ -474,7 +489,7 @@ extern "C" int gn_block_det_fwd(float* pooled, const float* feats_in, const floa
                                 const float* w_rd, const float* b_rd, float* feats_out,
                                 float* red_f32, void* red_hl, int num_dets, int shortcut_dim,
                                 int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
-  return launch_block_det("gn_block_det_fwd", pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd,
+  return launch_block_det("gn_block_det_fwd", true, pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd,
                           b_rd, nullptr, pooled != nullptr, w_rd != nullptr, feats_out, red_f32,
                           red_hl, nullptr, nullptr, num_dets, shortcut_dim, pairfeat_dim,
                           reduced_dim, stream);
@@ -487,9 +502,23 @@ extern "C" int gn_block_det_fwd_img(float* pooled, const float* feats_in, const 
                                     float* ab_out, int num_dets, int shortcut_dim,
                                     int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
   GN_REQUIRE(wimg != nullptr, "gn_block_det_fwd_img: null weight image");
-  return launch_block_det("gn_block_det_fwd_img", pooled, feats_in, nullptr, b_fc1, nullptr, b_fc2,
-                          nullptr, b_rd, wimg, has_stage_a, has_stage_b, feats_out, red_f32, red_hl,
-                          b_ab, ab_out, num_dets, shortcut_dim, pairfeat_dim, reduced_dim, stream);
+  return launch_block_det("gn_block_det_fwd_img", true, pooled, feats_in, nullptr, b_fc1, nullptr,
+                          b_fc2, nullptr, b_rd, wimg, has_stage_a, has_stage_b, feats_out, red_f32,
+                          red_hl, b_ab, ab_out, num_dets, shortcut_dim, pairfeat_dim, reduced_dim,
+                          stream);
+}
+
+extern "C" int gn_block_det_fwd_img_bf16(float* pooled, const float* feats_in, const void* wimg,
+                                         const float* b_fc1, const float* b_fc2, const float* b_rd,
+                                         int has_stage_a, int has_stage_b, float* feats_out,
+                                         float* red_f32, void* red_hl, const float* b_ab,
+                                         float* ab_out, int num_dets, int shortcut_dim,
+                                         int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
+  GN_REQUIRE(wimg != nullptr, "gn_block_det_fwd_img_bf16: null weight image");
+  return launch_block_det("gn_block_det_fwd_img_bf16", false, pooled, feats_in, nullptr, b_fc1,
+                          nullptr, b_fc2, nullptr, b_rd, wimg, has_stage_a, has_stage_b, feats_out,
+                          red_f32, red_hl, b_ab, ab_out, num_dets, shortcut_dim, pairfeat_dim,
+                          reduced_dim, stream);
 }
 
 extern "C" int64_t gn_block_det_image_bytes(void) { return (int64_t)gn::DT_OFF_A; }

@@ -147,7 +147,9 @@ __device__ long long pp_trace[64];
 #define PP_TR(i) do { } while (0)
 #endif
 
-template <bool MULTI>
+// X3: bf16x3 products (fp32 semantics); !X3: plain bf16 operands, a third of the UMMAs and
+// half of the W2 stream (BASELINE configs[2] arithmetic).
+template <bool MULTI, bool X3>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ scores,
                    const int32_t* __restrict__ classes, const int32_t* __restrict__ pair_c,
@@ -234,7 +236,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       umma::tc_fence_after();
       const uint32_t dst = tm_h + b * 64 + tlane + (uint32_t)cg * 8;
       umma::tmem_st8(dst, hh);
-      umma::tmem_st8(dst + 32, hl);
+      if (X3) umma::tmem_st8(dst + 32, hl);
       umma::tmem_st_wait();
       umma::tc_fence_before();
       __syncwarp();
@@ -342,8 +344,12 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       auto issue_l1 = [&](int ab, int q) {
         const uint64_t d_ah = umma::smem_desc(s_a1 + (uint32_t)ab * (4 * PT_LBO_A), PT_LBO_A, PT_SBO);
         const uint64_t d_al = umma::smem_desc(s_a1 + (uint32_t)ab * (4 * PT_LBO_A) + 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
-        umma::mma_bf16x3(tm_l1 + (uint32_t)(q & 1) * 64, d_ah, d_al, d_b1h, d_b1l, 0,
-                         (uint32_t)q * (PP_Q * 16 >> 4), idesc64, 0);
+        if (X3)
+          umma::mma_bf16x3(tm_l1 + (uint32_t)(q & 1) * 64, d_ah, d_al, d_b1h, d_b1l, 0,
+                           (uint32_t)q * (PP_Q * 16 >> 4), idesc64, 0);
+        else
+          umma::mma_bf16_ss(tm_l1 + (uint32_t)(q & 1) * 64, d_ah,
+                            d_b1h + (uint32_t)q * (PP_Q * 16 >> 4), idesc64, 0);
         umma::mma_commit(&l1_done[q & 1]);
       };
       umma::mbar_wait(&a1_full[0], 0);
@@ -371,9 +377,13 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
             umma::tc_fence_after();
             const uint32_t boff = s * (PT_STAGE >> 4);
             const uint32_t acc = (q | ksl) != 0;
-            umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_ringh + boff, idesc256, acc);
-            umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringl + boff, idesc256, 1);
-            umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringh + boff, idesc256, 1);
+            if (X3) {
+              umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_ringh + boff, idesc256, acc);
+              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringl + boff, idesc256, 1);
+              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringh + boff, idesc256, 1);
+            } else {
+              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringh + boff, idesc256, acc);
+            }
             umma::mma_commit(&empty[s]);
           }
           umma::mma_commit(&h_empty[hb]);
@@ -397,9 +407,13 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
           for (int ksl = 0; ksl < 4; ++ksl) {
             const uint32_t boff = (uint32_t)((q * 4 + ksl) * 2) * (PT_LBO_W3 >> 4);
             const uint32_t acc = (q | ksl) != 0;
-            umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_b3h + boff, idesc32, acc);
-            umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3l + boff, idesc32, 1);
-            umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3h + boff, idesc32, 1);
+            if (X3) {
+              umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_b3h + boff, idesc32, acc);
+              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3l + boff, idesc32, 1);
+              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3h + boff, idesc32, 1);
+            } else {
+              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3h + boff, idesc32, acc);
+            }
           }
           umma::mma_commit(&h_empty[hb]);
           ++cons;
@@ -427,7 +441,9 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       for (uint32_t i = 0; i < total; ++i) {
         const uint32_t s = i % PP_RING;
         if (i >= PP_RING) umma::mbar_wait_relaxed(&empty[s], ((i / PP_RING) - 1) & 1u);
-        bulk_g2s(s_ring + s * PT_STAGE, img + PT_IMG_W2 + (size_t)((blockIdx.x % PT_W2_COPIES) * 16 + (i & 15u)) * PT_STAGE, PT_STAGE, &full[s]);
+        // a stage image is [hi: 2 chunks | lo: 2 chunks]; plain bf16 streams the hi half only
+        bulk_g2s(s_ring + s * PT_STAGE, img + PT_IMG_W2 + (size_t)((blockIdx.x % PT_W2_COPIES) * 16 + (i & 15u)) * PT_STAGE,
+                 X3 ? PT_STAGE : PT_STAGE / 2, &full[s]);
       }
     }
   } else {
@@ -512,7 +528,7 @@ extern "C" int gn_pwfeat_trace(long long* host_out) {
 
 extern "C" int64_t gn_pwfeat_prep_bytes(void) { return (int64_t)gn::PT_IMG_BYTES; }
 
-extern "C" int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const int32_t* classes,
+static int launch_pwfeat(bool x3, const float* dets, const float* scores, const int32_t* classes,
                                  const int32_t* pair_c, const int32_t* pair_n,
                                  const float* pair_iou, const int32_t* num_pairs, int capacity,
                                  int num_classes, float multiplier, const float* w1,
@@ -540,25 +556,50 @@ extern "C" int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const i
   const int sms = gn::sm_count();
   if (grid > sms) grid = sms;
   cudaError_t e;
+#define GN_PWFEAT_LAUNCH(MULTI_, X3_)                                                          \
+  do {                                                                                         \
+    e = cudaFuncSetAttribute(gn::pwfeat_pipe_kernel<MULTI_, X3_>,                              \
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gn::PQ_BYTES);  \
+    if (e == cudaSuccess)                                                                      \
+      gn::pwfeat_pipe_kernel<MULTI_, X3_><<<grid, gn::PP_THREADS, gn::PQ_BYTES, s>>>(          \
+          dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,   \
+          multiplier, w1, b1, b2, b3, img, pw_out);                                            \
+  } while (0)
   if (num_classes > 1) {
-    e = cudaFuncSetAttribute(gn::pwfeat_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)gn::PQ_BYTES);
-    if (e == cudaSuccess)
-      gn::pwfeat_pipe_kernel<true><<<grid, gn::PP_THREADS, gn::PQ_BYTES, s>>>(
-          dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,
-          multiplier, w1, b1, b2, b3, img, pw_out);
+    if (x3) GN_PWFEAT_LAUNCH(true, true); else GN_PWFEAT_LAUNCH(true, false);
   } else {
-    e = cudaFuncSetAttribute(gn::pwfeat_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)gn::PQ_BYTES);
-    if (e == cudaSuccess)
-      gn::pwfeat_pipe_kernel<false><<<grid, gn::PP_THREADS, gn::PQ_BYTES, s>>>(
-          dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,
-          multiplier, w1, b1, b2, b3, img, pw_out);
+    if (x3) GN_PWFEAT_LAUNCH(false, true); else GN_PWFEAT_LAUNCH(false, false);
   }
+#undef GN_PWFEAT_LAUNCH
   if (e != cudaSuccess) {
     gn::set_error("gn_pwfeat_mlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return GN_ERR_CUDA;
   }
   GN_CHECK_LAUNCH("gn_pwfeat_mlp_fwd");
   return GN_OK;
+}
+
+extern "C" int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const int32_t* classes,
+                                 const int32_t* pair_c, const int32_t* pair_n,
+                                 const float* pair_iou, const int32_t* num_pairs, int capacity,
+                                 int num_classes, float multiplier, const float* w1,
+                                 const float* b1, const float* w2, const float* b2,
+                                 const float* w3, const float* b3, int hidden, int out_dim,
+                                 void* wprep, float* pw_out, gn_stream_t stream) {
+  return launch_pwfeat(true, dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
+                       num_classes, multiplier, w1, b1, w2, b2, w3, b3, hidden, out_dim, wprep,
+                       pw_out, stream);
+}
+
+extern "C" int gn_pwfeat_mlp_fwd_bf16(const float* dets, const float* scores,
+                                      const int32_t* classes, const int32_t* pair_c,
+                                      const int32_t* pair_n, const float* pair_iou,
+                                      const int32_t* num_pairs, int capacity, int num_classes,
+                                      float multiplier, const float* w1, const float* b1,
+                                      const float* w2, const float* b2, const float* w3,
+                                      const float* b3, int hidden, int out_dim, void* wprep,
+                                      float* pw_out, gn_stream_t stream) {
+  return launch_pwfeat(false, dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
+                       num_classes, multiplier, w1, b1, w2, b2, w3, b3, hidden, out_dim, wprep,
+                       pw_out, stream);
 }

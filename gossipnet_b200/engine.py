@@ -47,6 +47,9 @@ class GnetEngine(object):
             'neighbor_feats', 'num_pwfeat_fc', 'pwfeat_dim', 'pwfeat_narrow_dim',
             'pw_feat_multiplyer'))
         # image-feature head (network.py:223-240): ROI-pooled crops of a feature map
+        if g.compute_dtype not in ('fp32', 'bf16'):
+            raise ValueError('cfg.gnet.compute_dtype must be fp32 or bf16, got %r' % (g.compute_dtype,))
+        self.bf16 = g.compute_dtype == 'bf16'
         self.imfeats = bool(g.imfeats)
         self.imfeat_dim = int(g.imfeat_dim)
         self.crop = (int(cfg.imfeat_crop_height), int(cfg.imfeat_crop_width))
@@ -177,7 +180,8 @@ class GnetEngine(object):
                                                 dtype=torch.uint8, device=self.device)
             return ops.pwfeat_mlp_fwd(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
                                       self.num_classes, mult, *w, out=out,
-                                      ffma=not self.use_tensor_cores, wprep=self._ws['wprep'])
+                                      ffma=not self.use_tensor_cores, wprep=self._ws['wprep'],
+                                      bf16=self.bf16)
         raw = self._buf('pw_raw', (cap, self.raw_width))
         ops.pair_geometry(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
                           self.num_classes, mult, raw)
@@ -284,6 +288,8 @@ class GnetEngine(object):
         operand images prepared by one launch per forward."""
         g, p = self.g, self.p
         T, d = feats.shape
+        if self.bf16 and self.pair_mode != 'pipe':
+            raise ValueError("cfg.gnet.compute_dtype = 'bf16' needs pair_mode 'pipe'")
         ab_mode = self.pair_mode == 'ab'
         pooled = self._buf('pooled', (T, g['pairfeat_dim']))
         pooled.zero_()   # every det launch re-zeroes it; this covers a dirty workspace
@@ -306,7 +312,7 @@ class GnetEngine(object):
                 None if last else p[nxt + 'reduce_dim/biases'], feats_out=out,
                 red_hl=None if (last or ab_mode) else inter,
                 b_ab=p[nxt + 'pw_fc1/biases'] if (ab_mode and not last) else None,
-                ab_out=inter if (ab_mode and not last) else None)
+                ab_out=inter if (ab_mode and not last) else None, bf16=self.bf16)
 
         det(0, None, feats, None)
         for b in range(1, nb + 1):
@@ -317,7 +323,8 @@ class GnetEngine(object):
                                       p[s + 'pw_fc2/biases'], wimg, pooled)
             elif self.pair_mode == 'pipe':
                 ops.block_pair_fwd_pipe(pw, inter, pair_c, pair_n, num_pairs, cap,
-                                        p[s + 'pw_fc1/biases'], p[s + 'pw_fc2/biases'], wimg, pooled)
+                                        p[s + 'pw_fc1/biases'], p[s + 'pw_fc2/biases'], wimg, pooled,
+                                        bf16=self.bf16)
             else:
                 ops.block_pair_fwd(pw, inter, inter, pair_c, pair_n, num_pairs, cap,
                                    None, p[s + 'pw_fc1/biases'], None, p[s + 'pw_fc2/biases'],

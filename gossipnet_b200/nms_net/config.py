@@ -106,6 +106,10 @@ _DEFAULTS = {
         # channels of the feature map fed as `imfeats` (ResNet-101 block3/unit_22 = 1024);
         # not a reference key: there the width comes from the ResNet graph itself
         'imfeat_channels': 1024,
+        # arithmetic of the fused tensor-core kernels (not a reference key): 'fp32' = fp32
+        # semantics via bf16x3 products; 'bf16' = plain bf16 operands, fp32 accumulation
+        # (BASELINE configs[2]); inference only
+        'compute_dtype': 'fp32',
         'neighbor_feats': False,
         'num_pwfeat_fc': 0,
         'pwfeat_dim': 256,

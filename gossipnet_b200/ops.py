@@ -123,7 +123,7 @@ _PREP = {}
 
 def pwfeat_mlp_fwd(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
                    num_classes, multiplier, w1, b1, w2, b2, w3, b3, out=None, ffma=False,
-                   wprep=None):
+                   wprep=None, bf16=False):
     """Fused geometry + 3-layer pair-feature MLP.  Tensor-core kernel by default
     (needs the `wprep` weight-image workspace; one per device is kept here when
     the caller does not pass its own); ffma=True runs the fp32 CUDA-core variant."""
@@ -147,7 +147,7 @@ def pwfeat_mlp_fwd(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, c
             _PREP[key] = torch.empty(int(_lib.load().gn_pwfeat_prep_bytes()), dtype=torch.uint8,
                                      device=dets.device)
         wprep = _PREP[key]
-    _lib.call('gn_pwfeat_mlp_fwd', *(args + [_chk(wprep, torch.uint8, 'wprep'),
+    _lib.call('gn_pwfeat_mlp_fwd_bf16' if bf16 else 'gn_pwfeat_mlp_fwd', *(args + [_chk(wprep, torch.uint8, 'wprep'),
                                              _chk(out, f32, 'pw_out'), _stream()]))
     return out
 
@@ -246,13 +246,14 @@ def prepare_operands(flat_params, table, image):
 
 
 def block_det_fwd_img(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out=None, red_f32=None,
-                      red_hl=None, b_ab=None, ab_out=None):
+                      red_hl=None, b_ab=None, ab_out=None, bf16=False):
     """gn_block_det_fwd with weights from a prepared operand image; a stage runs when
     its bias is given (b_fc1 & b_fc2 -> stage A, b_rd -> stage B); ab_out (+ b_ab)
     additionally requests the per-detection halves of the next pair FC."""
     f32 = torch.float32
     T, d = feats_in.shape
-    _lib.call('gn_block_det_fwd_img', _chk(pooled, f32, 'pooled', True),
+    _lib.call('gn_block_det_fwd_img_bf16' if bf16 else 'gn_block_det_fwd_img',
+              _chk(pooled, f32, 'pooled', True),
               _chk(feats_in, f32, 'feats_in'), _chk(wimg, torch.uint8, 'wimg'),
               _chk(b_fc1, f32, 'b_fc1', True), _chk(b_fc2, f32, 'b_fc2', True),
               _chk(b_rd, f32, 'b_rd', True), 1 if b_fc1 is not None else 0,
@@ -278,11 +279,13 @@ def rowdot_fwd(x, w, b, out):
     return out
 
 
-def block_pair_fwd_pipe(pw, feats_hl, pair_c, pair_n, num_pairs, capacity, b1, b2, wimg, pooled):
+def block_pair_fwd_pipe(pw, feats_hl, pair_c, pair_n, num_pairs, capacity, b1, b2, wimg, pooled,
+                        bf16=False):
     """Pipelined pair stage (see gn_block_pair_fwd_pipe): bf16 (hi | lo) reduced-feature
     rows [num_dets, 2r], prepared weight image; pooled must be zero-filled."""
     f32 = torch.float32
-    _lib.call('gn_block_pair_fwd_pipe', _chk(pw, f32, 'pw'), pw.shape[1],
+    _lib.call('gn_block_pair_fwd_pipe_bf16' if bf16 else 'gn_block_pair_fwd_pipe',
+              _chk(pw, f32, 'pw'), pw.shape[1],
               _chk(feats_hl, torch.bfloat16, 'feats_hl'), _chk(feats_hl, torch.bfloat16, 'nfeats_hl'),
               feats_hl.shape[1] // 2, _chk(pair_c, torch.int32, 'pair_c'),
               _chk(pair_n, torch.int32, 'pair_n'), _chk(num_pairs, torch.int32, 'num_pairs'),

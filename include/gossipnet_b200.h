@@ -181,6 +181,29 @@ int gn_block_pair_fwd_hl(const float* pw, int w, const void* feats_hl,
                          const float* w1, const float* b1, const float* w2,
                          const float* b2, const void* wimg, int f, float* pooled,
                          gn_stream_t stream);
+/* Plain-bf16 arithmetic (BASELINE configs[2] names bf16): the same three fused tensor-core
+ * kernels with bf16 operands (the hi parts of the operand images / activations only) and fp32
+ * accumulation - one UMMA per k-step instead of three, half of the W2 stream.  Same
+ * arguments as gn_pwfeat_mlp_fwd / gn_block_pair_fwd_pipe / gn_block_det_fwd_img.  Logits
+ * agree with the fp32 path to ~1e-2 relative (tests state the tolerance); index outputs
+ * (neighbor lists) do not depend on the mode. */
+int gn_pwfeat_mlp_fwd_bf16(const float* dets, const float* scores, const int32_t* classes,
+                           const int32_t* pair_c, const int32_t* pair_n, const float* pair_iou,
+                           const int32_t* num_pairs, int capacity, int num_classes,
+                           float multiplier, const float* w1, const float* b1, const float* w2,
+                           const float* b2, const float* w3, const float* b3, int hidden,
+                           int out_dim, void* wprep, float* pw_out, gn_stream_t stream);
+int gn_block_pair_fwd_pipe_bf16(const float* pw, int w, const void* feats_hl,
+                                const void* nfeats_hl, int r, const int32_t* pair_c,
+                                const int32_t* pair_n, const int32_t* num_pairs, int capacity,
+                                const float* b1, const float* b2, const void* wimg, int f,
+                                float* pooled, gn_stream_t stream);
+int gn_block_det_fwd_img_bf16(float* pooled, const float* feats_in, const void* wimg,
+                              const float* b_fc1, const float* b_fc2, const float* b_rd,
+                              int has_stage_a, int has_stage_b, float* feats_out, float* red_f32,
+                              void* red_hl, const float* b_ab, float* ab_out, int num_dets,
+                              int shortcut_dim, int pairfeat_dim, int reduced_dim,
+                              gn_stream_t stream);
 /* Predict head (A8, network.py:257-273): its hidden layers have activation_fn=None, so the
  * chain collapses to one affine map.  gn_predict_collapse folds the n_layers FCs described by
  * table (n_layers x 4 int32: weight offset, bias offset, in, out into flat_params; last out

@@ -166,3 +166,29 @@ def test_collapsed_predict_head_matches_staged_layers():
     net.engine.collapse_predict = False
     staged = net(img).cpu().numpy()
     assert rel_err(folded, staged) < 5e-6
+
+
+@pytest.mark.parametrize('n,blocks,exp,C', [(1000, 16, 'coco_person', 1),
+                                            (2000, 16, 'coco_multiclass', 80)])   # configs[2] as named
+def test_bf16_arithmetic_mode(n, blocks, exp, C, oracle_built):
+    """cfg.gnet.compute_dtype = 'bf16' (BASELINE configs[2]: "bf16"): plain bf16 operands with
+    fp32 accumulation in the three fused tensor-core kernels.  Index outputs do not depend on
+    the mode (bit-exact); logits agree with the fp32 oracle to the stated bf16 tolerance."""
+    BF16_TOL = 3e-2      # max|d| / max|ref| after 16 blocks of bf16-operand GEMMs
+    load_experiment(exp, num_blocks=blocks)
+    cfg.gnet.compute_dtype = 'bf16'
+    layout, total = P.param_layout(C, cfg)
+    flat = P.init_flat(layout, total, cfg, seed=11)
+    img = synthetic.make_image(n, C, image_index=0)
+    test_img = {k: img[k] for k in ('dets', 'det_scores', 'det_classes')}
+    ref = gnet_oracle.gnet_forward(test_img, P.views(layout, flat), cfg, C)
+    net = Gnet(C, params=flat)
+    assert net.engine.bf16
+    pred = net(test_img).cpu().numpy()
+    assert np.array_equal(net.neighbor_pair_idxs.cpu().numpy(), ref['neighbor_pair_idxs'])
+    err = rel_err(pred, ref['prediction'])
+    assert 1e-6 < err < BF16_TOL, err        # really the reduced-precision path, and close
+    # the same network in the default mode is 100x closer
+    cfg.gnet.compute_dtype = 'fp32'
+    net32 = Gnet(C, params=flat)
+    assert rel_err(net32(test_img).cpu().numpy(), ref['prediction']) < LOGIT_TOL
