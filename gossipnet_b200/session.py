@@ -32,16 +32,26 @@ class InferenceSession(object):
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self, T, B):
+        """One pinned staging buffer and one device buffer hold all four inputs (typed views at
+        256-byte aligned offsets), so a step's inputs travel in ONE host->device copy."""
         dev = self.device
-        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True)
-        self.h_dets, self.d_dets = pin((T, 4), torch.float32), torch.empty((T, 4), device=dev)
-        self.h_scores, self.d_scores = pin((T,), torch.float32), torch.empty(T, device=dev)
-        self.h_cls = pin((T,), torch.int32)
-        self.d_cls = torch.empty(T, dtype=torch.int32, device=dev)
-        self.h_off = pin((B + 1,), torch.int32)
-        self.d_off = torch.empty(B + 1, dtype=torch.int32, device=dev)
-        self.h_pred = pin((T,), torch.float32)
-        self.h_np = pin((1,), torch.int32)
+        sizes = [('dets', T * 16), ('scores', T * 4), ('cls', T * 4), ('off', (B + 1) * 4)]
+        offs, total = {}, 0
+        for name, nbytes in sizes:
+            offs[name] = total
+            total += (nbytes + 255) // 256 * 256
+        self.h_in = torch.empty(max(total, 256), dtype=torch.uint8, pin_memory=True)
+        self.d_in = torch.empty(max(total, 256), dtype=torch.uint8, device=dev)
+
+        def view(buf, name, nbytes, dtype, shape):
+            return buf[offs[name]:offs[name] + nbytes].view(dtype).view(*shape)
+        for buf, pre in ((self.h_in, 'h_'), (self.d_in, 'd_')):
+            setattr(self, pre + 'dets', view(buf, 'dets', T * 16, torch.float32, (T, 4)))
+            setattr(self, pre + 'scores', view(buf, 'scores', T * 4, torch.float32, (T,)))
+            setattr(self, pre + 'cls', view(buf, 'cls', T * 4, torch.int32, (T,)))
+            setattr(self, pre + 'off', view(buf, 'off', (B + 1) * 4, torch.int32, (B + 1,)))
+        self.h_pred = torch.empty((T,), dtype=torch.float32, pin_memory=True)
+        self.h_np = torch.empty((1,), dtype=torch.int32, pin_memory=True)
         self.h2d_bytes = T * (16 + 4 + 4) + (B + 1) * 4
         self.d2h_bytes = T * 4 + 4
         self._shape = (T, B)
@@ -93,10 +103,7 @@ class InferenceSession(object):
         self.h_off.numpy()[...] = img_off
         for attempt in range(3):
             with torch.cuda.stream(self.stream):
-                self.d_dets.copy_(self.h_dets, non_blocking=True)
-                self.d_scores.copy_(self.h_scores, non_blocking=True)
-                self.d_cls.copy_(self.h_cls, non_blocking=True)
-                self.d_off.copy_(self.h_off, non_blocking=True)
+                self.d_in.copy_(self.h_in, non_blocking=True)
                 if self._graph is None:
                     self._prepare()
                 if self._graph:
