@@ -1,5 +1,5 @@
-"""Times gn_pwfeat_mlp_fwd on the bench workload: pipelined kernel vs the
-unpipelined one (GN_PWFEAT_V1=1), and checks they agree."""
+"""Times gn_pwfeat_mlp_fwd (fp32 semantics and plain bf16) on the bench workload and checks
+it against the staged CUDA pieces (pair_geometry + 3 x fc_fwd)."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -12,13 +12,14 @@ net = Gnet(1)
 eng = net.engine
 d = lambda a: torch.from_numpy(a).cuda()
 dd, ds, dc, do = d(dets), d(scores), d(classes), d(img_off)
-row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dd, do)
-eng.capacity = 0
-row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dd, do)
+eng.neighbors(dd, do, 1000)
+row_ptr, num_pairs, pair_c, pair_n, pair_iou, cap = eng.neighbors(dd, do, 1000)
 P = int(num_pairs.item())
-outs = {}
-for v1 in ('1', '0'):
-    os.environ['GN_PWFEAT_V1'] = v1
+eng.use_fused = False
+ref = eng.pair_features(dd, ds, dc, pair_c, pair_n, pair_iou, num_pairs, cap)[:P].clone()
+eng.use_fused = True
+for bf16 in (False, True):
+    eng.bf16 = bf16
     times = []
     for rep in range(6):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -26,6 +27,6 @@ for v1 in ('1', '0'):
         pw = eng.pair_features(dd, ds, dc, pair_c, pair_n, pair_iou, num_pairs, cap)
         b.record(); torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
-    outs[v1] = pw[:P].clone()
-    print('GN_PWFEAT_V1=%s: %.1f us (P=%d)' % (v1, 1e3 * float(np.median(times[2:])), P))
-print('max |v2 - v1| =', float((outs['0'] - outs['1']).abs().max()), ' max |v1| =', float(outs['1'].abs().max()))
+    err = float((pw[:P] - ref).abs().max() / ref.abs().max())
+    print('%s: %.1f us (P=%d)  max rel err vs staged fp32 FCs %.2e' % (
+        'bf16 ' if bf16 else 'fp32 ', 1e3 * float(np.median(times[2:])), P, err))
