@@ -27,6 +27,7 @@ class InferenceSession(object):
         self._shape = None
         self._max_img = 0
         self._graph = None
+        self._graph_io = None
         self.stream = torch.cuda.Stream(device=self.device)
         self.launches_per_forward = None
 
@@ -82,8 +83,18 @@ class InferenceSession(object):
                 with torch.cuda.graph(g, stream=self.stream):
                     self._forward()
                 self._graph = g
+                # the whole host-buffer step as one graph: H2D of the staging buffer, the
+                # forward, D2H of the logits and of the pair count (one launch per run())
+                gio = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gio, stream=self.stream):
+                    self.d_in.copy_(self.h_in, non_blocking=True)
+                    self._forward()
+                    self.h_pred.copy_(self._pred, non_blocking=True)
+                    self.h_np.copy_(self._num_pairs, non_blocking=True)
+                self._graph_io = gio
             else:
                 self._graph = False
+                self._graph_io = None
 
     # ---------------------------------------------------------------------- run
     def run(self, dets, det_scores, det_classes, img_off):
@@ -103,15 +114,16 @@ class InferenceSession(object):
         self.h_off.numpy()[...] = img_off
         for attempt in range(3):
             with torch.cuda.stream(self.stream):
-                self.d_in.copy_(self.h_in, non_blocking=True)
                 if self._graph is None:
+                    self.d_in.copy_(self.h_in, non_blocking=True)   # warm-up runs on real inputs
                     self._prepare()
                 if self._graph:
-                    self._graph.replay()
+                    self._graph_io.replay()
                 else:
+                    self.d_in.copy_(self.h_in, non_blocking=True)
                     self._forward()
-                self.h_pred.copy_(self._pred, non_blocking=True)
-                self.h_np.copy_(self._num_pairs, non_blocking=True)
+                    self.h_pred.copy_(self._pred, non_blocking=True)
+                    self.h_np.copy_(self._num_pairs, non_blocking=True)
             self.stream.synchronize()
             if int(self.h_np[0]) <= self._cap:
                 return self.h_pred.numpy()
