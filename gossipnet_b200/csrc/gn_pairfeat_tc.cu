@@ -250,6 +250,11 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       const float* row_sn = row_sc + PT_TILE;
       const int* row_rc = reinterpret_cast<const int*>(row_sn + PT_TILE);
       const int* row_rn = row_rc + PT_TILE;
+      // the score tables were written by the geometry warps before they arrived on a1_full;
+      // the epilogue otherwise only sees that through the MMA thread (a1_full -> UMMA ->
+      // commit -> l1_done), so it acquires the barrier itself (always already complete;
+      // the phase cannot advance again before this tile's tab_free arrival below)
+      if (MULTI) umma::mbar_wait(&a1_full[tb], ((uint32_t)it >> 1) & 1u);
       // ---- layer-1 quarters -> H ------------------------------------------------------
 #pragma unroll 1
       for (int q = 0; q < 4; ++q) {
