@@ -91,3 +91,29 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'import oracle' not in text and 'from oracle' not in text, f
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) must print
+    ONE JSON line with the same metric / unit / config keys as the GPU arm plus impl,
+    cpu_baseline and a zero-copy e2e object."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference',
+                          '--steps', '1', '--warmup', '1', '--n-dets', '80', '--blocks', '2'],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'detections/s' and d['higher_is_better'] is True
+    assert d['metric'].startswith('detections/sec Gnet fwd')
+    assert d['value'] > 0 and d['steps'] == 1 and d['n_gpus'] == 1
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': 'detections/s', 'h2d_bytes_per_step': 0,
+                        'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config']
