@@ -137,14 +137,53 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------ clocks
 class ClockSampler(object):
+    """SM clock + throttle reasons DURING the timed region.  NVML is polled from a thread
+    every 5 ms (a timed region of K x 6 ms is shorter than nvidia-smi's start-up, which left
+    short multi-GPU runs without a single sample); `nvidia-smi -lms` is the fallback."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
+    NAMES = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+    BITS = (0x8, 0x40, 0x20, 0x4)      # nvmlClocksEventReason{HwSlowdown,HwThermalSlowdown,SwThermalSlowdown,SwPowerCap}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = self._physical_index(index), [], None, None
+        self._stop = threading.Event()
+
+    @staticmethod
+    def _physical_index(local):
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+        parts = [p.strip() for p in vis.split(',') if p.strip()]
+        if local < len(parts) and parts[local].isdigit():
+            return int(parts[local])
+        return local
+
+    def _poll_nvml(self):
+        n, h = self.nvml
+        while not self._stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                try:
+                    reasons = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), self._max, int(reasons)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def __enter__(self):
+        try:
+            import pynvml as n
+            n.nvmlInit()
+            h = n.nvmlDeviceGetHandleByIndex(self.index)
+            self._max = float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM))
+            self.nvml = (n, h)
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
@@ -158,9 +197,17 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(',')])
+            r = [x.strip() for x in line.split(',')]
+            try:
+                bits = sum(b for b, v in zip(self.BITS, r[2:6]) if v.lower().startswith('active'))
+                self.rows.append((float(r[0]), float(r[1]), bits))
+            except Exception:
+                continue
 
     def __exit__(self, *a):
+        self._stop.set()
+        if self.nvml is not None:
+            self.thread.join(timeout=1)
         if self.proc is not None:
             self.proc.terminate()
             try:
@@ -169,21 +216,17 @@ class ClockSampler(object):
                 self.proc.kill()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(names, r[2:6]):
-                if v.lower().startswith('active'):
-                    reasons.add(name)
-        if not sm:
+        if not self.rows:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(np.max(mx)),
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        reasons = set()
+        for _, _, bits in self.rows:
+            for name, b in zip(self.NAMES, self.BITS):
+                if bits & b:
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median([r[0] for r in self.rows])),
+                'sm_max_mhz': float(np.max([r[1] for r in self.rows])),
+                'reasons': sorted(reasons), 'samples': len(self.rows),
+                'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # ------------------------------------------------------------------------- B200
