@@ -242,10 +242,11 @@ def run_b200(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at the
-        # VERSION debug level some launch environments set
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at the
+        # VERSION / WARN debug levels, and honours NCCL_DEBUG_FILE only above VERSION
         if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
             os.environ['NCCL_DEBUG'] = 'WARN'
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     cfg = setup_cfg(args.blocks, args.precision)
     bf16 = args.precision == 'bf16'
