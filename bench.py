@@ -138,7 +138,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------ clocks
 class ClockSampler(object):
     """SM clock + throttle reasons DURING the timed region.  NVML is polled from a thread
-    every 5 ms (a timed region of K x 6 ms is shorter than nvidia-smi's start-up, which left
+    every 10 ms (a timed region of K x 6 ms is shorter than nvidia-smi's start-up, which left
     short multi-GPU runs without a single sample); `nvidia-smi -lms` is the fallback."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
@@ -170,7 +170,7 @@ class ClockSampler(object):
                 self.rows.append((float(sm), self._max, int(reasons)))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.01)
 
     def __enter__(self):
         try:
@@ -284,7 +284,7 @@ def run_b200(args):
         if sess._graph:
             sess._graph.replay()
         else:
-            sess._forward()
+            sess._forward(sess._cur)
 
     # ---- value: inputs resident, device time, L2 flushed between steps ----------
     with torch.cuda.stream(stream):

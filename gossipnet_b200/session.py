@@ -1,15 +1,22 @@
 """Host-buffer inference sessions: the batched equivalent of the reference's
 test loop (test.py:63-71: feed numpy arrays -> sess.run(net.prediction) -> numpy
-scores), with the host<->device copies done from pinned staging buffers and the
-whole forward replayed as ONE CUDA graph per batch shape.
+scores), with the host<->device copies done from pinned staging buffers.
 
     sess = InferenceSession(net)
     new_scores = sess.run(dets, det_scores, det_classes, img_off)   # numpy in, numpy out
 
+A batch shape (detections, images, size of the largest image) that comes back is
+replayed as ONE CUDA graph (H2D of the staging buffer, the whole forward, D2H of
+the logits): the graph is captured the second time the shape is seen, a few
+shapes are kept.  Shapes seen once - real detection files have a different
+number of detections in almost every batch - run the same calls eagerly through
+grow-only staging buffers, so nothing is captured or allocated per call.
+
 `run` is the call bench.py times for the end-to-end number: it includes the
-host->device copy of the step's inputs and the device->host read of its
-logits.
+host->device copy of the step's inputs and the device->host read of its logits.
 """
+import collections
+
 import numpy as np
 import torch
 
@@ -17,84 +24,113 @@ from gossipnet_b200 import _lib
 from gossipnet_b200.engine import CapacityOverflow
 
 
-class InferenceSession(object):
+class _Buffers(object):
+    """Pinned + device staging for up to (T, B): one buffer holds all four inputs (typed
+    views at 256-byte aligned offsets), so a step's inputs travel in ONE host->device copy."""
 
-    def __init__(self, net, use_graph=True):
-        self.net = net
-        self.engine = net.engine
-        self.device = net.device
-        self.use_graph = use_graph
-        self._shape = None
-        self._max_img = 0
-        self._graph = None
-        self._graph_io = None
-        self.stream = torch.cuda.Stream(device=self.device)
-        self.launches_per_forward = None
-
-    # ------------------------------------------------------------------ buffers
-    def _alloc(self, T, B):
-        """One pinned staging buffer and one device buffer hold all four inputs (typed views at
-        256-byte aligned offsets), so a step's inputs travel in ONE host->device copy."""
-        dev = self.device
+    def __init__(self, T, B, device):
+        self.T_cap, self.B_cap = T, B
         sizes = [('dets', T * 16), ('scores', T * 4), ('cls', T * 4), ('off', (B + 1) * 4)]
-        offs, total = {}, 0
+        self.offs, total = {}, 0
         for name, nbytes in sizes:
-            offs[name] = total
+            self.offs[name] = total
             total += (nbytes + 255) // 256 * 256
         self.h_in = torch.empty(max(total, 256), dtype=torch.uint8, pin_memory=True)
-        self.d_in = torch.empty(max(total, 256), dtype=torch.uint8, device=dev)
+        self.d_in = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+        self.h_pred_all = torch.empty((max(T, 1),), dtype=torch.float32, pin_memory=True)
+        self.h_np = torch.empty((1,), dtype=torch.int32, pin_memory=True)
+        self.bind(T, B)
 
+    def bind(self, T, B):
+        """Typed views for a batch of T detections in B images (T <= T_cap, B <= B_cap)."""
         def view(buf, name, nbytes, dtype, shape):
-            return buf[offs[name]:offs[name] + nbytes].view(dtype).view(*shape)
+            o = self.offs[name]
+            return buf[o:o + nbytes].view(dtype).view(*shape)
         for buf, pre in ((self.h_in, 'h_'), (self.d_in, 'd_')):
             setattr(self, pre + 'dets', view(buf, 'dets', T * 16, torch.float32, (T, 4)))
             setattr(self, pre + 'scores', view(buf, 'scores', T * 4, torch.float32, (T,)))
             setattr(self, pre + 'cls', view(buf, 'cls', T * 4, torch.int32, (T,)))
             setattr(self, pre + 'off', view(buf, 'off', (B + 1) * 4, torch.int32, (B + 1,)))
-        self.h_pred = torch.empty((T,), dtype=torch.float32, pin_memory=True)
-        self.h_np = torch.empty((1,), dtype=torch.int32, pin_memory=True)
+        self.h_pred = self.h_pred_all[:T]
+        self.T, self.B = T, B
+        # bytes that matter (the aligned staging buffer carries a little padding on top)
         self.h2d_bytes = T * (16 + 4 + 4) + (B + 1) * 4
         self.d2h_bytes = T * 4 + 4
-        self._shape = (T, B)
-        self._graph = None
+        self.copy_bytes = self.offs['off'] + (B + 1) * 4
 
-    def _forward(self):
-        res = self.engine.forward(self.d_dets, self.d_scores, self.d_cls, self.d_off,
+
+class InferenceSession(object):
+    MAX_GRAPHS = 4          # captured shapes kept (least recently used goes first)
+
+    def __init__(self, net, use_graph=True, graph_after=2):
+        self.net = net
+        self.engine = net.engine
+        self.device = net.device
+        self.use_graph = use_graph
+        self.graph_after = graph_after       # capture a shape when it is seen this many times
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.launches_per_forward = None
+        self._seen = collections.Counter()
+        self._states = collections.OrderedDict()    # shape key -> (buffers, graph, graph_io)
+        self._eager = None                            # grow-only buffers of the eager path
+        self._cur = None                              # buffers of the last run
+        self._graph = None                            # forward-only graph of the last run (or None)
+        self._max_img = 0
+
+    # attribute surface bench.py and the tests read -----------------------------------
+    def __getattr__(self, name):
+        if name in ('d_dets', 'd_scores', 'd_cls', 'd_off', 'h_dets', 'h_scores', 'h_cls', 'h_off',
+                    'h_np', 'h_pred', 'h2d_bytes', 'd2h_bytes'):
+            cur = self.__dict__.get('_cur')
+            if cur is None:
+                raise AttributeError('%s: no batch has been run yet' % name)
+            return getattr(cur, name)
+        raise AttributeError(name)
+
+    # ------------------------------------------------------------------- forward
+    def _forward(self, buf):
+        res = self.engine.forward(buf.d_dets, buf.d_scores, buf.d_cls, buf.d_off,
                                   max_img=self._max_img)
         self._pred, self._num_pairs, self._cap = res['prediction'], res['num_pairs'], res['capacity']
 
-    def _prepare(self):
-        """Warm up (learns the pair capacity, sets kernel attributes) and capture."""
-        with torch.cuda.stream(self.stream):
-            for _ in range(2):
-                while True:
-                    self._forward()
-                    try:
-                        self.engine.check_overflow()
-                        break
-                    except CapacityOverflow:
-                        continue
-            n0 = _lib.CALLS[0]
-            self._forward()
-            self.launches_per_forward = _lib.CALLS[0] - n0
-            self.stream.synchronize()
-            if self.use_graph:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=self.stream):
-                    self._forward()
-                self._graph = g
-                # the whole host-buffer step as one graph: H2D of the staging buffer, the
-                # forward, D2H of the logits and of the pair count (one launch per run())
-                gio = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gio, stream=self.stream):
-                    self.d_in.copy_(self.h_in, non_blocking=True)
-                    self._forward()
-                    self.h_pred.copy_(self._pred, non_blocking=True)
-                    self.h_np.copy_(self._num_pairs, non_blocking=True)
-                self._graph_io = gio
-            else:
-                self._graph = False
-                self._graph_io = None
+    def _warm(self, buf):
+        """Forward until the pair capacity fits (the engine learns it on its first batches)."""
+        while True:
+            self._forward(buf)
+            try:
+                self.engine.check_overflow()
+                return
+            except CapacityOverflow:
+                continue
+
+    def _capture(self, buf):
+        """Warm up on the real inputs (already in buf.d_in), count launches, capture the
+        forward alone (bench's resident measurement) and the whole host-buffer step."""
+        for _ in range(2):
+            self._warm(buf)
+        n0 = _lib.CALLS[0]
+        self._forward(buf)
+        self.launches_per_forward = _lib.CALLS[0] - n0
+        self.stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream):
+            self._forward(buf)
+        gio = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gio, stream=self.stream):
+            buf.d_in[:buf.copy_bytes].copy_(buf.h_in[:buf.copy_bytes], non_blocking=True)
+            self._forward(buf)
+            buf.h_pred.copy_(self._pred, non_blocking=True)
+            buf.h_np.copy_(self._num_pairs, non_blocking=True)
+        return g, gio
+
+    def _eager_buffers(self, T, B):
+        e = self._eager
+        if e is None or T > e.T_cap or B > e.B_cap:
+            grow = lambda need, have: max(need, int(have * 1.5))
+            e = self._eager = _Buffers(grow(T, e.T_cap if e else 0), grow(B, e.B_cap if e else 0),
+                                       self.device)
+        e.bind(T, B)
+        return e
 
     # ---------------------------------------------------------------------- run
     def run(self, dets, det_scores, det_classes, img_off):
@@ -102,32 +138,58 @@ class InferenceSession(object):
         img_off[B+1] i32 -> new scores (logits) [T] f32 (a view of the pinned
         result buffer, valid until the next run)."""
         T, B = int(dets.shape[0]), int(img_off.shape[0]) - 1
-        # the captured graph is specific to (T, B) and to the mask stride of the neighbor
-        # build, i.e. to the size of the largest image (rounded up to 32 detections)
-        max_img = (int(np.max(np.diff(img_off))) + 31) // 32 * 32 if B > 0 else 0
-        if self._shape != (T, B) or max_img != self._max_img:
-            self._max_img = max_img
-            self._alloc(T, B)
-        self.h_dets.numpy()[...] = dets
-        self.h_scores.numpy()[...] = det_scores
-        self.h_cls.numpy()[...] = det_classes
-        self.h_off.numpy()[...] = img_off
-        for attempt in range(3):
+        if T == 0:
+            return np.zeros((0,), dtype=np.float32)
+        # a graph is specific to (T, B) and to the mask stride of the neighbor build, i.e.
+        # to the size of the largest image (rounded up to 32 detections)
+        self._max_img = (int(np.max(np.diff(img_off))) + 31) // 32 * 32
+        key = (T, B, self._max_img)
+        self._seen[key] += 1
+        if len(self._seen) > 4096:           # variable-size data: do not grow without bound
+            self._seen.clear()
+        state = self._states.get(key)
+        want_graph = self.use_graph and (state is not None or self._seen[key] >= self.graph_after)
+        if want_graph and state is None:
+            buf = _Buffers(T, B, self.device)
+        elif state is not None:
+            buf = state[0]
+            self._states.move_to_end(key)
+        else:
+            buf = self._eager_buffers(T, B)
+        buf.h_dets.numpy()[...] = dets
+        buf.h_scores.numpy()[...] = det_scores
+        buf.h_cls.numpy()[...] = det_classes
+        buf.h_off.numpy()[...] = img_off
+        self._cur = buf
+        for attempt in range(4):
             with torch.cuda.stream(self.stream):
-                if self._graph is None:
-                    self.d_in.copy_(self.h_in, non_blocking=True)   # warm-up runs on real inputs
-                    self._prepare()
-                if self._graph:
-                    self._graph_io.replay()
+                if want_graph and state is None:
+                    buf.d_in[:buf.copy_bytes].copy_(buf.h_in[:buf.copy_bytes], non_blocking=True)
+                    state = (buf,) + self._capture(buf)
+                    self._states[key] = state
+                    while len(self._states) > self.MAX_GRAPHS:
+                        self._states.popitem(last=False)
+                if want_graph:
+                    self._graph = state[1]
+                    state[2].replay()
                 else:
-                    self.d_in.copy_(self.h_in, non_blocking=True)
-                    self._forward()
-                    self.h_pred.copy_(self._pred, non_blocking=True)
-                    self.h_np.copy_(self._num_pairs, non_blocking=True)
+                    self._graph = False if not self.use_graph else None
+                    buf.d_in[:buf.copy_bytes].copy_(buf.h_in[:buf.copy_bytes], non_blocking=True)
+                    if self.launches_per_forward is None:
+                        self._warm(buf)
+                        n0 = _lib.CALLS[0]
+                        self._forward(buf)
+                        self.launches_per_forward = _lib.CALLS[0] - n0
+                    else:
+                        self._forward(buf)
+                    buf.h_pred.copy_(self._pred, non_blocking=True)
+                    buf.h_np.copy_(self._num_pairs, non_blocking=True)
             self.stream.synchronize()
-            if int(self.h_np[0]) <= self._cap:
-                return self.h_pred.numpy()
-            # denser batch than the workspace was sized for: grow, re-capture, redo
-            self.engine.capacity = int(int(self.h_np[0]) * 1.25) + 256
-            self._graph = None
+            if int(buf.h_np[0]) <= self._cap:
+                return buf.h_pred.numpy()
+            # denser batch than the workspace was sized for: grow, drop the graphs (they were
+            # captured with the old capacity), redo
+            self.engine.capacity = int(int(buf.h_np[0]) * 1.25) + 256
+            self._states.clear()
+            state = None
         raise RuntimeError('pair capacity did not converge')

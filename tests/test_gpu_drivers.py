@@ -111,3 +111,37 @@ def test_batched_validation_equals_per_image_loop():
     assert np.array_equal(batched[2], np.concatenate(labels))
     m_ap, mc_ap, cls_ap = evaluation.val_run(net, val_imdb, images_per_call=4, verbose=False)
     assert 0.0 <= mc_ap <= 100.0 and len(cls_ap) == 3
+
+
+def test_session_graphs_repeated_shapes_and_runs_new_shapes_eagerly():
+    """InferenceSession: a batch shape that comes back is replayed as a CUDA graph (captured
+    the second time it is seen), one-off shapes run eagerly through grow-only staging - and
+    every path returns exactly what Gnet.run_batch computes."""
+    from gossipnet_b200 import synthetic
+    from gossipnet_b200.session import InferenceSession
+    load_experiment('coco_person', num_blocks=2)
+    net = Gnet(1)
+    sess = InferenceSession(net)
+
+    def batch(sizes, first):
+        imgs = [synthetic.make_image(n, 1, image_index=first + i) for i, n in enumerate(sizes)]
+        off = np.zeros(len(sizes) + 1, np.int32)
+        np.cumsum(sizes, out=off[1:])
+        cat = lambda k, dt: np.concatenate([im[k] for im in imgs]).astype(dt)
+        want = net.run_batch([{k: im[k] for k in ('dets', 'det_scores', 'det_classes')}
+                              for im in imgs])['prediction'].cpu().numpy().copy()
+        return (cat('dets', np.float32), cat('det_scores', np.float32),
+                cat('det_classes', np.int32), off), want
+
+    shapes = [[120, 80], [300], [120, 80], [50, 60, 70], [120, 80], [300], [640, 1], [120, 80]]
+    graphed = []
+    for i, sizes in enumerate(shapes):
+        args, want = batch(sizes, first=10 * i)          # same shape, different boxes each time
+        got = sess.run(*args)
+        assert np.array_equal(got, want), (i, sizes)
+        graphed.append(bool(sess._graph))
+    # [120,80] is captured at its 2nd appearance, [300] at its 2nd; the one-off shapes never
+    assert graphed == [False, False, True, False, True, True, False, True]
+    assert len(sess._states) == 2
+    assert sess.run(np.zeros((0, 4), np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32),
+                    np.zeros(1, np.int32)).shape == (0,)
