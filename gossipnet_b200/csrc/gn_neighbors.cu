@@ -7,6 +7,7 @@
 // of that image, so each column box is loaded once per warp (coalesced 512 B)
 // and reused from registers for all of the warp's rows.  Order inside a row is
 // kept with ballot + popc prefix counts.
+#include <type_traits>
 #include "gn_common.cuh"
 
 namespace gn {
@@ -115,20 +116,19 @@ __device__ __forceinline__ int find_image_warp(const int32_t* __restrict__ off, 
   return min(count, num_images - 1);
 }
 
-__device__ __forceinline__ bool iou_at_least(const Box& a, const Box& b, float thresh) {
+// EXACT = false: the division-free decision; `border` collects (per lane, no vote in the hot
+// loop) whether any pair fell into the band where only the exact test decides.
+// EXACT = true : fl(inter / union) >= thresh, the reference's own test.
+template <bool EXACT>
+__device__ __forceinline__ bool iou_at_least(const Box& a, const Box& b, float thresh, bool& border) {
+  if (EXACT) return box_iou(a, b) >= thresh;
   const float inter = box_intersection(a, b);
   const float uni = __fsub_rn(__fadd_rn(a.area, b.area), inter);
   const float t = __fmul_rn(thresh, uni);
   const float hi = __fmul_rn(t, 1.0f + 9.5367431640625e-07f);   // 1 + 2^-20
   const float lo = __fmul_rn(t, 1.0f - 9.5367431640625e-07f);
-  bool hit = inter >= hi;
-  // borderline, thresh <= 0 or a degenerate box: the exact test.  The common path stays
-  // branch free: one warp vote, and the division only runs if some lane needs it.
-  const bool border = !(thresh > 0.f && uni > 0.f) || (inter > lo && inter < hi);
-  if (__any_sync(0xffffffffu, border)) {
-    if (border) hit = box_iou(a, b) >= thresh;
-  }
-  return hit;
+  border |= !(uni > 0.f) || (inter > lo && inter < hi);
+  return inter >= hi;
 }
 
 __global__ void __launch_bounds__(NB_THREADS)
@@ -154,45 +154,56 @@ neighbor_mask_kernel(const float* __restrict__ dets, const int32_t* __restrict__
       rb[i] = make_box(ldg4(dets + (size_t)r * 4));
     }
   }
-  // rows of one image are contiguous: walk the (at most 4) images the warp's rows touch, so
-  // every row's mask words are aligned to its own image start.  All array indices are
-  // compile-time constants (dynamic ones would send lo / hi / rb to local memory).
+  // One pass over the warp's rows with the division-free test; in the (rare) case that some
+  // pair of the warp landed in the borderline band - or thresh <= 0 - the warp repeats its rows
+  // with the exact test and overwrites its masks and counts.
+  bool border = !(thresh > 0.f);
+  auto walk = [&](auto exact_tag) {
+    constexpr bool EXACT = decltype(exact_tag)::value;
 #pragma unroll
-  for (int s0 = 0; s0 < NB_ROWS_PER_WARP; ++s0) {
-    const bool starts = lo[s0] >= 0 && (s0 == 0 || lo[s0] != lo[s0 > 0 ? s0 - 1 : 0]);
-    if (!starts) continue;                          // warp uniform
-    const int seg_lo = lo[s0], seg_hi = hi[s0];
-    // lane (w % 32) keeps the mask of iteration w; every 32 iterations (and at the end) the
-    // warp writes 32 words of each row with one coalesced store
-    unsigned acc[NB_ROWS_PER_WARP] = {0u, 0u, 0u, 0u};
-    int w = 0;
-    for (int c0 = seg_lo; c0 < seg_hi; c0 += 32, ++w) {
-      const int c = c0 + lane;
-      const bool in_range = c < seg_hi;
-      const Box cb = make_box(in_range ? ldg4(dets + (size_t)c * 4) : make_float4(0.f, 0.f, 1.f, 1.f));
-#pragma unroll
-      for (int i = s0; i < NB_ROWS_PER_WARP; ++i) {
-        if (lo[i] != seg_lo) continue;              // warp uniform
-        const bool over = iou_at_least(rb[i], cb, thresh);   // all lanes: it votes
-        const unsigned mask = __ballot_sync(0xffffffffu, in_range && over);
-        if ((w & 31) == lane) acc[i] = mask;
-        cnt[i] += __popc(mask);
+    for (int i = 0; i < NB_ROWS_PER_WARP; ++i) cnt[i] = 0;
+    // rows of one image are contiguous: walk the (at most 4) images the warp's rows touch, so
+    // every row's mask words are aligned to its own image start.  All array indices are
+    // compile-time constants (dynamic ones would send lo / hi / rb to local memory).
+  #pragma unroll
+    for (int s0 = 0; s0 < NB_ROWS_PER_WARP; ++s0) {
+      const bool starts = lo[s0] >= 0 && (s0 == 0 || lo[s0] != lo[s0 > 0 ? s0 - 1 : 0]);
+      if (!starts) continue;                          // warp uniform
+      const int seg_lo = lo[s0], seg_hi = hi[s0];
+      // lane (w % 32) keeps the mask of iteration w; every 32 iterations (and at the end) the
+      // warp writes 32 words of each row with one coalesced store
+      unsigned acc[NB_ROWS_PER_WARP] = {0u, 0u, 0u, 0u};
+      int w = 0;
+      for (int c0 = seg_lo; c0 < seg_hi; c0 += 32, ++w) {
+        const int c = c0 + lane;
+        const bool in_range = c < seg_hi;
+        const Box cb = make_box(in_range ? ldg4(dets + (size_t)c * 4) : make_float4(0.f, 0.f, 1.f, 1.f));
+  #pragma unroll
+        for (int i = s0; i < NB_ROWS_PER_WARP; ++i) {
+          if (lo[i] != seg_lo) continue;              // warp uniform
+          const bool over = iou_at_least<EXACT>(rb[i], cb, thresh, border);
+          const unsigned mask = __ballot_sync(0xffffffffu, in_range && over);
+          if ((w & 31) == lane) acc[i] = mask;
+          cnt[i] += __popc(mask);
+        }
+        if ((w & 31) == 31) {
+  #pragma unroll
+          for (int i = s0; i < NB_ROWS_PER_WARP; ++i)
+            if (lo[i] == seg_lo && (w - 31 + lane) < stride)
+              masks[(size_t)(row0 + i) * stride + (w - 31) + lane] = acc[i];
+        }
       }
-      if ((w & 31) == 31) {
-#pragma unroll
+      if ((w & 31) != 0) {
+        const int wbase = w & ~31;
+  #pragma unroll
         for (int i = s0; i < NB_ROWS_PER_WARP; ++i)
-          if (lo[i] == seg_lo && (w - 31 + lane) < stride)
-            masks[(size_t)(row0 + i) * stride + (w - 31) + lane] = acc[i];
+          if (lo[i] == seg_lo && lane < (w & 31) && wbase + lane < stride)
+            masks[(size_t)(row0 + i) * stride + wbase + lane] = acc[i];
       }
     }
-    if ((w & 31) != 0) {
-      const int wbase = w & ~31;
-#pragma unroll
-      for (int i = s0; i < NB_ROWS_PER_WARP; ++i)
-        if (lo[i] == seg_lo && lane < (w & 31) && wbase + lane < stride)
-          masks[(size_t)(row0 + i) * stride + wbase + lane] = acc[i];
-    }
-  }
+  };
+  walk(std::false_type{});
+  if (__any_sync(0xffffffffu, border)) walk(std::true_type{});
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < NB_ROWS_PER_WARP; ++i)
