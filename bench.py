@@ -84,17 +84,29 @@ def make_inputs(n_images, n_dets, first_index):
 
 
 # ------------------------------------------------------------------ CPU baseline
-def cpu_forward_rate(cfg, n_dets, seconds, max_images=64, first_index=0):
+def blas_threads():
+    """Threads the BLAS behind numpy uses (the FCs of the CPU restatement run there)."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [int(i.get('num_threads', 0)) for i in threadpool_info() if i.get('user_api') == 'blas']
+        return max(n) if n else None
+    except Exception:
+        return None
+
+
+def cpu_forward_rate(cfg, n_dets, seconds, max_images=64, first_index=0, warm=True):
     """Reference formulation on the host cores, one image per call like
-    test.py:63-71 (numpy float32 restatement, BLAS threads = all cores)."""
+    test.py:63-71 (numpy float32 restatement, BLAS threads = all cores).  `warm`: one
+    untimed forward first (callers that time several calls warm up once themselves)."""
     from gossipnet_b200 import params as P
     from gossipnet_b200 import synthetic
     from oracle import gnet_oracle
     layout, total = P.param_layout(1, cfg)
     pv = P.views(layout, P.init_flat(layout, total, cfg, seed=1))
     keys = ('dets', 'det_scores', 'det_classes')
-    img = synthetic.make_image(n_dets, 1, image_index=first_index)
-    gnet_oracle.gnet_forward({k: img[k] for k in keys}, pv, cfg, 1, keep_intermediates=False)
+    if warm:
+        img = synthetic.make_image(n_dets, 1, image_index=first_index)
+        gnet_oracle.gnet_forward({k: img[k] for k in keys}, pv, cfg, 1, keep_intermediates=False)
     done, t0 = 0, time.perf_counter()
     while done < max_images:
         img = synthetic.make_image(n_dets, 1, image_index=first_index + done)
@@ -117,10 +129,13 @@ def run_reference(args):
         cpu_forward_rate(cfg, args.n_dets, 1e9, max_images=1)
     t0 = time.perf_counter()
     for s in range(args.steps):
-        cpu_forward_rate(cfg, args.n_dets, 1e9, max_images=per_step, first_index=s * per_step)
+        # exactly per_step forwards per step: the warm-up forward stays outside the timer
+        cpu_forward_rate(cfg, args.n_dets, 1e9, max_images=per_step, first_index=s * per_step,
+                         warm=False)
     dt = time.perf_counter() - t0
     value = args.steps * per_step * args.n_dets / dt
-    sample = '%d images x N=%d per step, one image per call' % (per_step, args.n_dets)
+    sample = ('%d images x N=%d per step, one image per call, %s BLAS threads'
+              % (per_step, args.n_dets, blas_threads()))
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,

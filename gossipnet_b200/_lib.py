@@ -100,6 +100,17 @@ SIGNATURES = {
                         c_float, c_void_p, c_void_p, c_void_p],
     'gn_roi_pool_bwd': [c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                         c_int, c_float, c_void_p, c_void_p],
+    'gn_pwfeat_mlp_fwd_hl': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                             c_void_p],
+    'gn_block_pair_tma_image_bytes': [],
+    'gn_prepare_pair_tma_image': [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    'gn_block_pair_fwd_tma': [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                              c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'gn_block_pair_fwd_tma_bf16': [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'gn_selftest_tma': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     'gn_selftest_umma': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     'gn_selftest_umma_ts': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     'gn_selftest_umma_rate': [c_int, c_int, c_int, c_int, c_void_p, c_void_p],
@@ -107,7 +118,8 @@ SIGNATURES = {
 _RESTYPES = {'gn_last_error': ctypes.c_char_p, 'gn_pwfeat_prep_bytes': ctypes.c_int64,
              'gn_block_pair_image_bytes': ctypes.c_int64,
              'gn_block_det_image_bytes': ctypes.c_int64,
-             'gn_block_pair_ab_image_bytes': ctypes.c_int64}
+             'gn_block_pair_ab_image_bytes': ctypes.c_int64,
+             'gn_block_pair_tma_image_bytes': ctypes.c_int64}
 
 _lib = None
 # number of C-ABI compute calls made so far (each is one kernel launch of this

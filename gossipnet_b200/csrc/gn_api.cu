@@ -31,3 +31,38 @@ int gn_abi_version(void) { return 1; }
 int gn_sm_count(void) { return gn::sm_count(); }
 
 }  // extern "C"
+
+// ---- tensor-map encoder (gn_tma.cuh) ------------------------------------------------
+#include "gn_tma.cuh"
+
+namespace gn {
+
+tmap_encode_fn tmap_encoder() {
+  // process constant (the driver's entry point), resolved once; C++11 makes this thread safe
+  static const tmap_encode_fn fn = []() -> tmap_encode_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<tmap_encode_fn>(p);
+  }();
+  return fn;
+}
+
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                        uint64_t pitch_bytes, uint32_t box_rows, uint32_t box_cols) {
+  const tmap_encode_fn enc = tmap_encoder();
+  if (enc == nullptr) return -1;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+}  // namespace gn

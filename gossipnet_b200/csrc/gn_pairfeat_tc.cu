@@ -157,7 +157,8 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
                    const int32_t* __restrict__ num_pairs, int capacity, int num_classes, float mult,
                    const float* __restrict__ w1, const float* __restrict__ b1,
                    const float* __restrict__ b2, const float* __restrict__ b3,
-                   const unsigned char* __restrict__ img, float* __restrict__ pw_out) {
+                   const unsigned char* __restrict__ img, float* __restrict__ pw_out,
+                   uint4* __restrict__ pw_hl) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -310,21 +311,45 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         if (t == 0) PP_TR(47);
         const float* bb = bias3 + cg * 8;
         unsigned char* stage = smem + PQ_OUT;
-        float4* dst = reinterpret_cast<float4*>(stage + erow * PP_OUT_PITCH + cg * 32);
-        dst[0] = make_float4(fmaxf(v[0] + bb[0], 0.f), fmaxf(v[1] + bb[1], 0.f),
-                             fmaxf(v[2] + bb[2], 0.f), fmaxf(v[3] + bb[3], 0.f));
-        dst[1] = make_float4(fmaxf(v[4] + bb[4], 0.f), fmaxf(v[5] + bb[5], 0.f),
-                             fmaxf(v[6] + bb[6], 0.f), fmaxf(v[7] + bb[7], 0.f));
-        asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
+        float o[8];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int idx = i * (PP_EPI_WARPS * 32) + t;       // 1024 chunks of 16 bytes
-          const int r = idx >> 3, ch = idx & 7;
-          const int p = tile * PT_TILE + r;
-          const float4 x = *reinterpret_cast<const float4*>(stage + r * PP_OUT_PITCH + ch * 16);
-          if (p < P) *reinterpret_cast<float4*>(pw_out + (size_t)p * PT_O + ch * 4) = x;
+        for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + bb[e], 0.f);
+        if (pw_out != nullptr) {
+          float4* dst = reinterpret_cast<float4*>(stage + erow * PP_OUT_PITCH + cg * 32);
+          dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int idx = i * (PP_EPI_WARPS * 32) + t;       // 1024 chunks of 16 bytes
+            const int r = idx >> 3, ch = idx & 7;
+            const int p = tile * PT_TILE + r;
+            const float4 x = *reinterpret_cast<const float4*>(stage + r * PP_OUT_PITCH + ch * 16);
+            if (p < P) *reinterpret_cast<float4*>(pw_out + (size_t)p * PT_O + ch * 4) = x;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");   // staging reusable
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");   // staging reusable
+        if (pw_hl != nullptr) {
+          // the same row as the block kernels' tensor-core operand: [32 bf16 hi | 32 bf16 lo]
+          // (128 bytes per pair, gn_block_tma.cu loads it with one tensor-map TMA per tile)
+          uint4 h, l;
+          umma::split_bf16x2(o[0], o[1], h.x, l.x);
+          umma::split_bf16x2(o[2], o[3], h.y, l.y);
+          umma::split_bf16x2(o[4], o[5], h.z, l.z);
+          umma::split_bf16x2(o[6], o[7], h.w, l.w);
+          *reinterpret_cast<uint4*>(stage + erow * PP_OUT_PITCH + cg * 16) = h;
+          *reinterpret_cast<uint4*>(stage + erow * PP_OUT_PITCH + 64 + cg * 16) = l;
+          asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int idx = i * (PP_EPI_WARPS * 32) + t;
+            const int r = idx >> 3, ch = idx & 7;
+            const int p = tile * PT_TILE + r;
+            const uint4 x = *reinterpret_cast<const uint4*>(stage + r * PP_OUT_PITCH + ch * 16);
+            if (p < P) pw_hl[(size_t)p * 8 + ch] = x;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
+        }
       }
       if (t == 0) PP_TR(46);
       umma::tc_fence_before();   // the next production's arrive orders these loads before the
@@ -539,7 +564,7 @@ static int launch_pwfeat(bool x3, const float* dets, const float* scores, const 
                                  int num_classes, float multiplier, const float* w1,
                                  const float* b1, const float* w2, const float* b2,
                                  const float* w3, const float* b3, int hidden, int out_dim,
-                                 void* wprep, float* pw_out, gn_stream_t stream) {
+                                 void* wprep, float* pw_out, void* pw_hl, gn_stream_t stream) {
   GN_REQUIRE(capacity >= 0 && num_classes >= 1, "gn_pwfeat_mlp_fwd: bad sizes");
   if (hidden != gn::PT_H || out_dim != gn::PT_O) {
     gn::set_error("gn_pwfeat_mlp_fwd: fused kernel is built for hidden=%d out=%d (got %d, %d)",
@@ -547,11 +572,12 @@ static int launch_pwfeat(bool x3, const float* dets, const float* scores, const 
     return GN_ERR_UNSUPPORTED;
   }
   if (capacity == 0) return GN_OK;
-  GN_REQUIRE(dets && scores && pair_c && pair_n && pair_iou && num_pairs && pw_out && w1 && b1 &&
-                 w2 && b2 && w3 && b3 && wprep,
+  GN_REQUIRE(dets && scores && pair_c && pair_n && pair_iou && num_pairs && (pw_out || pw_hl) &&
+                 w1 && b1 && w2 && b2 && w3 && b3 && wprep,
              "gn_pwfeat_mlp_fwd: null pointer");
   GN_REQUIRE(num_classes == 1 || classes != nullptr, "gn_pwfeat_mlp_fwd: classes required");
-  GN_REQUIRE((((uintptr_t)w1 | (uintptr_t)pw_out | (uintptr_t)dets | (uintptr_t)wprep) & 15) == 0,
+  GN_REQUIRE((((uintptr_t)w1 | (uintptr_t)pw_out | (uintptr_t)pw_hl | (uintptr_t)dets |
+               (uintptr_t)wprep) & 15) == 0,
              "gn_pwfeat_mlp_fwd: pointers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   unsigned char* img = static_cast<unsigned char*>(wprep);
@@ -568,7 +594,7 @@ static int launch_pwfeat(bool x3, const float* dets, const float* scores, const 
     if (e == cudaSuccess)                                                                      \
       gn::pwfeat_pipe_kernel<MULTI_, X3_><<<grid, gn::PP_THREADS, gn::PQ_BYTES, s>>>(          \
           dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity, num_classes,   \
-          multiplier, w1, b1, b2, b3, img, pw_out);                                            \
+          multiplier, w1, b1, b2, b3, img, pw_out, static_cast<uint4*>(pw_hl));                \
   } while (0)
   if (num_classes > 1) {
     if (x3) GN_PWFEAT_LAUNCH(true, true); else GN_PWFEAT_LAUNCH(true, false);
@@ -593,7 +619,7 @@ extern "C" int gn_pwfeat_mlp_fwd(const float* dets, const float* scores, const i
                                  void* wprep, float* pw_out, gn_stream_t stream) {
   return launch_pwfeat(true, dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
                        num_classes, multiplier, w1, b1, w2, b2, w3, b3, hidden, out_dim, wprep,
-                       pw_out, stream);
+                       pw_out, nullptr, stream);
 }
 
 extern "C" int gn_pwfeat_mlp_fwd_bf16(const float* dets, const float* scores,
@@ -606,5 +632,21 @@ extern "C" int gn_pwfeat_mlp_fwd_bf16(const float* dets, const float* scores,
                                       float* pw_out, gn_stream_t stream) {
   return launch_pwfeat(false, dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
                        num_classes, multiplier, w1, b1, w2, b2, w3, b3, hidden, out_dim, wprep,
-                       pw_out, stream);
+                       pw_out, nullptr, stream);
+}
+
+// The same MLP with the output (also) written as bf16 (hi | lo) operand rows pw_hl[P, 64]:
+// the format gn_block_pair_fwd_tma streams into its A tile.  pw_out may be null.
+extern "C" int gn_pwfeat_mlp_fwd_hl(const float* dets, const float* scores, const int32_t* classes,
+                                    const int32_t* pair_c, const int32_t* pair_n,
+                                    const float* pair_iou, const int32_t* num_pairs, int capacity,
+                                    int num_classes, float multiplier, const float* w1,
+                                    const float* b1, const float* w2, const float* b2,
+                                    const float* w3, const float* b3, int hidden, int out_dim,
+                                    void* wprep, float* pw_out, void* pw_hl, int plain_bf16,
+                                    gn_stream_t stream) {
+  GN_REQUIRE(pw_hl != nullptr, "gn_pwfeat_mlp_fwd_hl: null pw_hl");
+  return launch_pwfeat(plain_bf16 == 0, dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs,
+                       capacity, num_classes, multiplier, w1, b1, w2, b2, w3, b3, hidden, out_dim,
+                       wprep, pw_out, pw_hl, stream);
 }

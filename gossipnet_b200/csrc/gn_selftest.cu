@@ -284,3 +284,110 @@ extern "C" int gn_selftest_umma_rate(int n, int reps, int distinct_b, int ctas, 
   GN_CHECK_LAUNCH("gn_selftest_umma_rate");
   return GN_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// Tensor-map TMA self-test: pins the conventions gn_block_tma.cu relies on.
+//   1. tile load of 128 rows x 64 bf16 (SWIZZLE_128B) from mat[row0 ...]        -> A0
+//   2. 32 x gather4 of the rows idx[0..127] of the same matrix                  -> A1
+//   3. tile load of wmat[64 x 64 bf16]                                          -> B
+//   4. raw dump of A0 | A1 | B (40 KB), then D[128 x 64] = (A0 + A1) . B^T with eight
+//      SS-form UMMAs on SWIZZLE_128B K-major descriptors (K advance = 32 bytes)
+// tests/test_gpu_umma.py checks the dump against the expected swizzle (16-byte chunk j of
+// row r at r * 128 + ((j ^ (r % 8)) * 16)) and D against a float64 product.
+// ---------------------------------------------------------------------------------
+#include "gn_tma.cuh"
+
+namespace gn {
+constexpr uint32_t TS_A_BYTES = 128 * 128, TS_B_BYTES = 64 * 128;
+
+__global__ void __launch_bounds__(128, 1)
+tma_selftest_kernel(const __grid_constant__ CUtensorMap tm_tile,
+                    const __grid_constant__ CUtensorMap tm_row,
+                    const __grid_constant__ CUtensorMap tm_w, const int32_t* __restrict__ idx,
+                    int row0, unsigned char* __restrict__ dump, float* __restrict__ d_out) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ uint64_t bars[2];
+  __shared__ uint32_t tmem_base;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const uint32_t sbase = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
+  unsigned char* smem = smem_raw + (sbase - umma::smem_u32(smem_raw));
+  const uint32_t s_a0 = sbase, s_a1 = sbase + TS_A_BYTES, s_b = sbase + 2 * TS_A_BYTES;
+
+  if (warp == 0) umma::tmem_alloc(&tmem_base, 64);
+  if (t == 0) {
+    umma::mbar_init(&bars[0], 1);
+    umma::mbar_init(&bars[1], 1);
+    umma::fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    const int4 r = __ldg(reinterpret_cast<const int4*>(idx) + lane);
+    if (lane == 0) {
+      umma::mbar_expect_tx(&bars[0], 2 * TS_A_BYTES + TS_B_BYTES);
+      umma::tma_load_2d(s_a0, &tm_tile, 0, row0, &bars[0], umma::TMA_EVICT_FIRST);
+      umma::tma_load_2d(s_b, &tm_w, 0, 0, &bars[0], umma::TMA_EVICT_LAST);
+    }
+    __syncwarp();
+    umma::tma_gather4(s_a1 + lane * 512, &tm_row, 0, r.x, r.y, r.z, r.w, &bars[0],
+                      umma::TMA_EVICT_LAST);
+  }
+  umma::mbar_wait(&bars[0], 0);
+  for (int i = t; i < (int)(2 * TS_A_BYTES + TS_B_BYTES) / 16; i += 128)
+    reinterpret_cast<uint4*>(dump)[i] = reinterpret_cast<const uint4*>(smem)[i];
+  umma::tc_fence_before();
+  __syncthreads();
+  umma::tc_fence_after();
+  const uint32_t tmem = tmem_base;
+  if (t == 0) {
+    const uint32_t idesc = umma::idesc_bf16_f32(128, 64);
+    const uint64_t da0 = umma::smem_desc_sw128(s_a0), da1 = umma::smem_desc_sw128(s_a1);
+    const uint64_t db = umma::smem_desc_sw128(s_b);
+    for (int ks = 0; ks < 4; ++ks) {
+      umma::mma_bf16_ss(tmem, da0 + ks * 2, db + ks * 2, idesc, ks > 0);
+      umma::mma_bf16_ss(tmem, da1 + ks * 2, db + ks * 2, idesc, 1);
+    }
+    umma::mma_commit(&bars[1]);
+  }
+  umma::mbar_wait(&bars[1], 0);
+  umma::tc_fence_after();
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+    umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    umma::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d_out[(size_t)t * 64 + c0 + i] = v[i];
+  }
+  umma::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc(tmem, 64);
+}
+}  // namespace gn
+
+extern "C" int gn_selftest_tma(const void* mat_bf16, int rows, const void* wmat_bf16,
+                               const int32_t* idx, int row0, void* dump, float* d_out,
+                               gn_stream_t stream) {
+  GN_REQUIRE(mat_bf16 && wmat_bf16 && idx && dump && d_out, "gn_selftest_tma: null pointer");
+  GN_REQUIRE(rows >= 1 && row0 >= 0, "gn_selftest_tma: bad sizes");
+  GN_REQUIRE((((uintptr_t)mat_bf16 | (uintptr_t)wmat_bf16 | (uintptr_t)idx | (uintptr_t)dump) & 15) == 0,
+             "gn_selftest_tma: unaligned pointer");
+  CUtensorMap tm_tile, tm_row, tm_w;
+  int r = gn::encode_tmap_2d_bf16(&tm_tile, mat_bf16, rows, 64, 128, 128, 64);
+  if (r == 0) r = gn::encode_tmap_2d_bf16(&tm_row, mat_bf16, rows, 64, 128, 1, 64);
+  if (r == 0) r = gn::encode_tmap_2d_bf16(&tm_w, wmat_bf16, 64, 64, 128, 64, 64);
+  if (r != 0) {
+    gn::set_error("gn_selftest_tma: cuTensorMapEncodeTiled failed (%d)", r);
+    return GN_ERR_CUDA;
+  }
+  const int smem = 2 * gn::TS_A_BYTES + gn::TS_B_BYTES + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gn::tma_selftest_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    gn::set_error("gn_selftest_tma: %s", cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
+  gn::tma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
+      tm_tile, tm_row, tm_w, idx, row0, static_cast<unsigned char*>(dump), d_out);
+  GN_CHECK_LAUNCH("gn_selftest_tma");
+  return GN_OK;
+}

@@ -100,6 +100,52 @@ __device__ __forceinline__ void bulk_wait_group0() {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ---- tensor-map TMA (cp.async.bulk.tensor) ------------------------------------------
+// The tensor map (CUtensorMap, built on the host by gn::encode_tmap_2d, gn_tma.cuh) is a
+// __grid_constant__ kernel parameter; `tmap` is its generic address.  Completion is
+// reported to `bar` as box-bytes of complete_tx (out-of-bounds rows are zero filled and
+// still counted).  L2 cache-policy words: createpolicy encodings used by CUTLASS.
+constexpr uint64_t TMA_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t TMA_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t TMA_EVICT_LAST = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
+}
+// 2D tile: box {box0 (inner), box1 (rows)} at coordinates {c0 (inner element), c1 (row)}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap, int32_t c0,
+                                            int32_t c1, uint64_t* bar, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1),
+        "r"(smem_u32(bar)), "l"(hint) : "memory");
+}
+// gather4 (sm_100): four rows r0..r3 of a 2D tensor (box {box0, 1}) land as four consecutive
+// box0-wide rows at dst_smem, swizzled like a tile load
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const void* tmap, int32_t c0,
+                                            int32_t r0, int32_t r1, int32_t r2, int32_t r3,
+                                            uint64_t* bar, uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes"
+      ".cta_group::1.L2::cache_hint [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(r0), "r"(r1), "r"(r2),
+        "r"(r3), "r"(smem_u32(bar)), "l"(hint) : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B (layout_type 2): rows of 128 bytes
+// (64 bf16 of K), 8-row groups 1024 bytes apart (SBO), 16-byte chunk j of row r stored at
+// chunk position j ^ (r % 8) - the layout a SWIZZLE_128B tensor map writes.  The tile base
+// must be 1024-byte aligned; a K = 16 step advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;   // SBO
+  d |= (uint64_t)1 << 46;             // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;             // SWIZZLE_128B
+  return d;
+}
+
 // ---- TMEM ---------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address
 // is written to *dst_smem.

@@ -89,9 +89,17 @@ class GnetEngine(object):
         # the pair kernel (+14 us in the det kernel): 'ab' halves the shared-memory
         # traffic but doubles the random L2 gather bytes per pair (2 x 256 B fp32 rows
         # instead of 2 x 128 B), whose latency lands in the epilogue.  Kept selectable.
-        # 'pipe': the 'hl' arithmetic as a warp-specialised pipeline (gn_block_pipe.cu), the
-        # shipped variant.
-        self.pair_mode = 'pipe'
+        # 'pipe': the 'hl' arithmetic as a warp-specialised pipeline (gn_block_pipe.cu).
+        # 'tma': operands fed by tensor-map TMA (tile load of the pair's own bf16 hi|lo pw row,
+        # gather4 of the neighbor's reduced row), the detection-level third of pw_fc1 hoisted
+        # into the det kernel (gn_block_tma.cu).
+        self.pair_mode = 'tma'
+        # fp32 pw_feats next to the bf16 (hi|lo) operand rows the 'tma' pair stage consumes
+        # (the `pw_feats` attribute of the reference surface); False on the inference hot path
+        self.want_pw_f32 = True
+        # bumped whenever a workspace buffer is reallocated: captured CUDA graphs hold raw
+        # pointers into the workspace and must be dropped when this changes (session.py)
+        self.ws_generation = 0
         # the predict head's hidden layers are linear (network.py:263): apply it as one folded
         # affine map instead of three FC launches (False: the staged FCs)
         self.collapse_predict = True
@@ -106,6 +114,7 @@ class GnetEngine(object):
         if t is None or t.numel() < n or t.dtype != dtype:
             t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
             self._ws[name] = t
+            self.ws_generation += 1
         return t[:n].view(*shape)
 
     def _ensure_capacity(self, num_pairs_dev, num_dets):
@@ -173,11 +182,20 @@ class GnetEngine(object):
         mult = g['pw_feat_multiplyer']
         if g['num_pwfeat_fc'] > 0 and self.fused_pw and self.use_fused:
             s = 'gnet/pw_feats/fc%d/'
-            out = self._buf('pw', (cap, 32))
             w = [self.p[(s % i) + k] for i in (1, 2, 3) for k in ('weights', 'biases')]
             if 'wprep' not in self._ws:
                 self._ws['wprep'] = torch.empty(int(ops._lib.load().gn_pwfeat_prep_bytes()),
                                                 dtype=torch.uint8, device=self.device)
+                self.ws_generation += 1
+            if self._tma_path():
+                # bf16 (hi | lo) operand rows for the TMA-fed pair stage; fp32 rows on request
+                self._pw_hl = self._buf('pw_hl', (cap, 64), torch.bfloat16)
+                out = self._buf('pw', (cap, 32)) if self.want_pw_f32 else None
+                return ops.pwfeat_mlp_fwd(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs,
+                                          cap, self.num_classes, mult, *w, out=out,
+                                          wprep=self._ws['wprep'], bf16=self.bf16,
+                                          out_hl=self._pw_hl, want_f32=self.want_pw_f32)
+            out = self._buf('pw', (cap, 32))
             return ops.pwfeat_mlp_fwd(dets, scores, cls, pair_c, pair_n, pair_iou, num_pairs, cap,
                                       self.num_classes, mult, *w, out=out,
                                       ffma=not self.use_tensor_cores, wprep=self._ws['wprep'],
@@ -191,6 +209,12 @@ class GnetEngine(object):
             y = self._buf('pw_fc%d' % (i % 2), (cap, width))
             x = self._fc(x, 'gnet/pw_feats/fc%d' % i, True, out=y, rows_dev=num_pairs)
         return x
+
+    def _tma_path(self):
+        """True when the forward runs the TMA-fed pair stage (needs every fused piece)."""
+        return (self.pair_mode == 'tma' and self.fused_pw and self.fused_det and self.use_fused
+                and self.use_tensor_cores and self.g['num_blocks'] > 0
+                and self.g['num_pwfeat_fc'] > 0)
 
     def block(self, b, infeats, row_ptr, pair_c, pair_n, num_pairs, cap, pw, out):
         """A7: nms_net/network.py:344-409."""
@@ -233,11 +257,11 @@ class GnetEngine(object):
         block b, reduce_dim and (pw_fc1[32:64] | pw_fc1[64:96])^T of block b+1].
         pair_mode 'hl': pair image = [pw_fc1^T (K = 96), pw_fc2^T]; det image without the
         last part."""
-        key = 'wimg_' + ('ab' if self.pair_mode == 'ab' else 'hl')
+        ab = self.pair_mode in ('ab', 'tma')
+        key = 'wimg_' + ('ab' if ab else 'hl')
         if key in self._ws:
             return self._ws[key]
         lib = ops._lib.load()
-        ab = self.pair_mode == 'ab'
         pair_b = int(lib.gn_block_pair_ab_image_bytes() if ab else lib.gn_block_pair_image_bytes())
         det_b = int(lib.gn_block_det_image_bytes())
         nb = self.g['num_blocks']
@@ -279,7 +303,23 @@ class GnetEngine(object):
         table = torch.tensor(rows, dtype=torch.int32, device=self.device)
         image = torch.zeros(off, dtype=torch.uint8, device=self.device)
         self._ws[key] = (image, table, (pair_off, det_off, pair_b, det_b))
+        self.ws_generation += 1
         return self._ws[key]
+
+    def _tma_images(self):
+        """Swizzled operand images of the TMA-fed pair stage (one per block) + the offset
+        table gn_prepare_pair_tma_image rebuilds them from."""
+        if 'wimg_tma' not in self._ws:
+            nb = self.g['num_blocks']
+            rows = [[self.layout['gnet/block%d/pw_fc1/weights' % b].offset,
+                     self.layout['gnet/block%d/pw_fc2/weights' % b].offset]
+                    for b in range(1, nb + 1)]
+            table = torch.tensor(rows, dtype=torch.int32, device=self.device)
+            image = torch.zeros(nb * ops.pair_tma_image_bytes(), dtype=torch.uint8,
+                                device=self.device)
+            self._ws['wimg_tma'] = (image, table)
+            self.ws_generation += 1
+        return self._ws['wimg_tma']
 
     def _blocks_fused(self, feats, pair_c, pair_n, num_pairs, cap, pw, block_feats):
         """All blocks with two launches each: the tensor-core pair stage and the fused
@@ -288,14 +328,25 @@ class GnetEngine(object):
         operand images prepared by one launch per forward."""
         g, p = self.g, self.p
         T, d = feats.shape
-        if self.bf16 and self.pair_mode != 'pipe':
-            raise ValueError("cfg.gnet.compute_dtype = 'bf16' needs pair_mode 'pipe'")
+        if self.bf16 and self.pair_mode not in ('pipe', 'tma'):
+            raise ValueError("cfg.gnet.compute_dtype = 'bf16' needs pair_mode 'tma' or 'pipe'")
         ab_mode = self.pair_mode == 'ab'
+        tma_mode = self._tma_path()
+        if self.pair_mode == 'tma' and not tma_mode:
+            raise ValueError("pair_mode 'tma' needs the fused pair-feature MLP (shipped shapes)")
         pooled = self._buf('pooled', (T, g['pairfeat_dim']))
         pooled.zero_()   # every det launch re-zeroes it; this covers a dirty workspace
-        if ab_mode:
+        if ab_mode or tma_mode:
             inter = self._buf('ab', (T, 2 * g['pairfeat_dim']))
-        else:
+        if tma_mode:
+            # reduced features as bf16 (hi | lo) rows + the all-zero row a self pair gathers
+            red_all = self._buf('red_hl', (T + 1, 2 * g['reduced_dim']), torch.bfloat16)
+            red_all[T].zero_()
+            inter_hl = red_all[:T]
+            tma_image, tma_table = self._tma_images()
+            ops.prepare_pair_tma_image(self.flat, tma_table, tma_image)
+            tma_b = ops.pair_tma_image_bytes()
+        elif not ab_mode:
             inter = self._buf('red_hl', (T, 2 * g['reduced_dim']), torch.bfloat16)
         image, table, (pair_off, det_off, pair_b, det_b) = self._operand_images()
         ops.prepare_operands(self.flat, table, image)
@@ -310,15 +361,20 @@ class GnetEngine(object):
                 pooled_in, feats_in, image[det_off[b]:det_off[b] + det_b],
                 p[s + 'fc1/biases'] if b >= 1 else None, p[s + 'fc2/biases'] if b >= 1 else None,
                 None if last else p[nxt + 'reduce_dim/biases'], feats_out=out,
-                red_hl=None if (last or ab_mode) else inter,
-                b_ab=p[nxt + 'pw_fc1/biases'] if (ab_mode and not last) else None,
-                ab_out=inter if (ab_mode and not last) else None, bf16=self.bf16)
+                red_hl=None if (last or ab_mode) else (inter_hl if tma_mode else inter),
+                b_ab=p[nxt + 'pw_fc1/biases'] if ((ab_mode or tma_mode) and not last) else None,
+                ab_out=inter if ((ab_mode or tma_mode) and not last) else None, bf16=self.bf16)
 
         det(0, None, feats, None)
         for b in range(1, nb + 1):
             s = 'gnet/block%d/' % b
             wimg = image[pair_off[b - 1]:pair_off[b - 1] + pair_b]
-            if ab_mode:
+            if tma_mode:
+                ops.block_pair_fwd_tma(self._pw_hl, red_all, T, inter, pair_c, pair_n, num_pairs,
+                                       cap, p[s + 'pw_fc2/biases'],
+                                       tma_image[(b - 1) * tma_b:b * tma_b], pooled,
+                                       bf16=self.bf16)
+            elif ab_mode:
                 ops.block_pair_fwd_ab(pw, inter, pair_c, pair_n, num_pairs, cap,
                                       p[s + 'pw_fc2/biases'], wimg, pooled)
             elif self.pair_mode == 'pipe':

@@ -123,12 +123,12 @@ _PREP = {}
 
 def pwfeat_mlp_fwd(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, capacity,
                    num_classes, multiplier, w1, b1, w2, b2, w3, b3, out=None, ffma=False,
-                   wprep=None, bf16=False):
+                   wprep=None, bf16=False, out_hl=None, want_f32=True):
     """Fused geometry + 3-layer pair-feature MLP.  Tensor-core kernel by default
     (needs the `wprep` weight-image workspace; one per device is kept here when
     the caller does not pass its own); ffma=True runs the fp32 CUDA-core variant."""
     hidden, out_dim = w2.shape[1], w3.shape[1]
-    if out is None:
+    if out is None and (want_f32 or out_hl is None):
         out = torch.empty((capacity, out_dim), dtype=torch.float32, device=dets.device)
     f32 = torch.float32
     args = [_chk(dets, f32, 'dets'), _chk(scores, f32, 'scores'),
@@ -147,6 +147,14 @@ def pwfeat_mlp_fwd(dets, scores, classes, pair_c, pair_n, pair_iou, num_pairs, c
             _PREP[key] = torch.empty(int(_lib.load().gn_pwfeat_prep_bytes()), dtype=torch.uint8,
                                      device=dets.device)
         wprep = _PREP[key]
+    if out_hl is not None:
+        # bf16 (hi | lo) operand rows [capacity, 64] for gn_block_pair_fwd_tma; the fp32 rows
+        # only when asked for
+        _lib.call('gn_pwfeat_mlp_fwd_hl', *(args + [
+            _chk(wprep, torch.uint8, 'wprep'),
+            _chk(out, f32, 'pw_out') if (want_f32 and out is not None) else None,
+            _chk(out_hl, torch.bfloat16, 'pw_hl'), 1 if bf16 else 0, _stream()]))
+        return out if want_f32 else None
     _lib.call('gn_pwfeat_mlp_fwd_bf16' if bf16 else 'gn_pwfeat_mlp_fwd', *(args + [_chk(wprep, torch.uint8, 'wprep'),
                                              _chk(out, f32, 'pw_out'), _stream()]))
     return out
@@ -291,6 +299,35 @@ def block_pair_fwd_pipe(pw, feats_hl, pair_c, pair_n, num_pairs, capacity, b1, b
               _chk(pair_n, torch.int32, 'pair_n'), _chk(num_pairs, torch.int32, 'num_pairs'),
               int(capacity), _chk(b1, f32, 'b1'), _chk(b2, f32, 'b2'),
               _chk(wimg, torch.uint8, 'wimg'), b2.numel(), _chk(pooled, f32, 'pooled'), _stream())
+    return pooled
+
+
+def pair_tma_image_bytes():
+    return int(_lib.load().gn_block_pair_tma_image_bytes())
+
+
+def prepare_pair_tma_image(flat_params, table, image):
+    """table[num_blocks, 2] int32 (flat offsets of pw_fc1 / pw_fc2 weights) -> the swizzled
+    operand images of gn_block_pair_fwd_tma, one launch for all blocks."""
+    _lib.call('gn_prepare_pair_tma_image', _chk(flat_params, torch.float32, 'flat_params'),
+              _chk(table, torch.int32, 'table'), table.shape[0], _chk(image, torch.uint8, 'image'),
+              _stream())
+
+
+def block_pair_fwd_tma(pw_hl, red_hl, num_dets, u, pair_c, pair_n, num_pairs, capacity, b2, wimg,
+                       pooled, bf16=False):
+    """Pair stage with TMA-fed operands: pw_hl[capacity,64] bf16 (hi|lo) rows, red_hl[T+1,64]
+    bf16 (hi|lo) reduced features with an all-zero row T, u[T,pitch] fp32 = red @ W1[32:64] + b1
+    in its first 64 columns."""
+    if red_hl.shape[0] < num_dets + 1:
+        raise ValueError('red_hl needs %d rows (zero row at the end)' % (num_dets + 1))
+    _lib.call('gn_block_pair_fwd_tma_bf16' if bf16 else 'gn_block_pair_fwd_tma',
+              _chk(pw_hl, torch.bfloat16, 'pw_hl'), _chk(red_hl, torch.bfloat16, 'red_hl'),
+              int(num_dets), _chk(u, torch.float32, 'u'), int(u.shape[1]),
+              _chk(pair_c, torch.int32, 'pair_c'), _chk(pair_n, torch.int32, 'pair_n'),
+              _chk(num_pairs, torch.int32, 'num_pairs'), int(capacity),
+              _chk(b2, torch.float32, 'b2'), _chk(wimg, torch.uint8, 'wimg'),
+              _chk(pooled, torch.float32, 'pooled'), _stream())
     return pooled
 
 
@@ -476,3 +513,15 @@ def selftest_umma(a, w, a_in_tmem=False):
     _lib.call('gn_selftest_umma_ts' if a_in_tmem else 'gn_selftest_umma', _chk(a, torch.float32, 'a'), _chk(w, torch.float32, 'w'),
               _chk(c, torch.float32, 'c'), int(a.shape[1]), _stream())
     return c
+
+
+def selftest_tma(mat, wmat, idx, row0):
+    """Tensor-map TMA conventions (gn_selftest.cu): mat[rows,64] bf16, wmat[64,64] bf16,
+    idx[128] int32 -> (raw dump of the A0 | A1 | B shared-memory tiles as uint8[40960],
+    D[128,64] = (mat[row0:row0+128] + mat[idx]) @ wmat^T)."""
+    dump = torch.zeros(2 * 16384 + 8192, dtype=torch.uint8, device=mat.device)
+    d = torch.zeros((128, 64), dtype=torch.float32, device=mat.device)
+    _lib.call('gn_selftest_tma', _chk(mat, torch.bfloat16, 'mat'), mat.shape[0],
+              _chk(wmat, torch.bfloat16, 'wmat'), _chk(idx, torch.int32, 'idx'), int(row0),
+              _chk(dump, torch.uint8, 'dump'), _chk(d, torch.float32, 'd'), _stream())
+    return dump, d

@@ -89,8 +89,13 @@ class InferenceSession(object):
 
     # ------------------------------------------------------------------- forward
     def _forward(self, buf):
-        res = self.engine.forward(buf.d_dets, buf.d_scores, buf.d_cls, buf.d_off,
-                                  max_img=self._max_img)
+        eng = self.engine
+        keep, eng.want_pw_f32 = eng.want_pw_f32, False    # logits only: no fp32 pw_feats copy
+        try:
+            res = eng.forward(buf.d_dets, buf.d_scores, buf.d_cls, buf.d_off,
+                              max_img=self._max_img)
+        finally:
+            eng.want_pw_f32 = keep
         self._pred, self._num_pairs, self._cap = res['prediction'], res['num_pairs'], res['capacity']
 
     def _warm(self, buf):
@@ -148,6 +153,11 @@ class InferenceSession(object):
         if len(self._seen) > 4096:           # variable-size data: do not grow without bound
             self._seen.clear()
         state = self._states.get(key)
+        if state is not None and state[3] != self.engine.ws_generation:
+            # the engine reallocated part of its workspace since this graph was captured (a
+            # larger batch came through): the graph holds pointers into freed memory - drop it
+            del self._states[key]
+            state = None
         want_graph = self.use_graph and (state is not None or self._seen[key] >= self.graph_after)
         if want_graph and state is None:
             buf = _Buffers(T, B, self.device)
@@ -165,7 +175,7 @@ class InferenceSession(object):
             with torch.cuda.stream(self.stream):
                 if want_graph and state is None:
                     buf.d_in[:buf.copy_bytes].copy_(buf.h_in[:buf.copy_bytes], non_blocking=True)
-                    state = (buf,) + self._capture(buf)
+                    state = (buf,) + self._capture(buf) + (self.engine.ws_generation,)
                     self._states[key] = state
                     while len(self._states) > self.MAX_GRAPHS:
                         self._states.popitem(last=False)

@@ -391,6 +391,48 @@ int gn_selftest_umma_ts(const float* a, const float* w, float* c, int k, gn_stre
 int gn_selftest_umma_rate(int n, int reps, int distinct_b, int ctas, int64_t* out_dev,
                           gn_stream_t stream);
 
+/* Tensor-map TMA conventions used by gn_block_pair_fwd_tma (no reference counterpart):
+ * mat[rows,64] bf16, wmat[64,64] bf16, idx[128] int32 row indices.  dump[40960] = raw
+ * shared-memory bytes of (tile load of rows row0..row0+127 | gather4 of rows idx | wmat)
+ * in the SWIZZLE_128B layout; d_out[128,64] = (mat[row0:row0+128] + mat[idx]) @ wmat^T. */
+int gn_selftest_tma(const void* mat_bf16, int rows, const void* wmat_bf16, const int32_t* idx,
+                    int row0, void* dump, float* d_out, gn_stream_t stream);
+
+/* ---- A7 pair stage, TMA-fed (gn_block_tma.cu) ----------------------------------------
+ * Same contract as gn_block_pair_fwd_pipe (network.py:367-388: gather/concat, pw_fc1,
+ * pw_fc2, segment_max -> atomic max into pooled[T,64], which the caller zeroed), other
+ * operand formats:
+ *   pw_hl[capacity,64] bf16   pair features as (32 hi | 32 lo) rows (gn_pwfeat_mlp_fwd_hl)
+ *   red_hl[num_dets+1,64] bf16 reduced features as (hi | lo) rows; row num_dets all zero
+ *                             (the self pair's neighbor half, network.py:372-374)
+ *   u[num_dets,u_pitch] f32   first 64 columns: red @ pw_fc1[32:64] + b_pw_fc1 (the
+ *                             detection-level half of pw_fc1; gn_block_det_fwd_img ab_out)
+ *   wimg                      gn_block_pair_tma_image_bytes() bytes of block b's image from
+ *                             gn_prepare_pair_tma_image (table[b] = flat offsets of
+ *                             pw_fc1/weights, pw_fc2/weights)
+ * _bf16: plain bf16 operands (hi parts only), fp32 accumulation. */
+int64_t gn_block_pair_tma_image_bytes(void);
+int gn_prepare_pair_tma_image(const float* flat_params, const int32_t* table, int num_blocks,
+                              void* image, gn_stream_t stream);
+int gn_block_pair_fwd_tma(const void* pw_hl, const void* red_hl, int num_dets, const float* u,
+                          int u_pitch, const int32_t* pair_c, const int32_t* pair_n,
+                          const int32_t* num_pairs, int capacity, const float* b2,
+                          const void* wimg, float* pooled, gn_stream_t stream);
+int gn_block_pair_fwd_tma_bf16(const void* pw_hl, const void* red_hl, int num_dets, const float* u,
+                               int u_pitch, const int32_t* pair_c, const int32_t* pair_n,
+                               const int32_t* num_pairs, int capacity, const float* b2,
+                               const void* wimg, float* pooled, gn_stream_t stream);
+/* gn_pwfeat_mlp_fwd (network.py:324-342, 411-454) writing the pair features as bf16
+ * (hi | lo) operand rows pw_hl[capacity,64]; pw_out (fp32 [capacity,32]) may be null.
+ * plain_bf16 != 0: the bf16 arithmetic of gn_pwfeat_mlp_fwd_bf16. */
+int gn_pwfeat_mlp_fwd_hl(const float* dets, const float* scores, const int32_t* classes,
+                         const int32_t* pair_c, const int32_t* pair_n, const float* pair_iou,
+                         const int32_t* num_pairs, int capacity, int num_classes,
+                         float multiplier, const float* w1, const float* b1, const float* w2,
+                         const float* b2, const float* w3, const float* b3, int hidden,
+                         int out_dim, void* wprep, float* pw_out, void* pw_hl, int plain_bf16,
+                         gn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

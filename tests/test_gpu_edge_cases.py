@@ -98,6 +98,28 @@ def test_stress_n10000_properties():
     assert np.array_equal(both['prediction'].cpu().numpy()[off[1]:off[2]], pred)
 
 
+@pytest.mark.parametrize('mode', ['tma', 'pipe'])
+def test_stress_n10000_against_oracle(mode):
+    """configs[4] against the CPU oracle itself (numpy handles 10 000^2 fp32): pair index
+    lists and the pairs' IoU bits identical, logits within 1e-4 (network.py:474-511, 192-195)."""
+    load_experiment('coco_person', num_blocks=2)
+    net = Gnet(1)
+    net.engine.pair_mode = mode
+    img = {k: synthetic.make_image(10000, 1, image_index=0)[k] for k in KEYS}
+    pred = net(img).cpu().numpy().copy()
+    layout, _ = P.param_layout(1, cfg)
+    ref = gnet_oracle.gnet_forward(img, P.views(layout, net.engine.flat.cpu().numpy()), cfg, 1)
+    assert np.array_equal(net.neighbor_pair_idxs.cpu().numpy(), ref['neighbor_pair_idxs'])
+    Pn = ref['neighbor_pair_idxs'].shape[0]
+    d = img['dets']
+    bd = gnet_oracle.xyxy_to_boxdata(d)
+    c, n = ref['neighbor_pair_idxs'][:, 0], ref['neighbor_pair_idxs'][:, 1]
+    want_iou = gnet_oracle.iou(bd, bd)[c, n]
+    got_iou = net._res['pair_iou'][:Pn].cpu().numpy()
+    assert np.array_equal(got_iou.view(np.uint32), want_iou.view(np.uint32))
+    assert rel_err(pred, ref['prediction']) < 1e-4
+
+
 def test_multiclass_matching_respects_classes(oracle_built):
     """Multi-class det/GT overlaps are zeroed across classes (network.py:177-187), so a
     detection can only match a ground truth of its own class."""

@@ -38,7 +38,7 @@ def check_against(net, ref, with_loss=True):
 
 
 @pytest.mark.parametrize('name', CASES)
-@pytest.mark.parametrize('fused', ['pipe', 'ab', 'hl', False])
+@pytest.mark.parametrize('fused', ['tma', 'pipe', 'ab', 'hl', False])
 def test_forward_matches_reference_golden(name, fused):
     g, num_classes, layout, flat, img = setup_case(name)
     net = Gnet(num_classes, class_weights=g['class_weights'], params=flat)
@@ -62,7 +62,8 @@ def test_forward_matches_reference_golden(name, fused):
 @pytest.mark.parametrize('n,blocks,exp,C', [(300, 2, 'coco_person', 1),       # BASELINE configs[0]
                                             (1000, 16, 'coco_person', 1),     # configs[1]
                                             (2000, 16, 'coco_multiclass', 80)])  # configs[2] (fp32)
-def test_forward_matches_oracle_at_baseline_configs(n, blocks, exp, C, oracle_built):
+@pytest.mark.parametrize('mode', ['tma', 'pipe'])
+def test_forward_matches_oracle_at_baseline_configs(n, blocks, exp, C, mode, oracle_built):
     load_experiment(exp, num_blocks=blocks)
     layout, total = P.param_layout(C, cfg)
     flat = P.init_flat(layout, total, cfg, seed=11)
@@ -70,8 +71,17 @@ def test_forward_matches_oracle_at_baseline_configs(n, blocks, exp, C, oracle_bu
     ref = gnet_oracle.gnet_forward(img, P.views(layout, flat), cfg, C,
                                    matching_fn=det_matching_oracle.detection_matching)
     net = Gnet(C, params=flat)
+    net.engine.pair_mode = mode
     net(img)
     check_against(net, ref)
+    # per-logit relative error next to the max-normalised criterion (informational bound:
+    # logits near zero make it arbitrarily large, so it is reported for |ref| > 0.1 max|ref|)
+    pred, r = net.prediction.cpu().numpy().astype(np.float64), ref['prediction'].astype(np.float64)
+    big = np.abs(r) > 0.1 * np.max(np.abs(r))
+    per_elem = float(np.max(np.abs(pred - r)[big] / np.abs(r)[big]))
+    print('config N=%d C=%d mode=%s: max-normalised %.2e, per-element (|ref|>10%% max) %.2e'
+          % (n, C, mode, rel_err(pred, r), per_elem))
+    assert per_elem < 1e-3
 
 
 def test_batched_forward_equals_per_image():

@@ -32,6 +32,22 @@ def test_det_det_iou_bit_exact(n):
     assert np.array_equal(got, got.T)
 
 
+@pytest.mark.parametrize('n', [128, 129, 1000, 1003, 4000, 10000])
+def test_symmetric_iou_kernel_bit_exact(n):
+    """The SAME tensor on both sides selects iou_symmetric_kernel (gn_iou.cu: upper-triangle
+    tiles computed once, stored twice) - the kernel `roofline_iou` is quoted on.  Bit-exact
+    against the oracle (network.py:474-511) up to the stress size."""
+    t = dev(synthetic.make_image(n, 1, image_index=n)['dets'])
+    got = ops.iou_dense(t, t).cpu().numpy()
+    d = t.cpu().numpy()
+    ref = go.iou(go.xyxy_to_boxdata(d), go.xyxy_to_boxdata(d))
+    assert np.array_equal(bits(got), bits(ref))
+    del ref
+    assert np.all(np.diag(got) == 1.0)
+    # and the general kernel (two buffers) gives the same bits
+    assert np.array_equal(bits(ops.iou_dense(t, t.clone()).cpu().numpy()), bits(got))
+
+
 def test_iou_known_answers():
     d = np.array([[0, 0, 10, 10], [5, 0, 15, 10], [100, 100, 110, 120]], F32)
     got = ops.iou_dense(dev(d), dev(d)).cpu().numpy()
