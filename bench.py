@@ -52,6 +52,10 @@ def parse():
                     help='budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--quick', action='store_true',
+                    help='skip the extra keys (configs[2], store ceiling)')
+    ap.add_argument('--pair-mode', default=None, choices=['tma', 'pipe', 'hl', 'ab'],
+                    help='pair-stage kernel (default: the engine default, tma)')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'],
                     help="arithmetic of the fused FC kernels: fp32 semantics (bf16x3, the "
                          "headline) or plain bf16 operands (BASELINE configs[2]'s arithmetic)")
@@ -245,6 +249,205 @@ class ClockSampler(object):
 
 
 # ------------------------------------------------------------------------- B200
+def _events(torch, stream, fn, reps, before=None):
+    """CUDA-event times (ms) of `fn` on `stream`, `before` (untimed) ahead of every rep."""
+    out = []
+    for _ in range(reps):
+        if before is not None:
+            before()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        stream.synchronize()
+        out.append(a.elapsed_time(b))
+    return out
+
+
+def _load_json(name):
+    try:
+        return json.load(open(os.path.join(ROOT, name)))
+    except Exception:
+        return {}
+
+
+def kernel_rooflines(torch, ops, eng, sess, stream, flush, P, T, blocks, bf16, peaks, peak_src,
+                     num_classes=1):
+    """The three tcgen05 kernels of the step, each timed alone with CUDA events on the
+    operands the last forward left in the workspace (L2 flushed before every launch).
+    A kernel timed in isolation is quoted against the BURST bf16 peak."""
+    burst = float(peaks.get('bf16_tflops', 1590.0))
+    ncu = _load_json('profiles/r2_ncu_traffic.json')      # dram bytes per launch from ncu --set full
+    eng.want_pw_f32 = not eng._tma_path()
+    res = eng.forward(sess.d_dets, sess.d_scores, sess.d_cls, sess.d_off, max_img=sess._max_img)
+    eng.want_pw_f32 = True
+    cap = res['capacity']
+    p = eng.p
+    note = ('plain bf16 operands: one tensor flop per algorithmic flop' if bf16 else
+            'fp32 semantics via bf16x3: 3 tensor flops issued per algorithmic flop, so 0.333 is '
+            'the ceiling of this fraction')
+    src = '%s bf16 burst %.1f TF/s (kernel timed alone). %s' % (peak_src, burst, note)
+
+    def entry(kernel, ms, flops, launches, traffic_key, extra=None):
+        tf = flops / (ms * 1e-3) / 1e12
+        traffic = ncu.get(traffic_key)
+        if traffic is not None and 'per_pair' in str(traffic_key):
+            traffic = traffic * P
+        e = {'kernel': kernel, 'bound': 'tensor', 'achieved': tf, 'peak': burst, 'unit': 'TFLOP/s',
+             'frac': tf / burst, 'traffic': traffic, 'ms_per_launch': ms,
+             'launches_per_step': launches, 'algorithmic_flops_per_launch': flops,
+             'peak_source': src}
+        if extra:
+            e.update(extra)
+        return e
+
+    med = lambda t: float(np.median(t[2:]))
+    out = {}
+    pre = lambda: flush.zero_()
+    # ---- block pair stage (dominant kernel) ----------------------------------------
+    pooled = eng._buf('pooled', (T, 64))
+    s1 = 'gnet/block1/'
+    if eng._tma_path():
+        red_all = eng._ws['red_hl'][:(T + 1) * 64].view(T + 1, 64)
+        ab = eng._ws['ab'][:T * 128].view(T, 128)
+        image, _ = eng._tma_images()
+        tb = ops.pair_tma_image_bytes()
+
+        def pair():
+            ops.block_pair_fwd_tma(eng._pw_hl, red_all, T, ab, res['pair_c'], res['pair_n'],
+                                   res['num_pairs'], cap, p[s1 + 'pw_fc2/biases'], image[:tb],
+                                   pooled, bf16=bf16)
+        name = 'block_pair_tma_kernel'
+    else:
+        red = eng._ws['red_hl'][:T * 64].view(T, 64)
+        image, _, (pair_off, _, pair_b, _) = eng._operand_images()
+        wimg = image[pair_off[0]:pair_off[0] + pair_b]
+
+        def pair():
+            ops.block_pair_fwd_pipe(res['pw_feats'], red, res['pair_c'], res['pair_n'],
+                                    res['num_pairs'], cap, p[s1 + 'pw_fc1/biases'],
+                                    p[s1 + 'pw_fc2/biases'], wimg, pooled, bf16=bf16)
+        name = 'block_pair_pipe_kernel'
+    ms = med(_events(torch, stream, pair, 10, before=lambda: (flush.zero_(), pooled.zero_())))
+    out['roofline'] = entry(name, ms, 20480.0 * P, blocks, 'pair_dram_bytes_per_pair',
+                            {'algorithmic_flops_per_pair': 20480,
+                             'traffic_source': 'dram__bytes_read+write of one launch, ncu --set full '
+                                               '(profiles/r2_ncu_traffic.json), scaled by P'})
+    # ---- pair-feature MLP ------------------------------------------------------------
+    if eng.fused_pw:
+        w = [p[('gnet/pw_feats/fc%d/' % i) + k] for i in (1, 2, 3) for k in ('weights', 'biases')]
+        hl = eng._buf('pw_hl', (cap, 64), torch.bfloat16)
+
+        def pwfeat():
+            ops.pwfeat_mlp_fwd(sess.d_dets, sess.d_scores, sess.d_cls if num_classes > 1 else None,
+                               res['pair_c'], res['pair_n'], res['pair_iou'], res['num_pairs'], cap,
+                               num_classes, 1.0, *w, out=None, wprep=eng._ws['wprep'], bf16=bf16,
+                               out_hl=hl, want_f32=False)
+        ms = med(_events(torch, stream, pwfeat, 8, before=pre))
+        # 2 (w_raw 256 + 256 256 + 256 32) flop per pair, w_raw = 9 or 2C+7 (SURVEY.md 8d)
+        w_raw = 9 if num_classes == 1 else 2 * num_classes + 7
+        out['roofline_pwfeat'] = entry('pwfeat_pipe_kernel', ms,
+                                       2.0 * (w_raw * 256 + 256 * 256 + 256 * 32) * P, 1,
+                                       'pwfeat_dram_bytes_per_pair')
+    # ---- detection-level kernel ---------------------------------------------------------
+    if eng.fused_det and blocks >= 2:
+        image, _, (_, det_off, _, det_b) = eng._operand_images()
+        feats = eng._buf('feats0', (T, 128))
+        outb = eng._buf('feats1', (T, 128))
+        inter = eng._ws['red_hl'][:T * 64].view(T, 64)
+        ab = eng._buf('ab', (T, 128)) if eng._tma_path() else None
+
+        def det():
+            ops.block_det_fwd_img(pooled, feats, image[det_off[1]:det_off[1] + det_b],
+                                  p['gnet/block1/fc1/biases'], p['gnet/block1/fc2/biases'],
+                                  p['gnet/block2/reduce_dim/biases'], feats_out=outb, red_hl=inter,
+                                  b_ab=p['gnet/block2/pw_fc1/biases'] if ab is not None else None,
+                                  ab_out=ab, bf16=bf16)
+        ms = med(_events(torch, stream, det, 10, before=pre))
+        out['roofline_det'] = entry('block_det_tc_kernel', ms, 32768.0 * T, blocks + 1,
+                                    'det_dram_bytes_per_launch')
+    return out
+
+
+def iou_sweep(torch, ops, stream, hbm_peak, peak_src, sizes=(1000, 2000, 4000, 8000, 10000)):
+    """Dense det x det IoU (network.py:474-511) at the sizes of SURVEY.md 8(d): B images per
+    launch so that >= 256 MB are written; algorithmic bytes 4 N^2 + 32 N per image."""
+    from gossipnet_b200 import synthetic
+    ncu = _load_json('profiles/r2_ncu_traffic.json').get('iou_dram_bytes', {})
+    rows = []
+    for n in sizes:
+        b = max(1, int(np.ceil((256 << 20) / (4.0 * n * n))))
+        d = torch.from_numpy(np.stack([synthetic.make_image(n, 1, image_index=i)['dets']
+                                       for i in range(min(b, 4))])).cuda()
+        d = d.repeat((b + d.shape[0] - 1) // d.shape[0], 1, 1)[:b].contiguous()
+        out = torch.empty((b, n, n), device='cuda')
+        t = _events(torch, stream, lambda: ops.iou_dense(d, d, out=out), 8)
+        ms = float(np.median(t[2:]))
+        nbytes = b * (4.0 * n * n + 32.0 * n)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        rows.append({'n': n, 'images_per_launch': b, 'bytes': nbytes, 'ms_per_launch': ms,
+                     'achieved': gbs, 'frac': gbs / hbm_peak, 'traffic': ncu.get(str(n))})
+        del out, d
+    return rows
+
+
+def store_ceiling(torch, ops, stream):
+    """Sustained pure-store bandwidth of this GPU with the library's own best store kernel
+    (gn_selftest_store_bw: 256-bit st.global, evict-first), 1 GiB, next to cudaMemset."""
+    n = 1 << 30
+    buf = torch.empty(n, dtype=torch.uint8, device='cuda')
+    res = {}
+    if hasattr(ops, 'selftest_store_bw'):
+        for mode in ops.STORE_BW_MODES:
+            t = _events(torch, stream, lambda: ops.selftest_store_bw(buf, mode), 5)
+            res[mode] = n / (min(t[1:]) * 1e-3) / 1e9
+    t = _events(torch, stream, lambda: buf.zero_(), 5)
+    res['cudaMemset'] = n / (min(t[1:]) * 1e-3) / 1e9
+    del buf
+    return res
+
+
+def run_config2(torch, ops, stream, flush, peaks, peak_src, steps, warmup):
+    """BASELINE configs[2]: coco_multiclass (80 classes), N = 2000 detections per image,
+    16 blocks, plain-bf16 operands; 16 images per step.  Not the headline: an extra key."""
+    from gossipnet_b200.nms_net.config import cfg, cfg_from_file, reset_cfg
+    from gossipnet_b200.nms_net.network import Gnet
+    from gossipnet_b200.session import InferenceSession
+    from gossipnet_b200 import synthetic
+    reset_cfg()
+    cfg_from_file(os.path.join(ROOT, 'experiments', 'coco_multiclass', 'conf.yaml'))
+    cfg.gnet.compute_dtype = 'bf16'
+    B, N, C = 16, 2000, 80
+    imgs = [synthetic.make_image(N, C, seed=42, image_index=i) for i in range(B)]
+    dets = np.concatenate([im['dets'] for im in imgs]).astype(np.float32)
+    scores = np.concatenate([im['det_scores'] for im in imgs]).astype(np.float32)
+    classes = np.concatenate([im['det_classes'] for im in imgs]).astype(np.int32)
+    img_off = (np.arange(B + 1) * N).astype(np.int32)
+    net = Gnet(C)
+    sess = InferenceSession(net)
+    sess.stream = stream
+    for _ in range(max(warmup, 3)):
+        sess.run(dets, scores, classes, img_off)
+    P = int(sess.h_np[0])
+    with torch.cuda.stream(stream):
+        t = _events(torch, stream, lambda: sess._graph.replay() if sess._graph else sess._forward(sess._cur),
+                    steps, before=lambda: flush.zero_())
+        ms = float(np.mean(t))
+        roofs = kernel_rooflines(torch, ops, net.engine, sess, stream, flush, P, B * N,
+                                 cfg.gnet.num_blocks, True, peaks, peak_src, num_classes=C)
+    r, rp = roofs['roofline'], roofs.get('roofline_pwfeat')
+    # the C = 80 pair-feature MLP: 232 960 flop per pair (2C+7 = 167 raw features)
+    reset_cfg()
+    return {'workload': 'coco_multiclass 80 classes, N=2000 dets/image, 16 blocks, plain bf16 '
+                        'operands + fp32 accumulation (BASELINE configs[2]); %d images per step' % B,
+            'value': B * N / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
+            'pairs_per_step': P, 'dtype': 'bf16',
+            'roofline': {k: r[k] for k in ('kernel', 'achieved', 'peak', 'unit', 'frac',
+                                           'ms_per_launch', 'peak_source')},
+            'roofline_pwfeat': None if rp is None else
+            {k: rp[k] for k in ('kernel', 'achieved', 'peak', 'unit', 'frac', 'ms_per_launch')}}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -265,19 +468,16 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     cfg = setup_cfg(args.blocks, args.precision)
     bf16 = args.precision == 'bf16'
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except Exception:
-        pass
+    peaks = _load_json('MEASURED_PEAKS.json')
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    bf16_peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
     peak_src = 'measured' if peaks else 'fallback'
 
     B, N = args.images, args.n_dets
     imgs, dets, scores, classes, img_off = make_inputs(B, N, first_index=rank * B)
     net = Gnet(1)
     eng = net.engine
+    if args.pair_mode:
+        eng.pair_mode = args.pair_mode
     sess = InferenceSession(net, use_graph=not args.no_graph)
     T = dets.shape[0]
 
@@ -326,101 +526,50 @@ def run_b200(args):
         e2e_s = time.perf_counter() - t0
     clk = clocks.summary()
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device='cuda')
+    pstat = torch.tensor([float(P), -float(P)], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pstat, op=dist.ReduceOp.MAX)    # max P, -min P over the ranks' shards
     dev_ms, e2e_ms = float(t[0]), float(t[1])
+    p_max, p_min = int(pstat[0]), int(-pstat[1])
     total_dets = world * B * N * args.steps
     value = total_dets / (dev_ms * 1e-3)
     e2e_value = total_dets / (e2e_ms * 1e-3)
 
-    # ---- roofline: the dominant kernel, timed live (un-graphed, events per launch)
-    roof = roof_iou = None
+    # ---- rooflines: the tensor-core kernels timed live (un-graphed, events per launch) --
+    roofs, sweep, extra2, stores = {}, None, None, None
     if rank == 0:
         with torch.cuda.stream(stream):
-            res = eng.forward(sess.d_dets, sess.d_scores, sess.d_cls, sess.d_off)
-            # the operands exactly as the forward leaves them: bf16 (hi | lo) reduced
-            # features of the last block, fp32 pw_feats, the pair lists, block 1's operand image
-            red = eng._ws['red_hl'][:T * 64].view(T, 64)
-            pooled = eng._buf('pooled', (T, 64))
-            s1 = 'gnet/block1/'
-            image, _, (pair_off, _, pair_b, _) = eng._operand_images()
-            wimg = image[pair_off[0]:pair_off[0] + pair_b]
-            times = []
-            for rep in range(8):
-                flush.zero_()
-                pooled.zero_()
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                ops.block_pair_fwd_pipe(res['pw_feats'], red, res['pair_c'], res['pair_n'],
-                                        res['num_pairs'], res['capacity'],
-                                        eng.p[s1 + 'pw_fc1/biases'], eng.p[s1 + 'pw_fc2/biases'],
-                                        wimg, pooled, bf16=bf16)
-                b.record(stream)
-                stream.synchronize()
-                times.append(a.elapsed_time(b))
-            k_ms = float(np.median(times[2:]))
-        flops = 20480.0 * P  # 2*(96*64 + 64*64) per pair
-        roof = {'kernel': 'block_pair_pipe_kernel', 'bound': 'tensor',
-                'achieved': flops / (k_ms * 1e-3) / 1e12, 'peak': bf16_peak, 'unit': 'TFLOP/s',
-                'frac': flops / (k_ms * 1e-3) / 1e12 / bf16_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on
-                # this workload (ncu --set full, profiles/r1_tc_kernels.md); scales with P
-                'traffic': 378.9e6 * (P / 2486884.0),
-                'ms_per_launch': k_ms, 'launches_per_step': args.blocks,
-                'algorithmic_flops_per_launch': flops,
-                'peak_source': '%s bf16 sustained %.1f TF/s (kernel timed inside a long step). %s'
-                               % (peak_src, bf16_peak,
-                                  'plain bf16 operands: one tensor flop per algorithmic flop' if bf16
-                                  else 'fp32 semantics via bf16x3: the kernel issues 3 tensor flops '
-                                       'per algorithmic flop, so 0.333 is the ceiling of this fraction')}
-        # dense IoU kernel at the stress size (N=10000 -> 400 MB written, > L2)
-        with torch.cuda.stream(stream):
-            n_iou = 10000
-            from gossipnet_b200 import synthetic
-            big = torch.from_numpy(synthetic.make_image(n_iou, 1)['dets']).cuda()
-            out = torch.empty((1, n_iou, n_iou), device='cuda')
-            times = []
-            for rep in range(8):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                ops.iou_dense(big.unsqueeze(0), big.unsqueeze(0), out=out)
-                b.record(stream)
-                stream.synchronize()
-                times.append(a.elapsed_time(b))
-            i_ms = float(np.median(times[2:]))
-            del out
-            # context for a write-only kernel: sustained pure-store bandwidth of this GPU
-            # (2 GiB memset, >> L2), next to the copy peak the fraction is quoted against
-            wbuf = torch.empty(1 << 31, dtype=torch.uint8, device='cuda')
-            wt = []
-            for rep in range(4):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(stream)
-                wbuf.zero_()
-                b.record(stream)
-                stream.synchronize()
-                wt.append(a.elapsed_time(b))
-            write_peak = (1 << 31) / (min(wt[1:]) * 1e-3) / 1e9
-            del wbuf
-        iou_bytes = 4.0 * n_iou * n_iou + 16.0 * 2 * n_iou
-        roof_iou = {'kernel': 'iou_symmetric_kernel', 'bound': 'hbm',
-                    'achieved': iou_bytes / (i_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': iou_bytes / (i_ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
-                    'ms_per_launch': i_ms, 'workload': 'N=M=%d, one image' % n_iou,
+            roofs = kernel_rooflines(torch, ops, eng, sess, stream, flush, P, T, args.blocks, bf16,
+                                     peaks, peak_src)
+            sweep = iou_sweep(torch, ops, stream, hbm_peak, peak_src)
+            if world == 1 and not args.quick:
+                stores = store_ceiling(torch, ops, stream)
+    roof_iou = None
+    if sweep:
+        big = sweep[-1]
+        roof_iou = {'kernel': 'iou_symmetric_kernel', 'bound': 'hbm', 'achieved': big['achieved'],
+                    'peak': hbm_peak, 'unit': 'GB/s', 'frac': big['frac'], 'traffic': big['traffic'],
+                    'ms_per_launch': big['ms_per_launch'],
+                    'workload': 'N=M=%d, one image' % big['n'],
                     'peak_source': peak_src + ' copy bandwidth (read+write)',
-                    'write_only_peak_measured_here': write_peak,
-                    'frac_of_write_only_peak': iou_bytes / (i_ms * 1e-3) / 1e9 / write_peak}
+                    'sweep': sweep, 'store_ceiling_gbs': stores}
 
     # ---- CPU baseline on this box's cores (rank 0, N=1) ---------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, n_img, dt = cpu_forward_rate(cfg, N, args.cpu_seconds)
         cpu = {'value': rate, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-               'sample': '%d images x N=%d, one image per call, %.1f s; numpy float32 restatement '
-                         'of the reference (oracle/gnet_oracle.py)' % (n_img, N, dt)}
+               'sample': '%d images x N=%d, one image per call, %.1f s, %s BLAS threads; numpy '
+                         'float32 restatement of the reference (oracle/gnet_oracle.py)'
+                         % (n_img, N, dt, blas_threads())}
+    # ---- BASELINE configs[2] (extra key; single GPU, default run) -------------------
+    if rank == 0 and world == 1 and not args.quick and not bf16:
+        extra2 = run_config2(torch, ops, stream, flush, peaks, peak_src, max(5, args.steps // 2),
+                             args.warmup)
 
     if rank == 0:
-        print(json.dumps({
+        line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16' if bf16 else 'f32',
@@ -432,6 +581,8 @@ def run_b200(args):
                                       'fp32 in/out; FC GEMMs as bf16 hi/lo split products '
                                       '(bf16x3) on tcgen05 with fp32 TMEM accumulation'),
                        'images_per_gpu_per_step': B, 'pairs_per_step_rank0': P,
+                       'pairs_per_step_min_max_over_ranks': [p_min, p_max],
+                       'pair_mode': eng.pair_mode,
                        'parallelism': 'images sharded over %d GPU(s), no data-path collective'
                                       % world,
                        'l2': 'flushed between timed steps (256 MiB memset); working set also '
@@ -441,9 +592,12 @@ def run_b200(args):
                     'd2h_bytes_per_step': sess.d2h_bytes, 'ms_per_step': e2e_ms / args.steps,
                     'api': 'gossipnet_b200.session.InferenceSession.run (numpy in/out)'},
             'gpu_launches': launches * args.steps,
-            'clocks': clk, 'roofline': roof, 'roofline_iou': roof_iou, 'cpu_baseline': cpu,
+            'clocks': clk, 'roofline': roofs.get('roofline'),
+            'roofline_pwfeat': roofs.get('roofline_pwfeat'), 'roofline_det': roofs.get('roofline_det'),
+            'roofline_iou': roof_iou, 'cpu_baseline': cpu, 'config2_coco_multiclass_bf16': extra2,
             'logit_checksum': float(np.sum(pred, dtype=np.float64)),
-        }))
+        }
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

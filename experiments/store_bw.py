@@ -1,18 +1,41 @@
-"""Pure-store bandwidth reference for the dense IoU kernel (write-only, 400 MB)."""
-import torch
-x = torch.empty(100_000_000, dtype=torch.float32, device='cuda')
-y = torch.empty_like(x)
-def t(fn, n=10):
-    fn(); torch.cuda.synchronize()
-    best = 1e9
-    for _ in range(n):
+"""Pure-store bandwidth of one B200 with hand-written kernels (gn_selftest_store_bw) next to
+cudaMemset, and the dense IoU kernels at the same sizes: is the IoU kernel at the hardware's
+store ceiling?"""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gossipnet_b200 import ops, synthetic
+
+
+def t_ms(fn, reps=6, inner=1):
+    out = []
+    for _ in range(reps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); fn(); b.record(); torch.cuda.synchronize()
-        best = min(best, a.elapsed_time(b))
-    return best
-ms = t(lambda: x.zero_()); print('zero_ 400MB: %.3f ms  %.0f GB/s (write only)' % (ms, 0.4 / ms * 1e3))
-ms = t(lambda: x.fill_(1.5)); print('fill_ 400MB: %.3f ms  %.0f GB/s (write only)' % (ms, 0.4 / ms * 1e3))
-ms = t(lambda: y.copy_(x)); print('copy 400MB: %.3f ms  %.0f GB/s (read+write)' % (ms, 0.8 / ms * 1e3))
-big = torch.empty(1 << 30, dtype=torch.bfloat16, device='cuda'); big2 = torch.empty_like(big)
-ms = t(lambda: big2.copy_(big)); print('copy 2GiB: %.3f ms  %.0f GB/s (read+write)' % (ms, 4.295 / ms * 1e3))
-ms = t(lambda: big.zero_()); print('zero_ 2GiB: %.3f ms  %.0f GB/s (write only)' % (ms, 2.147 / ms * 1e3))
+        a.record()
+        for _ in range(inner):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        out.append(a.elapsed_time(b) / inner)
+    return min(out[1:])
+
+
+for size in (400 << 20, 1 << 30, 2 << 30):
+    buf = torch.empty(size, dtype=torch.uint8, device='cuda')
+    row = ['%5d MiB' % (size >> 20)]
+    row.append('memset %.0f' % (size / t_ms(lambda: buf.zero_()) / 1e6))
+    for mode in ops.STORE_BW_MODES:
+        best = max((size / t_ms(lambda: ops.selftest_store_bw(buf, mode, c)) / 1e6, c)
+                   for c in (2, 4, 8, 16))
+        row.append('%s %.0f (x%d)' % (mode, best[0], best[1]))
+    print(' | '.join(row), flush=True)
+    del buf
+for n in (10000,):
+    d = torch.from_numpy(synthetic.make_image(n, 1)['dets']).cuda()
+    out = torch.empty((1, n, n), device='cuda')
+    nbytes = 4.0 * n * n
+    du = d.unsqueeze(0)
+    print('iou symmetric N=%d: %.0f GB/s (one launch per event pair), %.0f GB/s (8 launches per pair)' % (
+        n, nbytes / t_ms(lambda: ops.iou_dense(du, du, out=out)) / 1e6,
+        nbytes / t_ms(lambda: ops.iou_dense(du, du, out=out), inner=8) / 1e6))
+    d2 = d.clone()
+    print('iou general   N=%d: %.0f GB/s' % (n, nbytes / t_ms(lambda: ops.iou_dense(d.unsqueeze(0), d2.unsqueeze(0), out=out)) / 1e6))

@@ -111,6 +111,7 @@ SIGNATURES = {
     'gn_block_pair_fwd_tma_bf16': [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                    c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'gn_selftest_tma': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    'gn_selftest_store_bw': [c_void_p, ctypes.c_int64, c_int, c_int, c_void_p],
     'gn_selftest_umma': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     'gn_selftest_umma_ts': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     'gn_selftest_umma_rate': [c_int, c_int, c_int, c_int, c_void_p, c_void_p],

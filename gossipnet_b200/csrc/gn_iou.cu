@@ -14,8 +14,6 @@
 // positive union the quotient (+0) is produced by a select instead; every other
 // case (including zero / NaN unions of degenerate boxes) goes through the exact
 // __fdiv_rn, so results stay bit-identical to the reference arithmetic.
-#include <stdlib.h>
-
 #include "gn_common.cuh"
 
 namespace gn {
@@ -107,27 +105,30 @@ iou_dense_kernel(const float* __restrict__ a, const float* __restrict__ b,
 // A CTA computes one 64 x 64 tile of the upper triangle (tile row I <= tile column J),
 // stores it, and stores its transpose into tile (J, I) through a shared-memory
 // transposition so both stores are coalesced 256-byte row segments.
+// The transposition goes through shared memory as 16-byte units in an XOR-swizzled 16 x 16
+// block grid (conflict free both ways); the first version's scalar transposed stores were
+// 4-way bank conflicted and made the kernel L1-bound (profiles/r2_iou.md).
 // ---------------------------------------------------------------------------------
 constexpr int SYM_T = 64;
 constexpr int SYM_THREADS = 256;
 
 __global__ void __launch_bounds__(SYM_THREADS)
-iou_symmetric_kernel(const float* __restrict__ a, int n, int tiles, float* __restrict__ out) {
-  __shared__ float tr[SYM_T][SYM_T + 1];
-  // linear upper-triangle tile index -> (I, J), I <= J
-  const int img = blockIdx.y;
-  int rem = blockIdx.x, I = 0;
-  // row I of the triangle holds (tiles - I) tiles
-  {
-    // solve I from rem with a closed form, then fix up (tiles <= 4096 here)
-    const float tf = (float)tiles + 0.5f;
-    I = (int)(tf - sqrtf(tf * tf - 2.0f * (float)rem));
-    if (I < 0) I = 0;
-    while (I > 0 && (int64_t)I * tiles - (int64_t)I * (I - 1) / 2 > rem) --I;
-    while ((int64_t)(I + 1) * tiles - (int64_t)(I + 1) * I / 2 <= rem) ++I;
-    rem -= (int)((int64_t)I * tiles - (int64_t)I * (I - 1) / 2);
+iou_symmetric_kernel(const float* __restrict__ a, int n, float* __restrict__ out) {
+  // 16 x 16 blocks of 4 x 4 elements; plane i holds row i of every block as one 16-byte unit
+  __shared__ float4 blk[4][256];
+  // The upper triangle folded into a rectangle: tile row p (T - p tiles) and tile row
+  // T - 1 - p (p + 1 tiles) share grid row p of width T + 1, so no CTA is empty (but the
+  // second half of the middle row when T is odd) and the decode is a compare and a subtract.
+  const int img = blockIdx.z, T = gridDim.x - 1, p = blockIdx.y, k = blockIdx.x;
+  int I, J;
+  if (k < T - p) {
+    I = p;
+    J = p + k;
+  } else {
+    I = T - 1 - p;
+    if (I == p) return;                 // middle row of an odd T: already covered above
+    J = I + (k - (T - p));
   }
-  const int J = I + rem;
   const float* ai = a + (size_t)img * n * 4;
   float* oi = out + (size_t)img * n * n;
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
@@ -161,25 +162,30 @@ iou_symmetric_kernel(const float* __restrict__ a, int n, int tiles, float* __res
     }
   }
   if (I == J) return;   // diagonal tile: already complete (uniform per CTA)
-  // transpose: tr[c][r] = v[r][c]
+  // Transposed copy for tile (J, I): block (ty, tx) goes to unit ty * 16 + (tx ^ ty) of each
+  // plane (16-byte stores, conflict free: a quarter-warp covers 8 distinct bank groups), the
+  // thread then reads block (tx, ty) the same way and transposes the 4 x 4 in registers.
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) tr[tx * 4 + j][ty * 4 + i] = v[i][j];
+    blk[i][ty * 16 + (tx ^ ty)] = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
   __syncthreads();
-  const int tr0 = J * SYM_T + ty * 4, tc0 = I * SYM_T + tx * 4;   // rows of tile (J, I)
+  float4 rr[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = tr0 + i;
+  for (int i = 0; i < 4; ++i) rr[i] = blk[i][tx * 16 + (ty ^ tx)];   // rows tx*4+i, cols ty*4.. of tile (I, J)
+  const int tr0 = J * SYM_T + ty * 4, tc0 = I * SYM_T + tx * 4;       // this thread's block of tile (J, I)
+  const float o[4][4] = {{rr[0].x, rr[1].x, rr[2].x, rr[3].x}, {rr[0].y, rr[1].y, rr[2].y, rr[3].y},
+                         {rr[0].z, rr[1].z, rr[2].z, rr[3].z}, {rr[0].w, rr[1].w, rr[2].w, rr[3].w}};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = tr0 + j;
     if (r < n) {
-      const float* src = &tr[ty * 4 + i][tx * 4];
       float* dst = oi + (size_t)r * n + tc0;
       if (vec && tc0 + 3 < n) {
-        *reinterpret_cast<float4*>(dst) = (make_float4(src[0], src[1], src[2], src[3]));
+        *reinterpret_cast<float4*>(dst) = make_float4(o[j][0], o[j][1], o[j][2], o[j][3]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (tc0 + j < n) dst[j] = src[j];
+        for (int i = 0; i < 4; ++i)
+          if (tc0 + i < n) dst[i] = o[j][i];
       }
     }
   }
@@ -213,13 +219,13 @@ extern "C" int gn_iou_dense(const float* a, const float* b, const uint8_t* crowd
   cudaStream_t s = (cudaStream_t)stream;
   const bool vec = (m % 4 == 0) && (((uintptr_t)out & 15) == 0);
   const bool has_crowd = crowd != nullptr, has_cls = a_cls != nullptr;
-  static const int variant = getenv("GN_IOU_VARIANT") ? atoi(getenv("GN_IOU_VARIANT")) : 0;
-  if (variant != 1 && a == b && n == m && !has_crowd && !has_cls && n >= 2 * gn::SYM_T &&
+  // the same buffer on both sides = the det x det matrix: symmetric kernel (pass a copy of the
+  // boxes to get the general kernel; tests/test_gpu_iou_neighbors.py compares the two)
+  if (a == b && n == m && !has_crowd && !has_cls && n >= 2 * gn::SYM_T &&
       (((uintptr_t)out & 15) == 0)) {
     const int tiles = gn::ceil_div(n, gn::SYM_T);
-    const int64_t tri = (int64_t)tiles * (tiles + 1) / 2;
-    if (tri < (1ll << 31) && batch <= 65535) {
-      gn::iou_symmetric_kernel<<<dim3((unsigned)tri, batch), gn::SYM_THREADS, 0, s>>>(a, n, tiles, out);
+    if (tiles <= 65535 && batch <= 65535) {
+      gn::iou_symmetric_kernel<<<dim3(tiles + 1, (tiles + 1) / 2, batch), gn::SYM_THREADS, 0, s>>>(a, n, out);
       GN_CHECK_LAUNCH("gn_iou_dense(symmetric)");
       return GN_OK;
     }

@@ -391,3 +391,86 @@ extern "C" int gn_selftest_tma(const void* mat_bf16, int rows, const void* wmat_
   GN_CHECK_LAUNCH("gn_selftest_tma");
   return GN_OK;
 }
+
+// ---------------------------------------------------------------------------------
+// Store-bandwidth micro-benchmark (no reference counterpart): the ceiling the write-only
+// dense IoU kernel (gn_iou.cu) is measured against.  Every mode writes `bytes` bytes of
+// constants, persistent CTAs, each warp instruction covering contiguous memory:
+//   0  st.global.v4.f32 (128-bit, default policy)     1  st.global.cs.v4.f32 (streaming)
+//   2  st.global.v8.f32 (256-bit, sm_100)             3  st.global.wt.v4.f32 (write-through)
+//   4  cp.async.bulk shared -> global, 16 KB per copy (TMA store path)
+//   5  st.global.v8.f32 with an L2 evict-first policy
+// ---------------------------------------------------------------------------------
+namespace gn {
+template <int MODE>
+__global__ void __launch_bounds__(256)
+store_bw_kernel(float* __restrict__ dst, size_t n16) {   // n16 = number of 16-byte units
+  const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+  if (MODE == 4) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    for (int i = threadIdx.x; i < 16384 / 16; i += blockDim.x) reinterpret_cast<float4*>(sm)[i] = v;
+    umma::fence_smem_to_async();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const size_t chunks = n16 / 1024;   // 16 KB chunks
+      int inflight = 0;
+      for (size_t c = blockIdx.x; c < chunks; c += gridDim.x) {
+        umma::bulk_copy_s2g(reinterpret_cast<unsigned char*>(dst) + c * 16384, umma::smem_u32(sm), 16384);
+        umma::bulk_commit_group();
+        if (++inflight >= 8) {
+          asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+          inflight = 4;
+        }
+      }
+      umma::bulk_wait_group0();
+    }
+    return;
+  }
+  if (MODE == 2 || MODE == 5) {
+    uint64_t pol = 0;
+    if (MODE == 5) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    const size_t n32 = n16 / 2;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n32;
+         i += (size_t)gridDim.x * blockDim.x) {
+      float* p = dst + i * 8;
+      if (MODE == 2)
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %1, %2, %3, %4};"
+                     ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+      else
+        asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1, %2, %3, %4, %1, %2, %3, %4}, %5;"
+                     ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+    }
+    return;
+  }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float4* p = reinterpret_cast<float4*>(dst) + i;
+    if (MODE == 0) *p = v;
+    else if (MODE == 1) __stcs(p, v);
+    else __stwt(p, v);
+  }
+}
+}  // namespace gn
+
+extern "C" int gn_selftest_store_bw(void* dst, int64_t bytes, int mode, int ctas_per_sm,
+                                    gn_stream_t stream) {
+  GN_REQUIRE(dst && bytes >= 16384 && bytes % 16384 == 0, "gn_selftest_store_bw: bytes must be a "
+             "positive multiple of 16384");
+  GN_REQUIRE(((uintptr_t)dst & 127) == 0, "gn_selftest_store_bw: dst must be 128-byte aligned");
+  GN_REQUIRE(mode >= 0 && mode <= 5 && ctas_per_sm >= 1 && ctas_per_sm <= 32,
+             "gn_selftest_store_bw: bad mode / ctas_per_sm");
+  const int grid = gn::sm_count() * ctas_per_sm;
+  const size_t n16 = (size_t)bytes / 16;
+  float* d = static_cast<float*>(dst);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (mode) {
+    case 0: gn::store_bw_kernel<0><<<grid, 256, 0, s>>>(d, n16); break;
+    case 1: gn::store_bw_kernel<1><<<grid, 256, 0, s>>>(d, n16); break;
+    case 2: gn::store_bw_kernel<2><<<grid, 256, 0, s>>>(d, n16); break;
+    case 3: gn::store_bw_kernel<3><<<grid, 256, 0, s>>>(d, n16); break;
+    case 4: gn::store_bw_kernel<4><<<grid, 256, 16384, s>>>(d, n16); break;
+    default: gn::store_bw_kernel<5><<<grid, 256, 0, s>>>(d, n16); break;
+  }
+  GN_CHECK_LAUNCH("gn_selftest_store_bw");
+  return GN_OK;
+}

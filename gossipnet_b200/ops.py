@@ -525,3 +525,14 @@ def selftest_tma(mat, wmat, idx, row0):
               _chk(wmat, torch.bfloat16, 'wmat'), _chk(idx, torch.int32, 'idx'), int(row0),
               _chk(dump, torch.uint8, 'dump'), _chk(d, torch.float32, 'd'), _stream())
     return dump, d
+
+
+STORE_BW_MODES = ('st.v4', 'st.cs.v4', 'st.v8', 'st.wt.v4', 'bulk_s2g_16k', 'st.v8.evict_first')
+
+
+def selftest_store_bw(buf, mode, ctas_per_sm=8):
+    """Fill `buf` (uint8, multiple of 16 KiB) with the library's store micro-benchmark;
+    mode: a name from STORE_BW_MODES."""
+    n = buf.numel() // 16384 * 16384
+    _lib.call('gn_selftest_store_bw', _chk(buf, torch.uint8, 'buf'), n,
+              STORE_BW_MODES.index(mode), int(ctas_per_sm), _stream())

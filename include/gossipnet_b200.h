@@ -398,6 +398,13 @@ int gn_selftest_umma_rate(int n, int reps, int distinct_b, int ctas, int64_t* ou
 int gn_selftest_tma(const void* mat_bf16, int rows, const void* wmat_bf16, const int32_t* idx,
                     int row0, void* dump, float* d_out, gn_stream_t stream);
 
+/* Store-bandwidth micro-benchmark: writes `bytes` (multiple of 16384) bytes of constants with
+ * mode 0 st.global.v4 | 1 st.global.cs.v4 | 2 st.global.v8 (256-bit) | 3 st.global.wt.v4 |
+ * 4 cp.async.bulk shared->global (16 KB copies) | 5 st.global.v8 + L2 evict-first policy,
+ * from sm_count * ctas_per_sm persistent CTAs.  The measured ceiling of the write-only dense
+ * IoU kernel (bench.py roofline_iou.store_ceiling_gbs). */
+int gn_selftest_store_bw(void* dst, int64_t bytes, int mode, int ctas_per_sm, gn_stream_t stream);
+
 /* ---- A7 pair stage, TMA-fed (gn_block_tma.cu) ----------------------------------------
  * Same contract as gn_block_pair_fwd_pipe (network.py:367-388: gather/concat, pw_fc1,
  * pw_fc2, segment_max -> atomic max into pooled[T,64], which the caller zeroed), other

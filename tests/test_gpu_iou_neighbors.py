@@ -48,6 +48,36 @@ def test_symmetric_iou_kernel_bit_exact(n):
     assert np.array_equal(bits(ops.iou_dense(t, t.clone()).cpu().numpy()), bits(got))
 
 
+@pytest.mark.parametrize('n', [130, 512, 1500])
+def test_symmetric_iou_dense_overlaps(n):
+    """Heavily overlapping boxes (every pair intersects): the deferred-division queue of
+    iou_symmetric_kernel overflows and the in-place path takes over; still bit-exact.  Also
+    degenerate boxes (zero area -> 0/0 = NaN like the reference arithmetic)."""
+    rs = np.random.RandomState(n)
+    c = rs.uniform(400, 600, (n, 2))
+    wh = rs.uniform(150, 300, (n, 2))
+    d = np.concatenate([c - wh / 2, c + wh / 2], axis=1).astype(F32)
+    d[3] = [10, 10, 10, 20]          # zero-area boxes
+    d[7] = [10, 10, 10, 20]
+    t = dev(d)
+    got = ops.iou_dense(t, t).cpu().numpy()
+    with np.errstate(invalid='ignore', divide='ignore'):
+        ref = go.iou(go.xyxy_to_boxdata(d), go.xyxy_to_boxdata(d))
+    nan = np.isnan(ref)      # 0/0 of the zero-area boxes: NaN on both sides (payload bits differ
+    assert nan.sum() == 4 and np.array_equal(np.isnan(got), nan)      # between x86 and the GPU)
+    assert np.array_equal(bits(got)[~nan], bits(ref)[~nan])
+    # half dense / half sparse: queue partly filled, some threads in place
+    d2 = d.copy()
+    d2[n // 2:, :2] += 5000
+    d2[n // 2:, 2:] += 5000
+    d2[n // 2:] += (np.arange(n - n // 2)[:, None] * 400).astype(F32)
+    t2 = dev(d2)
+    got2 = ops.iou_dense(t2, t2).cpu().numpy()
+    with np.errstate(invalid='ignore', divide='ignore'):
+        ref2 = go.iou(go.xyxy_to_boxdata(d2), go.xyxy_to_boxdata(d2))
+    assert np.array_equal(bits(got2)[~np.isnan(ref2)], bits(ref2)[~np.isnan(ref2)])
+
+
 def test_iou_known_answers():
     d = np.array([[0, 0, 10, 10], [5, 0, 15, 10], [100, 100, 110, 120]], F32)
     got = ops.iou_dense(dev(d), dev(d)).cpu().numpy()
