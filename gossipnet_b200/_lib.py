@@ -111,6 +111,11 @@ SIGNATURES = {
     'gn_block_pair_fwd_tma_bf16': [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                    c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'gn_selftest_tma': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    'gn_prepare_fc_images': [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    'gn_fc_fwd_tc': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                     c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    'gn_fc_bwd_weight_tc': [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                            c_void_p, c_int, c_int, c_void_p],
     'gn_selftest_store_bw': [c_void_p, ctypes.c_int64, c_int, c_int, c_void_p],
     'gn_selftest_umma': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     'gn_selftest_umma_ts': [c_void_p, c_void_p, c_void_p, c_int, c_void_p],

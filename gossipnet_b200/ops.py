@@ -179,6 +179,50 @@ def fc_fwd(x, w, b, relu, residual=None, out=None, rows_dev=None):
     return out
 
 
+def prepare_fc_images(flat_params, table, image):
+    """table[entries, 6] int32 (src offset, k, n, dst byte offset, kpad, transposed) -> bf16
+    hi/lo K-major operand images of gn_fc_fwd_tc, one launch for all entries."""
+    _lib.call('gn_prepare_fc_images', _chk(flat_params, torch.float32, 'flat_params'),
+              _chk(table, torch.int32, 'table'), table.shape[0], _chk(image, torch.uint8, 'image'),
+              _stream())
+
+
+def fc_tc_supported(k, n):
+    """Shapes gn_fc_fwd_tc / gn_fc_bwd_weight_tc take (everything the reference's FCs use
+    except the 128 -> 1 logit layer)."""
+    return k <= 256 and n <= 256 and n % 32 == 0
+
+
+def fc_fwd_tc(x, wimg, k, n, bias, relu, residual=None, out=None, rows_dev=None, mask=None):
+    """y = act(residual + (x * (mask > 0)) @ W + b) on the tensor cores (bf16x3); `wimg` is the
+    operand image of W (gn_prepare_fc_images), k = true width of x, n = output width."""
+    rows = x.shape[0]
+    if x.dim() != 2 or x.shape[1] != k:
+        raise ValueError('fc_fwd_tc: x must be [rows, %d]' % k)
+    if mask is not None and tuple(mask.shape) != tuple(x.shape):
+        raise ValueError('fc_fwd_tc: mask must have the shape of x')
+    if out is None:
+        out = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+    f32 = torch.float32
+    kpad = (k + 15) // 16 * 16
+    _lib.call('gn_fc_fwd_tc', _chk(x, f32, 'x'), k, _chk(mask, f32, 'mask', True),
+              _chk(wimg, torch.uint8, 'wimg'), _chk(bias, f32, 'bias', True),
+              _chk(residual, f32, 'residual', True), n if residual is not None else 0,
+              1 if relu else 0, _chk(out, f32, 'y'), n, rows,
+              _chk(rows_dev, torch.int32, 'rows_dev', True), k, kpad, n, _stream())
+    return out
+
+
+def fc_bwd_weight_tc(x, dy, dw, db, rows_dev=None, mask=None):
+    """dW += x^T @ (dy * (mask > 0)); db += column sums of the masked dy (tensor cores)."""
+    rows, k = x.shape
+    n = dy.shape[1]
+    f32 = torch.float32
+    _lib.call('gn_fc_bwd_weight_tc', _chk(x, f32, 'x'), k, _chk(dy, f32, 'dy'), n,
+              _chk(mask, f32, 'mask', True), _chk(dw, f32, 'dw'), _chk(db, f32, 'db', True), rows,
+              _chk(rows_dev, torch.int32, 'rows_dev', True), k, n, _stream())
+
+
 # ------------------------------------------------------------------------ blocks
 def block_gather_concat(pw, feats, nfeats, pair_c, pair_n, num_pairs, capacity, out=None):
     w, r = pw.shape[1], feats.shape[1]

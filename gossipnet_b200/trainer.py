@@ -53,22 +53,90 @@ class Trainer(object):
         self.state2 = torch.zeros(eng.total, dtype=torch.float32, device=dev)   # Adam v
         self.global_step = 0
         self._zero_bias = torch.zeros(1024, dtype=torch.float32, device=dev)
+        # every FC and its gradients on the tensor cores (gn_fc_tc.cu, bf16x3); False: the fp32
+        # CUDA-core kernels (gn_fc.cu / gn_train.cu), kept as the cross-check.  Forward and
+        # backward switch separately: the gradient of this piecewise-linear network (relu,
+        # segment max) is discontinuous in the activations, so a 1e-5 perturbation of the
+        # FORWARD flips a few selections and moves some gradients by ~1e-3 against a float64
+        # oracle, while the tensor-core BACKWARD on identical activations stays within 1e-5
+        # (tests/test_gpu_training.py, experiments/grad_err.py).
+        self.use_tc_fwd = True
+        self.use_tc_bwd = True
+        self._build_fc_images()
+
+    @property
+    def use_tc(self):
+        return self.use_tc_fwd and self.use_tc_bwd
+
+    @use_tc.setter
+    def use_tc(self, v):
+        self.use_tc_fwd = self.use_tc_bwd = bool(v)
+
+    def _build_fc_images(self):
+        """Operand images of every FC weight for gn_fc_fwd_tc: one for y = x @ W and, where the
+        input gradient is a supported shape, one for dx = dy @ W^T.  Rebuilt from the flat
+        parameter buffer by ONE launch at the start of every step (the weights moved)."""
+        rows, off = [], 0
+        self._img_fwd, self._img_bwd = {}, {}
+        for name, e in self.eng.layout.items():
+            if not name.endswith('/weights') or len(e.shape) != 2:
+                continue
+            scope = name[:-len('/weights')]
+            k, n = e.shape
+            if ops.fc_tc_supported(k, n):
+                kpad = (k + 15) // 16 * 16
+                nbytes = 2 * (kpad // 8) * n * 16
+                rows.append([e.offset, k, n, off, kpad, 0])
+                self._img_fwd[scope] = (off, nbytes)
+                off += nbytes
+            if ops.fc_tc_supported(n, k):          # dx = dy[rows, n] @ W^T -> [rows, k]
+                kpad = (n + 15) // 16 * 16
+                nbytes = 2 * (kpad // 8) * k * 16
+                rows.append([e.offset, k, n, off, kpad, 1])
+                self._img_bwd[scope] = (off, nbytes)
+                off += nbytes
+        dev = self.eng.device
+        self._img_table = torch.tensor(rows, dtype=torch.int32, device=dev).reshape(-1, 6)
+        self._img = torch.zeros(max(off, 16), dtype=torch.uint8, device=dev)
+
+    def _image(self, table, scope):
+        off, nbytes = table[scope]
+        return self._img[off:off + nbytes]
 
     # ---------------------------------------------------------------- helpers
     def _fc(self, x, scope, relu, residual=None, rows_dev=None):
         e = self.eng
-        return ops.fc_fwd(x, e.p[scope + '/weights'], e.p[scope + '/biases'], relu,
-                          residual=residual, rows_dev=rows_dev)
+        w = e.p[scope + '/weights']
+        if self.use_tc_fwd and scope in self._img_fwd:
+            return ops.fc_fwd_tc(x, self._image(self._img_fwd, scope), w.shape[0], w.shape[1],
+                                 e.p[scope + '/biases'], relu, residual=residual,
+                                 rows_dev=rows_dev)
+        return ops.fc_fwd(x, w, e.p[scope + '/biases'], relu, residual=residual, rows_dev=rows_dev)
 
-    def _fc_bwd(self, x, dy, scope, rows_dev=None, need_dx=True):
-        """dW, db += ; returns dx = dy @ W^T (rows beyond *rows_dev are not written)."""
-        ops.fc_bwd_weight(x, dy, self.g[scope + '/weights'], self.g[scope + '/biases'],
-                          rows_dev=rows_dev)
+    def _fc_bwd(self, x, dy, scope, rows_dev=None, need_dx=True, mask=None):
+        """dW, db += ; returns dx = dy @ W^T (rows beyond *rows_dev are not written).
+        `mask`: the layer's activation output - its relu gradient (dy where mask > 0, else 0)
+        is applied to dy inside the tensor-core kernels, or in place before the fp32 ones."""
+        w = self.eng.p[scope + '/weights']
+        k, n = w.shape
+        tc_w = self.use_tc_bwd and k <= 256 and n in (32, 64, 128, 256)
+        tc_x = self.use_tc_bwd and scope in self._img_bwd
+        if mask is not None and not (tc_w and (tc_x or not need_dx)):
+            ops.relu_mask(dy, mask, rows_dev=rows_dev)     # one of the consumers needs it applied
+            mask = None
+        if tc_w:
+            ops.fc_bwd_weight_tc(x, dy, self.g[scope + '/weights'], self.g[scope + '/biases'],
+                                 rows_dev=rows_dev, mask=mask)
+        else:
+            ops.fc_bwd_weight(x, dy, self.g[scope + '/weights'], self.g[scope + '/biases'],
+                              rows_dev=rows_dev)
         if not need_dx:
             return None
-        w = self.eng.p[scope + '/weights']
+        if tc_x:
+            return ops.fc_fwd_tc(dy, self._image(self._img_bwd, scope), n, k, None, False,
+                                 rows_dev=rows_dev, mask=mask)
         wt = ops.transpose(w)
-        return ops.fc_fwd(dy, wt, self._zero_bias[:w.shape[0]], False, rows_dev=rows_dev)
+        return ops.fc_fwd(dy, wt, self._zero_bias[:k], False, rows_dev=rows_dev)
 
     # -------------------------------------------------------- forward + backward
     def forward_backward(self, batches, zero_grad=True):
@@ -81,6 +149,8 @@ class Trainer(object):
         T = dets.shape[0]
         if zero_grad:
             self.gradbuf.zero_()
+        if self.use_tc_fwd or self.use_tc_bwd:
+            ops.prepare_fc_images(eng.flat, self._img_table, self._img)
 
         # ---- forward, keeping activations (unfused CUDA pieces) ---------------------
         max_img = int(np.max(np.diff(io['img_off_host'])))
@@ -168,9 +238,8 @@ class Trainer(object):
             if hs:
                 ops.segment_max_bwd(hs[-1], ds[0], dd, row_ptr, dh)
                 for i in range(g['num_block_pw_fc'], 0, -1):
-                    ops.relu_mask(dh, hs[i - 1], rows_dev=num_pairs)
                     dh = self._fc_bwd(hs[i - 2] if i > 1 else x, dh, s + 'pw_fc%d' % i,
-                                      rows_dev=num_pairs)
+                                      rows_dev=num_pairs, mask=hs[i - 1])
             else:
                 dh = torch.empty_like(x)
                 ops.segment_max_bwd(x, ds[0], dd, row_ptr, dh)
@@ -199,9 +268,8 @@ class Trainer(object):
         # pair-feature MLP: sum of the gradients of all blocks; raw features are constants
         d = dpw
         for i in range(g['num_pwfeat_fc'], 0, -1):
-            ops.relu_mask(d, pw_acts[i], rows_dev=num_pairs)
             d = self._fc_bwd(pw_acts[i - 1], d, 'gnet/pw_feats/fc%d' % i, rows_dev=num_pairs,
-                             need_dx=i > 1)
+                             need_dx=i > 1, mask=pw_acts[i])
         self.gradbuf[-1] += float(len(batches))
         return res
 

@@ -351,6 +351,30 @@ int gn_adam_step(float* params, const float* grads, float* m, float* v, const fl
 int gn_momentum_step(float* params, const float* grads, float* accum, const float* decay,
                      int64_t n, float lr, float momentum, float grad_scale, gn_stream_t stream);
 
+/* Tensor-core (tcgen05, bf16x3 = fp32 semantics) versions of gn_fc_fwd / gn_fc_bwd_weight for
+ * the training step (tf.contrib.layers.fully_connected and its MatMul / BiasAdd / Relu
+ * gradients, network.py:229-272, 328-341, 348-405):
+ *   gn_prepare_fc_images  table: 6 int32 per entry (src offset in floats into flat_params, k, n,
+ *                         dst byte offset into image, kpad, transposed).  transposed = 0: the
+ *                         image of W[k,n] for y = x @ W (N = n, K = k padded to kpad);
+ *                         transposed = 1: the image for dx = dy @ W^T (N = k, K = n padded).
+ *                         Image bytes per entry: 2 * (kpad / 8) * N * 16.
+ *   gn_fc_fwd_tc          y[rows,n] = act(residual + (x . (mask > 0)) @ W + b); mask (nullable)
+ *                         has the shape and leading dimension of x and fuses the relu gradient
+ *                         of the incoming dy; bias nullable (= 0).  k <= kpad <= 256, kpad % 16
+ *                         == 0, n % 32 == 0, n <= 256, else GN_ERR_UNSUPPORTED.
+ *   gn_fc_bwd_weight_tc   dW[k,n] += x^T @ (dy . (mask > 0)); db[n] += its column sums (fp32
+ *                         atomics: the summation order is not fixed).  k <= 256,
+ *                         n in {32, 64, 128, 256}. */
+int gn_prepare_fc_images(const float* flat_params, const int32_t* table, int entries, void* image,
+                         gn_stream_t stream);
+int gn_fc_fwd_tc(const float* x, int ldx, const float* mask, const void* wimg, const float* bias,
+                 const float* residual, int ld_res, int relu, float* y, int ldy, int rows,
+                 const int32_t* rows_dev, int k, int kpad, int n, gn_stream_t stream);
+int gn_fc_bwd_weight_tc(const float* x, int ldx, const float* dy, int ldy, const float* mask,
+                        float* dw, float* db, int rows, const int32_t* rows_dev, int k, int n,
+                        gn_stream_t stream);
+
 /* gn_frcn_boxes: detection boxes -> rois of the image-feature head (network.py:78-100,
  * enlarge_windows + to_frcn_coords): rois[i] = (batch_index, cx - w (0.5 + padding),
  * cy - h (0.5 + padding), cx + w (0.5 + padding), cy + h (0.5 + padding)), float32 ops in the

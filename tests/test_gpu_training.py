@@ -35,12 +35,24 @@ def oracle_grad_for(img, flat, layout, num_classes, labels, weights):
     return out
 
 
-def grad_check(num_classes, imgs, tol=2e-3):
+# Trainer arithmetic -> tolerance against the float64 gradient oracle (max |d| / max |ref| per
+# parameter).  'ffma': fp32 CUDA-core FCs throughout.  'tc_bwd': fp32 forward, tensor-core
+# (bf16x3) backward GEMMs on the same activations - the kernel-level check of gn_fc_tc.cu.
+# 'tc' (the shipped default): tensor-core forward too; its ~1e-5 activation differences flip a
+# few relu / segment-max selections, and the gradient of a piecewise-linear network jumps
+# there, so the bound is the looser one (experiments/grad_err.py separates the two effects).
+MODES = {'ffma': 2e-3, 'tc_bwd': 1e-4, 'tc': 2e-2}
+
+
+def grad_check(num_classes, imgs, mode='tc'):
+    tol = MODES[mode]
     layout, total = P.param_layout(num_classes, cfg)
     flat = P.init_flat(layout, total, cfg, seed=21)
     cw = np.linspace(0.5, 1.5, num_classes + 1).astype(np.float32)
     net = Gnet(num_classes, class_weights=cw, params=flat)
     tr = Trainer(net)
+    tr.use_tc_fwd = mode == 'tc'
+    tr.use_tc_bwd = mode in ('tc', 'tc_bwd')
     res = tr.forward_backward(imgs)
     got = tr.grad.cpu().numpy().astype(np.float64)
     assert float(tr.gradbuf[-1]) == len(imgs)
@@ -58,7 +70,8 @@ def grad_check(num_classes, imgs, tol=2e-3):
     return tr, res
 
 
-def test_gradients_with_image_feature_head(oracle_built):
+@pytest.mark.parametrize('mode', ['tc_bwd', 'tc'])
+def test_gradients_with_image_feature_head(mode, oracle_built):
     load_experiment('coco_person', num_blocks=2)
     cfg.gnet.imfeats = True
     cfg.gnet.imfeat_channels, cfg.gnet.imfeat_dim = 16, 48
@@ -67,31 +80,36 @@ def test_gradients_with_image_feature_head(oracle_built):
         img = synthetic.make_image(n, 1, image_index=i)
         img['imfeats'] = np.random.RandomState(40 + i).normal(size=(1, 38, 63, 16)).astype(np.float32)
         imgs.append(img)
-    grad_check(1, imgs)
+    grad_check(1, imgs, mode)
 
 
-def test_gradients_coco_person_two_blocks():
+@pytest.mark.parametrize('mode', sorted(MODES))
+def test_gradients_coco_person_two_blocks(mode):
     load_experiment('coco_person', num_blocks=2)
-    grad_check(1, [synthetic.make_image(300, 1, image_index=0)])
+    grad_check(1, [synthetic.make_image(300, 1, image_index=0)], mode)
 
 
-def test_gradients_multi_image_batch_sum():
+@pytest.mark.parametrize('mode', sorted(MODES))
+def test_gradients_multi_image_batch_sum(mode):
     load_experiment('coco_person', num_blocks=3)
-    grad_check(1, [synthetic.make_image(n, 1, image_index=i) for i, n in enumerate([120, 57, 200])])
+    grad_check(1, [synthetic.make_image(n, 1, image_index=i) for i, n in enumerate([120, 57, 200])],
+               mode)
 
 
-def test_gradients_multiclass_and_normalized_loss():
+@pytest.mark.parametrize('mode', ['tc_bwd', 'tc'])
+def test_gradients_multiclass_and_normalized_loss(mode):
     load_experiment('coco_multiclass', num_blocks=2)
     cfg.train.normalize_loss = True
     cfg.train.loss_multiplyer = 3.0
-    grad_check(80, [synthetic.make_image(150, 80, image_index=2)])
+    grad_check(80, [synthetic.make_image(150, 80, image_index=2)], mode)
 
 
-def test_gradients_neighbor_feats_and_raw_pair_features():
+@pytest.mark.parametrize('mode', ['tc_bwd', 'tc'])
+def test_gradients_neighbor_feats_and_raw_pair_features(mode):
     cfg.gnet.num_blocks = 2
     cfg.gnet.neighbor_feats = True          # reduce_dim_neighbor branch, num_pwfeat_fc = 0
     cfg.gnet.bias_const_init = 0.05
-    grad_check(1, [synthetic.make_image(90, 1, image_index=4)])
+    grad_check(1, [synthetic.make_image(90, 1, image_index=4)], mode)
 
 
 def test_adam_and_momentum_updates_closed_form():
