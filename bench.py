@@ -309,7 +309,7 @@ def kernel_rooflines(torch, ops, eng, sess, stream, flush, P, T, blocks, bf16, p
     s1 = 'gnet/block1/'
     if eng._tma_path():
         red_all = eng._ws['red_hl'][:(T + 1) * 64].view(T + 1, 64)
-        ab = eng._ws['ab'][:T * 128].view(T, 128)
+        ab = eng._ws['u'][:T * 64].view(T, 64)
         image, _ = eng._tma_images()
         tb = ops.pair_tma_image_bytes()
 
@@ -355,14 +355,16 @@ def kernel_rooflines(torch, ops, eng, sess, stream, flush, P, T, blocks, bf16, p
         feats = eng._buf('feats0', (T, 128))
         outb = eng._buf('feats1', (T, 128))
         inter = eng._ws['red_hl'][:T * 64].view(T, 64)
-        ab = eng._buf('ab', (T, 128)) if eng._tma_path() else None
+        u = eng._buf('u', (T, 64)) if eng._tma_path() else None
 
         def det():
-            ops.block_det_fwd_img(pooled, feats, image[det_off[1]:det_off[1] + det_b],
-                                  p['gnet/block1/fc1/biases'], p['gnet/block1/fc2/biases'],
-                                  p['gnet/block2/reduce_dim/biases'], feats_out=outb, red_hl=inter,
-                                  b_ab=p['gnet/block2/pw_fc1/biases'] if ab is not None else None,
-                                  ab_out=ab, bf16=bf16)
+            args_ = (pooled, feats, image[det_off[1]:det_off[1] + det_b], p['gnet/block1/fc1/biases'],
+                     p['gnet/block1/fc2/biases'], p['gnet/block2/reduce_dim/biases'])
+            if u is not None:
+                ops.block_det_fwd_img_u(*args_, outb, inter, p['gnet/block2/pw_fc1/biases'], u,
+                                        bf16=bf16)
+            else:
+                ops.block_det_fwd_img(*args_, feats_out=outb, red_hl=inter, bf16=bf16)
         ms = med(_events(torch, stream, det, 10, before=pre))
         out['roofline_det'] = entry('block_det_tc_kernel', ms, 32768.0 * T, blocks + 1,
                                     'det_dram_bytes_per_launch')
@@ -454,6 +456,66 @@ def run_config2(torch, ops, stream, flush, peaks, peak_src, steps, warmup):
                                            'ms_per_launch', 'peak_source')},
             'roofline_pwfeat': None if rp is None else
             {k: rp[k] for k in ('kernel', 'achieved', 'peak', 'unit', 'frac', 'ms_per_launch')}}
+
+
+def run_train(torch, dist, world, rank, steps, warmup):
+    """BASELINE configs[3]: training, 8 images x N=1000 per GPU (64 images on 8 GPUs), 16 blocks:
+    forward with kept activations + DetectionMatching + loss + backward + ONE NCCL all-reduce of
+    the flat gradient buffer + fused Adam (train.py:64-77, 316-320).  Device time per step, max
+    over ranks; the all-reduce also timed alone."""
+    from gossipnet_b200 import synthetic
+    from gossipnet_b200.nms_net.network import Gnet
+    from gossipnet_b200.trainer import Trainer
+    per_gpu, n_dets = 8, 1000
+    imgs = [synthetic.make_image(n_dets, 1, image_index=rank * per_gpu + i) for i in range(per_gpu)]
+    net = Gnet(1)
+    tr = Trainer(net)
+    for _ in range(max(2, warmup)):
+        tr.step(imgs, 1e-4)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        res = tr.step(imgs, 1e-4)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    # the collective alone: the flat fp32 gradient buffer (+ the image count)
+    ar = []
+    for _ in range(12):
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if world > 1:
+            dist.all_reduce(tr.gradbuf)
+        e1.record()
+        torch.cuda.synchronize()
+        ar.append(e0.elapsed_time(e1) * 1e3)
+    ar_us = float(np.median(ar[2:]))
+    # replicas must stay bit-identical: same all-reduced gradient, same update on every rank
+    same = True
+    t = torch.tensor([ms, ar_us], dtype=torch.float64, device='cuda')
+    if world > 1:
+        ref = tr.eng.flat.clone()
+        dist.broadcast(ref, 0)
+        diff = (ref != tr.eng.flat).any().to(torch.int32)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        same = int(diff) == 0
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_us = float(t[0]), float(t[1])
+    return {'workload': 'training step, %d images x N=%d per GPU, 16 blocks, coco_person '
+                        '(BASELINE configs[3]: batch 64 on 8 GPUs); forward with kept activations, '
+                        'matching, loss, backward, all-reduce, Adam' % (per_gpu, n_dets),
+            'ms_per_step': ms, 'value': world * per_gpu * n_dets / (ms * 1e-3), 'unit': UNIT,
+            'steps': steps, 'pairs_per_step_rank0': int(res['P']),
+            'allreduce_us': ar_us if world > 1 else None,
+            'allreduce_bytes': int(tr.gradbuf.numel() * 4),
+            'params_identical_across_ranks': same,
+            'arithmetic': 'fp32 semantics: every FC and its gradients as bf16x3 tcgen05 GEMMs '
+                          '(gn_fc_tc.cu)'}
 
 
 def run_b200(args):
@@ -576,6 +638,16 @@ def run_b200(args):
         extra2 = run_config2(torch, ops, stream, flush, peaks, peak_src, max(5, args.steps // 2),
                              args.warmup)
 
+    # ---- BASELINE configs[3]: the training step and its one collective, at every N -------
+    train = None
+    pair_mode, used_graph = eng.pair_mode, bool(sess._graph)
+    h2d_bytes, d2h_bytes = sess.h2d_bytes, sess.d2h_bytes
+    if not args.quick and not bf16:
+        del sess, net, eng, flush
+        torch.cuda.empty_cache()
+        setup_cfg(args.blocks, args.precision)
+        train = run_train(torch, dist, world, rank, 5, 2)
+
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -590,19 +662,20 @@ def run_b200(args):
                                       '(bf16x3) on tcgen05 with fp32 TMEM accumulation'),
                        'images_per_gpu_per_step': B, 'pairs_per_step_rank0': P,
                        'pairs_per_step_min_max_over_ranks': [p_min, p_max],
-                       'pair_mode': eng.pair_mode,
+                       'pair_mode': pair_mode,
                        'parallelism': 'images sharded over %d GPU(s), no data-path collective'
                                       % world,
                        'l2': 'flushed between timed steps (256 MiB memset); working set also '
                              '> 126 MB L2',
-                       'cuda_graph': bool(sess._graph)},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': sess.h2d_bytes,
-                    'd2h_bytes_per_step': sess.d2h_bytes, 'ms_per_step': e2e_ms / args.steps,
+                       'cuda_graph': used_graph},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d_bytes,
+                    'd2h_bytes_per_step': d2h_bytes, 'ms_per_step': e2e_ms / args.steps,
                     'api': 'gossipnet_b200.session.InferenceSession.run (numpy in/out)'},
             'gpu_launches': launches * args.steps,
             'clocks': clk, 'roofline': roofs.get('roofline'),
             'roofline_pwfeat': roofs.get('roofline_pwfeat'), 'roofline_det': roofs.get('roofline_det'),
             'roofline_iou': roof_iou, 'cpu_baseline': cpu, 'config2_coco_multiclass_bf16': extra2,
+            'train_config3': train,
             'logit_checksum': float(np.sum(pred, dtype=np.float64)),
         }
         print(json.dumps(line))

@@ -48,7 +48,7 @@ print('P = %d; logits tma vs pipe: max|d| / max|ref| = %.3e' % (
 s1 = 'gnet/block1/'
 b1, b2 = eng.p[s1 + 'pw_fc1/biases'], eng.p[s1 + 'pw_fc2/biases']
 red_all = eng._ws['red_hl'][:(T + 1) * 64].view(T + 1, 64)
-ab = eng._ws['ab'][:T * 128].view(T, 128)
+ab = eng._ws['u'][:T * 64].view(T, 64)
 tma_image, _ = eng._tma_images()
 tb = ops.pair_tma_image_bytes()
 eng.pair_mode = 'pipe'

@@ -80,7 +80,7 @@ class Saver(object):
     def restore(self, trainer, path):
         """Loads parameters + optimizer slots; returns the iteration to continue
         at (train.py:303-304: global_step + 1)."""
-        blob = torch.load(path, map_location='cpu', weights_only=False)
+        blob = torch.load(path, map_location='cpu', weights_only=True)   # tensors + plain values only
         if blob.get('format') != 'gossipnet_b200-checkpoint-1':
             raise ValueError('{} is not a gossipnet_b200 checkpoint'.format(path))
         trainer.net.load_state_dict(blob['variables'])
@@ -99,7 +99,7 @@ class Saver(object):
 
 def load_variables(path):
     """name -> tensor dictionary of a checkpoint (what test.py's restorer needs)."""
-    blob = torch.load(path, map_location='cpu', weights_only=False)
+    blob = torch.load(path, map_location='cpu', weights_only=True)   # tensors + plain values only
     return blob['variables']
 
 

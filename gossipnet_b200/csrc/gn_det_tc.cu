@@ -133,8 +133,8 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
                     const float* __restrict__ w_rd, const float* __restrict__ b_rd,
                     const unsigned char* __restrict__ wimg, float* __restrict__ feats_out,
                     float* __restrict__ red_f32, __nv_bfloat16* __restrict__ red_hl,
-                    const float* __restrict__ b_ab, float* __restrict__ ab_out, int num_dets,
-                    int has_a, int has_b) {
+                    const float* __restrict__ b_ab, float* __restrict__ ab_out, int ab_cols,
+                    int num_dets, int has_a, int has_b) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -391,20 +391,21 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       }
       if (stage_ab) {
         // AB[d, 0:64] = red @ W1[32:64] + b1 ; AB[d, 64:128] = red @ W1[64:96]   (gn_block_ab.cu)
+        // ab_cols = 64: only the first half (gn_block_tma.cu gathers the neighbor rows itself)
         umma::fence_smem_to_async();
         umma::tc_fence_before();
         __syncthreads();
         if (t == 0) {
           umma::tc_fence_after();
-          dt_gemm<DT_R / 16, X3>(tm2, d_ah, d_al, d_wabh, d_wabl, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
+          dt_gemm<DT_R / 16, X3>(tm2, d_ah, d_al, d_wabh, d_wabl, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, ab_cols));
           umma::mma_commit(bar);
         }
         umma::mbar_wait(bar, par);
         par ^= 1;
         umma::tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < 64; cc += 32) {
-          const int col0 = ehalf * 64 + cc;
+        const int per = ab_cols >> 1;          // columns per warp half: 64 or 32
+        for (int cc = 0; cc < per; cc += 32) {
+          const int col0 = ehalf * per + cc;
           float v[32];
           umma::tmem_ld32(tm2 + tlane + col0, v);
           umma::tmem_ld_wait();
@@ -413,10 +414,10 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
             for (int g = 0; g < 8; ++g) {
               const int col = col0 + g * 4;
               float4 o = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-              if (col < DT_F) {          // uniform per warp: ehalf 0 owns the A half
+              if (col < DT_F) {          // uniform per warp
                 o.x += biasab[col]; o.y += biasab[col + 1]; o.z += biasab[col + 2]; o.w += biasab[col + 3];
               }
-              *reinterpret_cast<float4*>(ab_out + (size_t)grow * DT_D + col) = o;
+              *reinterpret_cast<float4*>(ab_out + (size_t)grow * ab_cols + col) = o;
             }
           }
         }
@@ -438,8 +439,8 @@ static int launch_block_det(const char* name, bool x3, float* pooled, const floa
                             const float* b_fc2, const float* w_rd, const float* b_rd,
                             const void* wimg, int has_a, int has_b, float* feats_out,
                             float* red_f32, void* red_hl, const float* b_ab, float* ab_out,
-                            int num_dets, int shortcut_dim, int pairfeat_dim, int reduced_dim,
-                            gn_stream_t stream) {
+                            int ab_cols, int num_dets, int shortcut_dim, int pairfeat_dim,
+                            int reduced_dim, gn_stream_t stream) {
   GN_REQUIRE(num_dets >= 0, "%s: negative size", name);
   if (shortcut_dim != gn::DT_D || pairfeat_dim != gn::DT_F || reduced_dim != gn::DT_R) {
     gn::set_error("%s: fused kernel is built for d=%d f=%d r=%d (got %d, %d, %d)", name,
@@ -456,6 +457,7 @@ static int launch_block_det(const char* name, bool x3, float* pooled, const floa
   GN_REQUIRE(ab_out == nullptr || (has_b && wimg && b_ab),
              "%s: the AB output needs stage B, the prepared image and the pw_fc1 bias", name);
   GN_REQUIRE(((uintptr_t)ab_out & 15) == 0, "%s: ab_out must be 16-byte aligned", name);
+  GN_REQUIRE(ab_out == nullptr || ab_cols == 64 || ab_cols == 128, "%s: ab_cols must be 64 or 128", name);
   GN_REQUIRE((((uintptr_t)pooled | (uintptr_t)feats_in | (uintptr_t)feats_out |
                (uintptr_t)red_f32 | (uintptr_t)red_hl | (uintptr_t)wimg) & 15) == 0,
              "%s: pointers must be 16-byte aligned", name);
@@ -474,12 +476,12 @@ static int launch_block_det(const char* name, bool x3, float* pooled, const floa
     gn::block_det_tc_kernel<true><<<grid, gn::DT_THREADS, gn::DT_SMEM, (cudaStream_t)stream>>>(
         pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd,
         static_cast<const unsigned char*>(wimg), feats_out, red_f32,
-        static_cast<__nv_bfloat16*>(red_hl), b_ab, ab_out, num_dets, has_a, has_b);
+        static_cast<__nv_bfloat16*>(red_hl), b_ab, ab_out, ab_cols, num_dets, has_a, has_b);
   else
     gn::block_det_tc_kernel<false><<<grid, gn::DT_THREADS, gn::DT_SMEM, (cudaStream_t)stream>>>(
         pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd, b_rd,
         static_cast<const unsigned char*>(wimg), feats_out, red_f32,
-        static_cast<__nv_bfloat16*>(red_hl), b_ab, ab_out, num_dets, has_a, has_b);
+        static_cast<__nv_bfloat16*>(red_hl), b_ab, ab_out, ab_cols, num_dets, has_a, has_b);
   GN_CHECK_LAUNCH(name);
   return GN_OK;
 }
@@ -491,7 +493,7 @@ extern "C" int gn_block_det_fwd(float* pooled, const float* feats_in, const floa
                                 int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
   return launch_block_det("gn_block_det_fwd", true, pooled, feats_in, w_fc1, b_fc1, w_fc2, b_fc2, w_rd,
                           b_rd, nullptr, pooled != nullptr, w_rd != nullptr, feats_out, red_f32,
-                          red_hl, nullptr, nullptr, num_dets, shortcut_dim, pairfeat_dim,
+                          red_hl, nullptr, nullptr, 128, num_dets, shortcut_dim, pairfeat_dim,
                           reduced_dim, stream);
 }
 
@@ -504,8 +506,8 @@ extern "C" int gn_block_det_fwd_img(float* pooled, const float* feats_in, const 
   GN_REQUIRE(wimg != nullptr, "gn_block_det_fwd_img: null weight image");
   return launch_block_det("gn_block_det_fwd_img", true, pooled, feats_in, nullptr, b_fc1, nullptr,
                           b_fc2, nullptr, b_rd, wimg, has_stage_a, has_stage_b, feats_out, red_f32,
-                          red_hl, b_ab, ab_out, num_dets, shortcut_dim, pairfeat_dim, reduced_dim,
-                          stream);
+                          red_hl, b_ab, ab_out, 128, num_dets, shortcut_dim, pairfeat_dim,
+                          reduced_dim, stream);
 }
 
 extern "C" int gn_block_det_fwd_img_bf16(float* pooled, const float* feats_in, const void* wimg,
@@ -517,7 +519,23 @@ extern "C" int gn_block_det_fwd_img_bf16(float* pooled, const float* feats_in, c
   GN_REQUIRE(wimg != nullptr, "gn_block_det_fwd_img_bf16: null weight image");
   return launch_block_det("gn_block_det_fwd_img_bf16", false, pooled, feats_in, nullptr, b_fc1,
                           nullptr, b_fc2, nullptr, b_rd, wimg, has_stage_a, has_stage_b, feats_out,
-                          red_f32, red_hl, b_ab, ab_out, num_dets, shortcut_dim, pairfeat_dim,
+                          red_f32, red_hl, b_ab, ab_out, 128, num_dets, shortcut_dim, pairfeat_dim,
+                          reduced_dim, stream);
+}
+
+// The same kernel writing only U = red @ pw_fc1[32:64] + b_pw_fc1 as u_out[T, 64]: the
+// detection-level term of the TMA-fed pair stage (gn_block_tma.cu), which gathers the
+// neighbor rows itself.  plain_bf16 != 0: the bf16 arithmetic.
+extern "C" int gn_block_det_fwd_img_u(float* pooled, const float* feats_in, const void* wimg,
+                                      const float* b_fc1, const float* b_fc2, const float* b_rd,
+                                      int has_stage_a, int has_stage_b, float* feats_out,
+                                      void* red_hl, const float* b_u, float* u_out, int plain_bf16,
+                                      int num_dets, int shortcut_dim, int pairfeat_dim,
+                                      int reduced_dim, gn_stream_t stream) {
+  GN_REQUIRE(wimg != nullptr, "gn_block_det_fwd_img_u: null weight image");
+  return launch_block_det("gn_block_det_fwd_img_u", plain_bf16 == 0, pooled, feats_in, nullptr, b_fc1,
+                          nullptr, b_fc2, nullptr, b_rd, wimg, has_stage_a, has_stage_b, feats_out,
+                          nullptr, red_hl, b_u, u_out, 64, num_dets, shortcut_dim, pairfeat_dim,
                           reduced_dim, stream);
 }
 

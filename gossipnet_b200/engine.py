@@ -336,8 +336,10 @@ class GnetEngine(object):
             raise ValueError("pair_mode 'tma' needs the fused pair-feature MLP (shipped shapes)")
         pooled = self._buf('pooled', (T, g['pairfeat_dim']))
         pooled.zero_()   # every det launch re-zeroes it; this covers a dirty workspace
-        if ab_mode or tma_mode:
+        if ab_mode:
             inter = self._buf('ab', (T, 2 * g['pairfeat_dim']))
+        if tma_mode:
+            inter = self._buf('u', (T, g['pairfeat_dim']))     # U = red @ pw_fc1[32:64] + b
         if tma_mode:
             # reduced features as bf16 (hi | lo) rows + the all-zero row a self pair gathers
             red_all = self._buf('red_hl', (T + 1, 2 * g['reduced_dim']), torch.bfloat16)
@@ -357,13 +359,21 @@ class GnetEngine(object):
             s = 'gnet/block%d/' % b
             nxt = 'gnet/block%d/' % (b + 1)
             last = b == nb
+            if tma_mode:
+                ops.block_det_fwd_img_u(
+                    pooled_in, feats_in, image[det_off[b]:det_off[b] + det_b],
+                    p[s + 'fc1/biases'] if b >= 1 else None, p[s + 'fc2/biases'] if b >= 1 else None,
+                    None if last else p[nxt + 'reduce_dim/biases'], out,
+                    None if last else inter_hl, None if last else p[nxt + 'pw_fc1/biases'],
+                    None if last else inter, bf16=self.bf16)
+                return
             ops.block_det_fwd_img(
                 pooled_in, feats_in, image[det_off[b]:det_off[b] + det_b],
                 p[s + 'fc1/biases'] if b >= 1 else None, p[s + 'fc2/biases'] if b >= 1 else None,
                 None if last else p[nxt + 'reduce_dim/biases'], feats_out=out,
-                red_hl=None if (last or ab_mode) else (inter_hl if tma_mode else inter),
-                b_ab=p[nxt + 'pw_fc1/biases'] if ((ab_mode or tma_mode) and not last) else None,
-                ab_out=inter if ((ab_mode or tma_mode) and not last) else None, bf16=self.bf16)
+                red_hl=None if (last or ab_mode) else inter,
+                b_ab=p[nxt + 'pw_fc1/biases'] if (ab_mode and not last) else None,
+                ab_out=inter if (ab_mode and not last) else None, bf16=self.bf16)
 
         det(0, None, feats, None)
         for b in range(1, nb + 1):

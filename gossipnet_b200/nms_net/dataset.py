@@ -17,10 +17,14 @@ from gossipnet_b200.nms_net.config import cfg  # noqa: F401
 
 
 def load_roi(need_images, roi, is_training=False):
-    """dataset.py:17-45."""
-    if need_images:
-        raise NotImplementedError('image loading (cfg.gnet.imfeats / load_imfeats) is outside '
-                                  'the B200 hot path')
+    """dataset.py:17-45.  With cfg.gnet.imfeats the reference loads the image and runs
+    ResNet-101 on it; here the stride-16 feature map travels with the roidb entry as
+    `imfeats` [1,H,W,C] (network.py: Gnet._pack_imfeats) and is passed through.  Only an
+    entry that would need a real image decoded - no `imfeats` on it - is refused."""
+    if need_images and roi.get('imfeats') is None:
+        raise NotImplementedError('image loading (load_imfeats, or cfg.gnet.imfeats without a '
+                                  'precomputed `imfeats` feature map on the roidb entry) is '
+                                  'outside the B200 hot path')
     roi = dict(roi)
     roi['im_scale'] = 1.0
     return roi
@@ -77,6 +81,11 @@ class ShuffledDataset(object):
                 for i in self._take(k)]
 
 
+class _LoaderError(object):
+    def __init__(self, error):
+        self.error = error
+
+
 class Prefetcher(object):
     """Background thread filling a bounded queue with batches
     (train.py:80-109 / dataset.py:115-139 without the TF queue ops)."""
@@ -87,25 +96,41 @@ class Prefetcher(object):
         self._dataset, self._num_iter, self._k = dataset, num_iter, images_per_step
         self._thread = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
-        for _ in range(self._num_iter):
-            if self._stop.is_set():
+    def _put(self, item):
+        while not self._stop.is_set():
+            try:
+                self.q.put(item, timeout=0.1)
                 return
-            item = (self._dataset.next_batches(self._k) if self._k > 1
-                    else [self._dataset.next_batch()])
-            while not self._stop.is_set():
-                try:
-                    self.q.put(item, timeout=0.1)
-                    break
-                except queue.Full:
-                    continue
+            except queue.Full:
+                continue
+
+    def _run(self):
+        try:
+            for _ in range(self._num_iter):
+                if self._stop.is_set():
+                    return
+                self._put(self._dataset.next_batches(self._k) if self._k > 1
+                          else [self._dataset.next_batch()])
+        except BaseException as e:      # hand the failure to the consumer instead of dying silently
+            self._put(_LoaderError(e))
 
     def start(self):
         self._thread.start()
         return self
 
     def get(self):
-        return self.q.get()
+        """Next batch; re-raises an exception of the loader thread, and never blocks forever on
+        a thread that is gone."""
+        while True:
+            try:
+                item = self.q.get(timeout=1.0)
+            except queue.Empty:
+                if not self._thread.is_alive() and self.q.empty():
+                    raise RuntimeError('prefetch thread ended without delivering a batch')
+                continue
+            if isinstance(item, _LoaderError):
+                raise item.error
+            return item
 
     def size(self):
         return self.q.qsize()

@@ -315,6 +315,21 @@ def block_det_fwd_img(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out=None
               T, d, 64, 32, _stream())
 
 
+def block_det_fwd_img_u(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out, red_hl, b_u, u_out,
+                        bf16=False):
+    """block_det_fwd_img for the TMA-fed pair stage: next to red_hl it writes only
+    u_out[T,64] = red @ pw_fc1[32:64] + b_u (the detection-level term of the next pw_fc1)."""
+    f32 = torch.float32
+    T, d = feats_in.shape
+    _lib.call('gn_block_det_fwd_img_u', _chk(pooled, f32, 'pooled', True),
+              _chk(feats_in, f32, 'feats_in'), _chk(wimg, torch.uint8, 'wimg'),
+              _chk(b_fc1, f32, 'b_fc1', True), _chk(b_fc2, f32, 'b_fc2', True),
+              _chk(b_rd, f32, 'b_rd', True), 1 if b_fc1 is not None else 0,
+              1 if b_rd is not None else 0, _chk(feats_out, f32, 'feats_out', True),
+              _chk(red_hl, torch.bfloat16, 'red_hl', True), _chk(b_u, f32, 'b_u', True),
+              _chk(u_out, f32, 'u_out', True), 1 if bf16 else 0, T, d, 64, 32, _stream())
+
+
 def predict_collapse(flat, table, max_dim, scratch, w_eff, b_eff):
     """Fold the linear predict head into (w_eff, b_eff) (see gn_predict_collapse)."""
     f32 = torch.float32

@@ -54,6 +54,12 @@ def allreduce_sum_(flat):
     return flat
 
 
+def barrier():
+    """All ranks wait for each other (no-op for a single process)."""
+    if world() > 1:
+        dist.barrier()
+
+
 def max_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     if world() > 1:

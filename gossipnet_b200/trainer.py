@@ -36,6 +36,11 @@ class Trainer(object):
             raise ValueError('unknown optimizer {}'.format(self.optimizer))   # train.py:73
         self.momentum = cfg.train.momentum if momentum is None else momentum
         self.beta1, self.beta2, self.eps = beta1, beta2, eps
+        if float(cfg.train.gradient_clipping) > 0:
+            # slim.learning.create_train_op(clip_gradient_norm=...) clips every variable's
+            # gradient by its own norm (train.py:73-76); the shipped configs leave it at -1
+            raise NotImplementedError('cfg.train.gradient_clipping > 0 is not implemented in the '
+                                      'fused optimizer step; set it to -1 (the reference default)')
         wd = cfg.train.weight_decay if weight_decay is None else weight_decay
         dev = eng.device
         # flat gradient buffer + one trailing slot carrying the image count, so a

@@ -422,6 +422,15 @@ int gn_selftest_umma_rate(int n, int reps, int distinct_b, int ctas, int64_t* ou
 int gn_selftest_tma(const void* mat_bf16, int rows, const void* wmat_bf16, const int32_t* idx,
                     int row0, void* dump, float* d_out, gn_stream_t stream);
 
+/* gn_block_det_fwd_img writing only the detection-level half of the next block's pw_fc1
+ * (network.py:376-386 split by input rows): u_out[num_dets,64] = red @ pw_fc1[32:64] + b_u,
+ * next to red_hl.  Feeds gn_block_pair_fwd_tma.  plain_bf16 != 0: bf16 arithmetic. */
+int gn_block_det_fwd_img_u(float* pooled, const float* feats_in, const void* wimg,
+                           const float* b_fc1, const float* b_fc2, const float* b_rd,
+                           int has_stage_a, int has_stage_b, float* feats_out, void* red_hl,
+                           const float* b_u, float* u_out, int plain_bf16, int num_dets,
+                           int shortcut_dim, int pairfeat_dim, int reduced_dim, gn_stream_t stream);
+
 /* Store-bandwidth micro-benchmark: writes `bytes` (multiple of 16384) bytes of constants with
  * mode 0 st.global.v4 | 1 st.global.cs.v4 | 2 st.global.v8 (256-bit) | 3 st.global.wt.v4 |
  * 4 cp.async.bulk shared->global (16 KB copies) | 5 st.global.v8 + L2 evict-first policy,

@@ -30,8 +30,11 @@ from gossipnet_b200.checkpoint import load_variables  # noqa: E402
 from gossipnet_b200.session import InferenceSession  # noqa: E402
 
 
-def test_run(test_imdb, images_per_call=64, model=None):
-    """test.py:42-83 -> [{'id', 'dets', 'det_classes', 'det_scores'}, ...]."""
+def test_run(test_imdb, images_per_call=64, model=None, allow_random_init=False):
+    """test.py:42-83 -> [{'id', 'dets', 'det_classes', 'det_scores'}, ...].  Like the
+    reference (restorer.restore(sess, cfg.test_model), test.py:52-54) this needs a trained
+    model: without one it raises instead of rescoring with random weights
+    (`allow_random_init` is for tests of the plumbing)."""
     roidb = test_imdb['roidb']
     batch_spec = Gnet.get_batch_spec(num_classes=test_imdb['num_classes'], is_training=False)
     need_image = 'image' in batch_spec
@@ -40,6 +43,8 @@ def test_run(test_imdb, images_per_call=64, model=None):
     model = cfg.get('test_model') if model is None else model
     if model:
         net.load_state_dict(load_variables(model))
+    elif not allow_random_init:
+        raise ValueError('no model to test: pass -m / --model or set cfg.test_model')
     sess = InferenceSession(net)
 
     rois = [load_roi(need_image, roi) for roi in roidb

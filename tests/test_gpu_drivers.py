@@ -78,7 +78,9 @@ def test_test_driver_writes_frcn_pickle(tmp_path, monkeypatch):
     small_cfg()
     test_imdb = imdb.get_imdb(cfg.test.imdb, is_training=False)
     test = import_driver('test')
-    dets = test.test_run(test_imdb, images_per_call=2)          # 3 images: chunks of 2 + 1
+    with pytest.raises(ValueError):        # no model configured: refuse, like the reference
+        test.test_run(test_imdb, images_per_call=2)
+    dets = test.test_run(test_imdb, images_per_call=2, allow_random_init=True)   # 3 images: chunks of 2 + 1
     assert [d['id'] for d in dets] == [r['id'] for r in test_imdb['roidb']]
     net = Gnet(1, reuse=True)
     for d, roi in zip(dets, test_imdb['roidb']):

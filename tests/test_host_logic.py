@@ -117,3 +117,33 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d['e2e'] == {'value': d['value'], 'unit': 'detections/s', 'h2d_bytes_per_step': 0,
                         'd2h_bytes_per_step': 0}
     assert 'workload' in d['config']
+
+
+def test_prefetcher_reraises_loader_errors_and_passes_feature_maps():
+    """A failing loader thread must surface in get() (it used to die silently and block the
+    training loop forever); roidb entries that carry their feature map pass through load_roi
+    when cfg.gnet.imfeats asks for image features."""
+    import numpy as np
+    import pytest
+    from gossipnet_b200.nms_net.dataset import Prefetcher, load_roi
+
+    class Broken(object):
+        def __init__(self):
+            self.n = 0
+
+        def next_batch(self):
+            self.n += 1
+            if self.n == 3:
+                raise KeyError('bad roidb entry')
+            return {'id': self.n}
+
+    p = Prefetcher(Broken(), 10, q_size=2).start()
+    assert p.get() == [{'id': 1}] and p.get() == [{'id': 2}]
+    with pytest.raises(KeyError):
+        p.get()
+    p.stop()
+
+    roi = {'dets': np.zeros((1, 4), np.float32), 'imfeats': np.zeros((1, 4, 4, 8), np.float32)}
+    assert load_roi(True, roi)['imfeats'] is roi['imfeats']
+    with pytest.raises(NotImplementedError):
+        load_roi(True, {'dets': np.zeros((1, 4), np.float32)})

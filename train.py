@@ -96,11 +96,13 @@ def train(resume, visualize, images_per_step=1):
             lr = lr_gen.get_lr(it)
             batches = prefetch.get()
             res = trainer.step(parallel.shard(batches), lr)
+            # the reference updates its ExponentialMovingAverage on EVERY train step
+            # (train.py:263-272, 316-320), not only when it prints
+            lo = res['loss_out'].sum(dim=0).cpu().numpy() / max(1, res['num_images']) \
+                if res.get('loss_out') is not None else np.zeros(3)
+            avg = smoothed.update(total=lo[2] + trainer.regularization_loss(), normed=lo[1],
+                                  unnormed=lo[0])
             if it % cfg.train.display_iter == 0 and chatty:
-                lo = res['loss_out'].sum(dim=0).cpu().numpy() / max(1, res['num_images']) \
-                    if res.get('loss_out') is not None else np.zeros(3)
-                reg = trainer.regularization_loss()
-                avg = smoothed.update(total=lo[2] + reg, normed=lo[1], unnormed=lo[0])
                 print(('{}  iter {:6d}   lr {:8g}   opt loss {:8g}     '
                        'data loss normalized {:8g}   unnormalized {:8g}').format(
                     datetime.now(), it, lr, avg['total'], avg['normed'], avg['unnormed']))
@@ -120,6 +122,10 @@ def train(resume, visualize, images_per_step=1):
                 if chatty:
                     save_path = saver.save(trainer, net.name, global_step=it)
                     print('wrote model to {}'.format(save_path))
+            if (do_val and it % cfg.train.val_iter == 0) or it % cfg.train.save_iter == 0:
+                # rank 0 validated / saved alone: the others wait HERE, not inside the next
+                # step's all-reduce (a long validation would run into the NCCL watchdog)
+                parallel.barrier()
     finally:
         prefetch.stop()
     if chatty:
