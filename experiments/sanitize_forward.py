@@ -45,5 +45,18 @@ img['imfeats'] = np.random.RandomState(0).normal(size=(1, 38, 63, 8)).astype(np.
 tr = Trainer(net)
 out = tr.step([img], 1e-3)
 print('imfeats train ', float(out['loss_out'].sum()))
+# training step on the tensor-core FC kernels (gn_fc_tc.cu), two images, multi-class
+setup('coco_multiclass', 2)
+tr = Trainer(Gnet(80))
+out = tr.step([synthetic.make_image(120, 80, image_index=1), synthetic.make_image(77, 80, image_index=2)], 1e-3)
+print('tc train      ', float(out['loss_out'].sum()))
+# dense IoU (symmetric kernel) and the TMA self-test
+from gossipnet_b200 import ops
+dd = torch.from_numpy(synthetic.make_image(333, 1)['dets']).cuda()
+print('iou           ', float(ops.iou_dense(dd, dd).sum()))
+mat = torch.randn(500, 64, device='cuda').to(torch.bfloat16)
+wm = torch.randn(64, 64, device='cuda').to(torch.bfloat16)
+dump, dout = ops.selftest_tma(mat, wm, torch.arange(128, dtype=torch.int32, device='cuda'), 0)
+print('tma selftest  ', float(dout.sum()))
 torch.cuda.synchronize()
 print('done')

@@ -111,8 +111,8 @@ block_pair_tma_kernel(const __grid_constant__ CUtensorMap tm_pw,
   uint64_t* h1_full = fc1_done + 2;              // [2] 8 epilogue-1 warps
   uint64_t* fc2_done = h1_full + 2;              // [2] tcgen05.commit
   uint64_t* d2_free = fc2_done + 2;              // [2] 4 epilogue-2 warps
-  uint64_t* stg_full = d2_free + 2;              // [2] 4 epilogue-2 warps
-  uint64_t* stg_free = stg_full + 2;             // [2] 8 pool warps
+  uint64_t* stg_full = d2_free + 2;              // [2] 128 epilogue-2 threads
+  uint64_t* stg_free = stg_full + 2;             // [2] 256 pool threads
   uint64_t* wbar = stg_free + 2;                 // weight image landed
 
   if (warp == 0) umma::tmem_alloc(&tmem_base_s, 512);
@@ -126,8 +126,8 @@ block_pair_tma_kernel(const __grid_constant__ CUtensorMap tm_pw,
       umma::mbar_init(&h1_full[s], BT_EPI1_WARPS);
       umma::mbar_init(&fc2_done[s], 1);
       umma::mbar_init(&d2_free[s], BT_EPI2_WARPS);
-      umma::mbar_init(&stg_full[s], BT_EPI2_WARPS);
-      umma::mbar_init(&stg_free[s], BT_POOL_WARPS);
+      umma::mbar_init(&stg_full[s], BT_EPI2_WARPS * 32);   // staging tile: every thread releases /
+      umma::mbar_init(&stg_free[s], BT_POOL_WARPS * 32);   // acquires its own rows (racecheck clean)
     }
     umma::mbar_init(wbar, 1);
     umma::fence_barrier_init();
@@ -376,8 +376,7 @@ block_pair_tma_kernel(const __grid_constant__ CUtensorMap tm_pw,
         dst[k] = make_float4(v0[4 * k], v0[4 * k + 1], v0[4 * k + 2], v0[4 * k + 3]);
         dst[8 + k] = make_float4(v1[4 * k], v1[4 * k + 1], v1[4 * k + 2], v1[4 * k + 3]);
       }
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&stg_full[b]);
+      umma::mbar_arrive(&stg_full[b]);
       if (t == BT_WARP_EPI2 * 32) BT_TR(11);
     }
     if (t == BT_WARP_EPI2 * 32) BT_ACC_FLUSH(16);
@@ -414,8 +413,7 @@ block_pair_tma_kernel(const __grid_constant__ CUtensorMap tm_pw,
       float2 x[16];
 #pragma unroll
       for (int r = 0; r < 16; ++r) x[r] = *reinterpret_cast<const float2*>(col + r * BT_LDS);
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&stg_free[b]);   // the rows live in registers now
+      umma::mbar_arrive(&stg_free[b]);   // this thread's rows live in registers now
       float cur0 = -FLT_MAX, cur1 = -FLT_MAX;
 #pragma unroll
       for (int r = 0; r < 16; ++r) {

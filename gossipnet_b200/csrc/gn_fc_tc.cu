@@ -283,7 +283,7 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
   unsigned char* raw_base = smem;
   unsigned char* op_base = smem + (bulk ? (uint32_t)raw_stages * raw_stage_bytes : 0u);
   uint64_t* raw_full = bars;                         // [raw_stages] bulk copies landed
-  uint64_t* raw_empty = bars + WT_MAX_RAW;           // [raw_stages] 8 converter warps
+  uint64_t* raw_empty = bars + WT_MAX_RAW;           // [raw_stages] 256 converter threads
   uint64_t* op_full = bars + 2 * WT_MAX_RAW;         // [2] 8 converter warps
   uint64_t* op_empty = op_full + WT_OPS;             // [2] tcgen05.commit
   uint64_t* done = op_empty + WT_OPS;
@@ -299,7 +299,7 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
   if (t == 0) {
     for (int s = 0; s < raw_stages; ++s) {
       umma::mbar_init(&raw_full[s], 1);
-      umma::mbar_init(&raw_empty[s], WT_CONV_WARPS);
+      umma::mbar_init(&raw_empty[s], WT_CONV);          // every converter thread releases its reads
     }
     for (int s = 0; s < WT_OPS; ++s) {
       umma::mbar_init(&op_full[s], WT_CONV_WARPS);
@@ -475,11 +475,9 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
         }
       }
       umma::fence_smem_to_async();
+      if (bulk) umma::mbar_arrive(&raw_empty[s]);     // this thread's reads of the raw stage are done
       __syncwarp();
-      if (lane == 0) {
-        umma::mbar_arrive(&op_full[o]);
-        if (bulk) umma::mbar_arrive(&raw_empty[s]);
-      }
+      if (lane == 0) umma::mbar_arrive(&op_full[o]);
       if (++s == raw_stages) { s = 0; ++nuse; }
     }
     if (db != nullptr) {

@@ -189,12 +189,12 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       umma::mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      umma::mbar_init(&a1_full[b], 4);
+      umma::mbar_init(&a1_full[b], 4 * 32);        // every geometry thread arrives itself
       umma::mbar_init(&a1_empty[b], 1);
       umma::mbar_init(&l1_done[b], 1);
       umma::mbar_init(&h_full[b], PP_EPI_WARPS);
       umma::mbar_init(&h_empty[b], 1);
-      umma::mbar_init(&tab_free[b], PP_EPI_WARPS);
+      umma::mbar_init(&tab_free[b], PP_EPI_WARPS * 32);
     }
     umma::mbar_init(acc2_done, 1);
     umma::mbar_init(acc3_done, 1);
@@ -283,8 +283,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         produce(v, bias1 + col);
         if (t == 0) PP_TR(33 + 2 * q);
       }
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&tab_free[tb]);   // score tables of this tile are dead
+      umma::mbar_arrive(&tab_free[tb]);   // this thread's score-table reads of the tile are done
       // ---- layer-2 accumulator quarters -> H --------------------------------------------
       umma::mbar_wait_relaxed(acc2_done, (uint32_t)it & 1u);
       umma::tc_fence_after();
@@ -537,9 +536,12 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         reinterpret_cast<int*>(t_sc)[2 * PT_TILE + row] = rc;
         reinterpret_cast<int*>(t_sc)[3 * PT_TILE + row] = rn;
       }
+      // every thread releases its own stores (operand rows and score-table entries) with its
+      // own arrival: the hand-off is then a plain per-thread release / acquire pair, which is
+      // also what compute-sanitizer's racecheck can follow (an elected lane arriving for its
+      // warp was reported as 4 hazards on the tables in round 1)
       umma::fence_smem_to_async();
-      __syncwarp();
-      if (lane == 0) umma::mbar_arrive(&a1_full[ab]);
+      umma::mbar_arrive(&a1_full[ab]);
     }
   }
 
