@@ -77,6 +77,7 @@ SIGNATURES = {
     'gn_block_pair_fwd_ffma': [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                c_void_p, c_void_p],
+    'gn_detection_matching_workspace_ints': [c_int],
     'gn_detection_matching': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p],
@@ -128,7 +129,8 @@ _RESTYPES = {'gn_last_error': ctypes.c_char_p, 'gn_pwfeat_prep_bytes': ctypes.c_
              'gn_block_pair_image_bytes': ctypes.c_int64,
              'gn_block_det_image_bytes': ctypes.c_int64,
              'gn_block_pair_ab_image_bytes': ctypes.c_int64,
-             'gn_block_pair_tma_image_bytes': ctypes.c_int64}
+             'gn_block_pair_tma_image_bytes': ctypes.c_int64,
+             'gn_detection_matching_workspace_ints': ctypes.c_int64}
 
 _lib = None
 # number of C-ABI compute calls made so far (each is one kernel launch of this

@@ -225,6 +225,10 @@ fc_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mas
 // (up to 4 in flight); eight converter warps read a raw stage, apply the mask, split to bf16
 // hi / lo and write both operands TRANSPOSED (an 8-row group of one column = one 16-byte
 // K-major chunk) into a two-stage operand ring; one thread issues the UMMAs.
+// Measured (wait-time accumulators, experiments/wgrad_time.py): the converters set the pace -
+// one pass over a warp's units costs ~1 300 (x) / ~2 400 (dy + mask) cycles whatever the number
+// of active lanes, so P-row calls take ~140 us (1.7-3.7 TB/s of operand traffic); dealing the
+// units out as quarter-warps over all eight warps made every warp run both passes (172 us).
 //   warps 0-7 converters (+ the epilogue)   warp 8 UMMA issuer   warp 9 bulk-copy producer
 // ==================================================================================
 constexpr int WT_CONV_WARPS = 8, WT_CONV = WT_CONV_WARPS * 32;
@@ -354,7 +358,8 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
 #pragma unroll 1
       for (int it = 0; it < my_chunks; ++it) {
         const int o = it & 1;
-        umma::mbar_wait(&op_full[o], ((uint32_t)it >> 1) & 1u);
+        // relaxed: a hot spin here would share its scheduler with two converter warps
+        umma::mbar_wait_relaxed(&op_full[o], ((uint32_t)it >> 1) & 1u);
         umma::tc_fence_after();
         const uint32_t sa = sbase + o * op_stage_bytes, sb = sa + 2 * a_half;
         const uint64_t d_bh = umma::smem_desc(sb, lbo_b, 128), d_bl = umma::smem_desc(sb + b_half, lbo_b, 128);

@@ -10,19 +10,24 @@
 //   2. GT order: introsort on the ignore flags (det_matching.cc:98), thread 0
 //      (G is small; the order among crowd GTs decides which one a detection
 //      gets, so it has to be the same permutation).
-//   3. greedy scan (det_matching.cc:125-159), warp 0: 32 ranks at a time each
-//      lane tests whether ITS detection has any IoU >= 0.5 at all (most do
-//      not, and an unmatched detection changes no state), then the candidates
-//      are visited strictly in order with the GT scan spread over the lanes:
-//      regular GTs -> arg max of (iou, position) among unmatched ones >= 0.5;
-//      only if none: first crowd GT >= 0.5.  Equivalent to the sequential loop
-//      for non-NaN IoUs.
+//   3. greedy scan (det_matching.cc:125-159).  The sequential loop takes, for a detection,
+//      the arg max of (iou, position) among the still unmatched regular GTs with
+//      iou >= 0.5, and only if there is none the first crowd GT with iou >= 0.5
+//      (equivalent for non-NaN IoUs).  Which GTs are ELIGIBLE does not depend on the order,
+//      only which are still unmatched does.  So all threads first build, per detection, the
+//      list of its eligible regular GTs sorted by (iou, position) descending (up to DM_K of
+//      them; a detection rarely overlaps more than two) and its first eligible crowd GT;
+//      the sequential part is then one thread walking short lists in shared memory - a few
+//      instructions per detection instead of a warp-wide scan + reduction (1.45 ms -> ~0.1 ms
+//      for 8 images of 1000 detections).
 #include "gn_common.cuh"
 #include "gn_introsort.cuh"
 
 namespace gn {
 
 constexpr int DM_THREADS = 256;
+constexpr int DM_K = 6;              // eligible regular GTs kept per detection
+constexpr int DM_REC = DM_K + 2;     // + number of eligible regular GTs, + first crowd position
 
 struct LessScore {
   const float* k;
@@ -38,7 +43,8 @@ detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restri
                           const float* __restrict__ score, const uint8_t* __restrict__ ignore,
                           const int32_t* __restrict__ img_off, const int32_t* __restrict__ gt_off,
                           float* __restrict__ labels, float* __restrict__ weights,
-                          int32_t* __restrict__ assignment, int32_t* __restrict__ order_ws) {
+                          int32_t* __restrict__ assignment, int32_t* __restrict__ order_ws,
+                          int32_t* __restrict__ lists) {
   extern __shared__ int32_t dm_smem[];
   const int img = blockIdx.x;
   const int d0 = img_off[img], n = img_off[img + 1] - d0;
@@ -93,71 +99,97 @@ detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restri
     }
     __syncthreads();
   }
-  if (t >= 32 || G == 0) return;
+  if (G == 0) return;
 
-  // number of regular GTs = first crowd position in gt_order
+  // number of regular GTs = first crowd position in gt_order (block-uniform)
   int R = 0;
-  for (int k = t; k < G; k += 32) R += (ign[gt_order[k]] == 0);
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) R += __shfl_xor_sync(0xffffffffu, R, d);
+  for (int k = 0; k < G; ++k) R += (ign[gt_order[k]] == 0);
 
-  // ---- 3. greedy ---------------------------------------------------------------
+  // ---- 3a. per-detection candidate records (all threads) -------------------------
   const float thresh = 0.5f;  // det_matching.cc:73
+  int32_t* rec = lists + (size_t)d0 * DM_REC;
+  for (int i = t; i < n; i += DM_THREADS) {
+    const float* row = M + (size_t)i * G;
+    float bv[DM_K];
+    int bp[DM_K];
+#pragma unroll
+    for (int j = 0; j < DM_K; ++j) { bv[j] = -1.f; bp[j] = -1; }
+    int cnt = 0;
+    for (int k = 0; k < R; ++k) {
+      const float v = __ldg(row + gt_order[k]);
+      if (v >= thresh) {               // (a NaN is never taken by the arg-max scan either)
+        ++cnt;
+        // insert (v, k) keeping (value, position) descending; later position wins ties
+        float cv = v;
+        int cp = k;
+#pragma unroll
+        for (int j = 0; j < DM_K; ++j) {
+          const bool better = bp[j] < 0 || cv > bv[j] || (cv == bv[j] && cp > bp[j]);
+          if (better) {
+            const float tv = bv[j]; const int tp = bp[j];
+            bv[j] = cv; bp[j] = cp;
+            cv = tv; cp = tp;
+          }
+        }
+      }
+    }
+    int fc = -1;
+    for (int k = R; k < G && fc < 0; ++k)
+      if (!(__ldg(row + gt_order[k]) < thresh)) fc = k;
+#pragma unroll
+    for (int j = 0; j < DM_K; ++j) rec[(size_t)i * DM_REC + j] = bp[j];
+    rec[(size_t)i * DM_REC + DM_K] = cnt;
+    rec[(size_t)i * DM_REC + DM_K + 1] = fc;
+  }
+  __syncthreads();
+  if (t >= 32) return;
+
+  // ---- 3b. greedy, in visiting order: warp 0 stages 32 records, lane 0 walks them --------
+  __shared__ int32_t chunk[32][DM_REC + 1];
   for (int base = 0; base < n; base += 32) {
     const int my_rank = base + t;
     const int my_det = my_rank < n ? order[my_rank] : -1;
-    bool cand = false;
+    chunk[t][DM_REC] = my_det;
     if (my_det >= 0) {
-      const float* row = M + (size_t)my_det * G;
-      for (int k = 0; k < G; ++k) cand |= !(__ldg(row + k) < thresh);
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, cand);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int det = __shfl_sync(0xffffffffu, my_det, src);
-      const float* row = M + (size_t)det * G;
-      // regular GTs: best = (iou, position) lexicographic max among unmatched >= thresh
-      float best = -1.f;
-      int best_pos = -1;
-      for (int k = t; k < R; k += 32) {
-        const int gt = gt_order[k];
-        const float v = __ldg(row + gt);
-        if (!taken[gt] && !(v < thresh) && (v > best || (v == best && k > best_pos))) {
-          best = v;
-          best_pos = k;
-        }
-      }
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, d);
-        const int op = __shfl_xor_sync(0xffffffffu, best_pos, d);
-        if (op >= 0 && (best_pos < 0 || ov > best || (ov == best && op > best_pos))) {
-          best = ov;
-          best_pos = op;
+      for (int j = 0; j < DM_REC; ++j) chunk[t][j] = rec[(size_t)my_det * DM_REC + j];
+    }
+    __syncwarp();
+    if (t == 0) {
+      const int m = min(32, n - base);
+      for (int e = 0; e < m; ++e) {
+        const int det = chunk[e][DM_REC];
+        const int cnt = chunk[e][DM_K], fc = chunk[e][DM_K + 1];
+        if (cnt == 0 && fc < 0) continue;            // overlaps nothing: changes no state
+        int match_pos = -1;
+        for (int j = 0; j < DM_K && j < cnt; ++j) {
+          const int pos = chunk[e][j];
+          if (!taken[gt_order[pos]]) { match_pos = pos; break; }
         }
-      }
-      int match_pos = best_pos;
-      if (match_pos < 0) {
-        // no regular GT: the first crowd GT (in gt_order) with IoA >= thresh wins
-        for (int k0 = R; k0 < G && match_pos < 0; k0 += 32) {
-          const int k = k0 + t;
-          const bool ok = k < G && !(__ldg(row + gt_order[k]) < thresh);
-          const unsigned m = __ballot_sync(0xffffffffu, ok);
-          if (m) match_pos = k0 + __ffs(m) - 1;
+        if (match_pos < 0 && cnt > DM_K) {
+          // more eligible GTs than the record keeps and all kept ones are taken: full scan
+          const float* row = M + (size_t)det * G;
+          float best = -1.f;
+          for (int k = 0; k < R; ++k) {
+            const int gt = gt_order[k];
+            const float v = __ldg(row + gt);
+            if (!taken[gt] && v >= thresh && (v > best || (v == best && k > match_pos))) {
+              best = v;
+              match_pos = k;
+            }
+          }
         }
-      }
-      if (match_pos >= 0) {
-        const int gt = gt_order[match_pos];
-        if (t == 0) {
+        if (match_pos < 0) match_pos = fc;           // no regular GT: the first eligible crowd GT
+        if (match_pos >= 0) {
+          const int gt = gt_order[match_pos];
           taken[gt] = 1;
           labels[d0 + det] = 1.f;
           assignment[d0 + det] = gt;
           if (ign[gt]) weights[d0 + det] = 0.f;
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   }
 }
 
@@ -217,6 +249,10 @@ loss_fwd_kernel(const float* __restrict__ prediction, const float* __restrict__ 
 
 }  // namespace gn
 
+extern "C" int64_t gn_detection_matching_workspace_ints(int num_dets) {
+  return (int64_t)(num_dets > 0 ? num_dets : 0) * (1 + gn::DM_REC) + 1;
+}
+
 extern "C" int gn_detection_matching(const float* iou, const int64_t* iou_off,
                                      const float* score, const uint8_t* ignore,
                                      const int32_t* img_off, const int32_t* gt_off,
@@ -238,8 +274,10 @@ extern "C" int gn_detection_matching(const float* iou, const int64_t* iou_off,
     gn::set_error("gn_detection_matching: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return GN_ERR_CUDA;
   }
+  // workspace: visiting order [num_dets], then the candidate records [num_dets, DM_REC]
   gn::detection_matching_kernel<<<num_images, gn::DM_THREADS, smem, (cudaStream_t)stream>>>(
-      iou, iou_off, score, ignore, img_off, gt_off, labels, weights, assignment, workspace);
+      iou, iou_off, score, ignore, img_off, gt_off, labels, weights, assignment, workspace,
+      workspace + num_dets);
   GN_CHECK_LAUNCH("gn_detection_matching");
   return GN_OK;
 }

@@ -408,7 +408,8 @@ def detection_matching_batched(iou, iou_off, score, ignore, img_off, gt_off, max
     labels = torch.empty(n, dtype=torch.float32, device=dev)
     weights = torch.empty(n, dtype=torch.float32, device=dev)
     assignment = torch.empty(n, dtype=torch.int32, device=dev)
-    ws = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ws = torch.empty(int(_lib.load().gn_detection_matching_workspace_ints(n)), dtype=torch.int32,
+                     device=dev)
     _lib.call('gn_detection_matching', _chk(iou, torch.float32, 'iou'),
               _chk(iou_off, torch.int64, 'iou_off'), _chk(score, torch.float32, 'score'),
               _chk(ignore, torch.uint8, 'ignore'), _chk(img_off, torch.int32, 'img_off'),

@@ -205,13 +205,14 @@ class Trainer(object):
             for i in range(1, g['num_block_pw_fc'] + 1):
                 h = self._fc(h, s + 'pw_fc%d' % i, True, rows_dev=num_pairs)
                 hs.append(h)
-            del x   # recomputed in backward: one gather instead of P x 96 floats per block
+            # x stays alive for the backward (pw_fc1's weight gradient needs it): 119 MB per
+            # block at P = 311 k is nothing on 180 GB, and re-gathering cost 79 us per block
             pooled = ops.segment_max(h, row_ptr, T)
             ds = [pooled]
             for i in range(1, g['num_block_fc']):
                 ds.append(self._fc(ds[-1], s + 'fc%d' % i, True))
             out = self._fc(ds[-1], s + 'fc%d' % g['num_block_fc'], True, residual=feats)
-            tape.append((feats, red, nred, hs, ds, out))
+            tape.append((feats, red, nred, hs, ds, out, x))
             feats = out
         pred_acts = [feats]
         for i in range(1, g['num_predict_fc']):
@@ -232,14 +233,14 @@ class Trainer(object):
         dpw = torch.zeros((cap, w), dtype=torch.float32, device=eng.device)
         for b in range(g['num_blocks'], 0, -1):
             s = 'gnet/block%d/' % b
-            feats_in, red, nred, hs, ds, out = tape[b - 1]
+            feats_in, red, nred, hs, ds, out, x = tape[b - 1]
+            tape[b - 1] = None                               # free this block's activations
             ops.relu_mask(dfeats, out)                      # shortcut relu (network.py:407-408)
             dd = self._fc_bwd(ds[-1], dfeats, s + 'fc%d' % g['num_block_fc'])
             for i in range(g['num_block_fc'] - 1, 0, -1):
                 ops.relu_mask(dd, ds[i])
                 dd = self._fc_bwd(ds[i - 1], dd, s + 'fc%d' % i)
             dh = torch.empty_like(hs[-1]) if hs else None
-            x = ops.block_gather_concat(pw, red, nred, pair_c, pair_n, num_pairs, cap)
             if hs:
                 ops.segment_max_bwd(hs[-1], ds[0], dd, row_ptr, dh)
                 for i in range(g['num_block_pw_fc'], 0, -1):

@@ -293,7 +293,9 @@ int gn_block_pair_fwd_ffma(const float* pw, int w, const float* feats,
  * sequence, gn_introsort.cuh), so results are bit-identical to a g++ build of
  * det_matching.cc for any non-NaN input.
  * max_gt: largest g_i of the batch (host-known; sizes the shared-memory GT
- * tables).  workspace: int32[num_dets] (visiting order). */
+ * tables).  workspace: int32[gn_detection_matching_workspace_ints(num_dets)] (visiting
+ * order + per-detection candidate records). */
+int64_t gn_detection_matching_workspace_ints(int num_dets);
 int gn_detection_matching(const float* iou, const int64_t* iou_off,
                           const float* score, const uint8_t* ignore,
                           const int32_t* img_off, const int32_t* gt_off,
