@@ -225,13 +225,15 @@ fc_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mas
 // (up to 4 in flight); eight converter warps read a raw stage, apply the mask, split to bf16
 // hi / lo and write both operands TRANSPOSED (an 8-row group of one column = one 16-byte
 // K-major chunk) into a two-stage operand ring; one thread issues the UMMAs.
-// Measured (wait-time accumulators, experiments/wgrad_time.py): the converters set the pace -
-// one pass over a warp's units costs ~1 300 (x) / ~2 400 (dy + mask) cycles whatever the number
-// of active lanes, so P-row calls take ~140 us (1.7-3.7 TB/s of operand traffic); dealing the
-// units out as quarter-warps over all eight warps made every warp run both passes (172 us).
-//   warps 0-7 converters (+ the epilogue)   warp 8 UMMA issuer   warp 9 bulk-copy producer
+// Measured (experiments/wgrad_time.py, P = 311 072 rows): 101 us for 64 x 64 (2.4 TB/s of
+// operand traffic), 243 us for 256 x 256 (3.9 TB/s).  The converters set the pace: one pass
+// over a warp's units costs 900-1 900 cycles almost independently of the unit width, so
+// sixteen converter warps with at most one unit of x and one of dy per thread and stage are
+// used (8 warps, 4-column units: 136 us; dealing units out as quarter-warps so that every warp
+// ran both passes: 172 us).
+//   warps 0-15 converters (0-7 also the epilogue)   warp 16 UMMA issuer   warp 17 bulk-copy producer
 // ==================================================================================
-constexpr int WT_CONV_WARPS = 8, WT_CONV = WT_CONV_WARPS * 32;
+constexpr int WT_CONV_WARPS = 16, WT_CONV = WT_CONV_WARPS * 32;
 constexpr int WT_THREADS = (WT_CONV_WARPS + 2) * 32;
 constexpr int WT_MAX_RAW = 4, WT_OPS = 2;
 
@@ -263,6 +265,63 @@ static WtPlan wt_plan(int k, int n, bool has_mask, bool contiguous) {
   return p;
 }
 
+// One converter unit: 8 rows (row group g of the stage) x W consecutive columns of an operand
+// tile -> W K-major chunk pairs (hi, lo).  Source: the raw fp32 stage in shared memory, or
+// global memory for chunks that did not go through the bulk-copy ring.  `msk`: relu mask of
+// the same shape (value kept where mask > 0); `bsum`: running column sums of what was kept.
+template <int W>
+__device__ __forceinline__ void wt_convert_unit(const float* __restrict__ src, const float* __restrict__ msk,
+                                                size_t pitch, int col, int row_first, int rows_left,
+                                                unsigned char* dst, uint32_t half_bytes,
+                                                float* bsum) {
+  float v[8][W];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+#pragma unroll
+    for (int c = 0; c < W; ++c) v[e][c] = 0.f;
+    if (e < rows_left) {
+      const float* p = src + (size_t)(row_first + e) * pitch + col;
+      float m[W];
+      if constexpr (W == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        v[e][0] = a.x; v[e][1] = a.y; v[e][2] = a.z; v[e][3] = a.w;
+        if (msk != nullptr) {
+          const float4 b = *reinterpret_cast<const float4*>(msk + (size_t)(row_first + e) * pitch + col);
+          m[0] = b.x; m[1] = b.y; m[2] = b.z; m[3] = b.w;
+        }
+      } else if constexpr (W == 2) {
+        const float2 a = *reinterpret_cast<const float2*>(p);
+        v[e][0] = a.x; v[e][1] = a.y;
+        if (msk != nullptr) {
+          const float2 b = *reinterpret_cast<const float2*>(msk + (size_t)(row_first + e) * pitch + col);
+          m[0] = b.x; m[1] = b.y;
+        }
+      } else {
+        v[e][0] = *p;
+        if (msk != nullptr) m[0] = msk[(size_t)(row_first + e) * pitch + col];
+      }
+      if (msk != nullptr) {
+#pragma unroll
+        for (int c = 0; c < W; ++c) v[e][c] = m[c] > 0.f ? v[e][c] : 0.f;
+      }
+      if (bsum != nullptr) {
+#pragma unroll
+        for (int c = 0; c < W; ++c) bsum[c] += v[e][c];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < W; ++c) {
+    uint4 h, l;
+    umma::split_bf16x2(v[0][c], v[1][c], h.x, l.x);
+    umma::split_bf16x2(v[2][c], v[3][c], h.y, l.y);
+    umma::split_bf16x2(v[4][c], v[5][c], h.z, l.z);
+    umma::split_bf16x2(v[6][c], v[7][c], h.w, l.w);
+    *reinterpret_cast<uint4*>(dst + c * 16) = h;
+    *reinterpret_cast<uint4*>(dst + half_bytes + c * 16) = l;
+  }
+}
+
 __global__ void __launch_bounds__(WT_THREADS, 1)
 fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ dy, int ldy,
                    const float* __restrict__ mask, float* __restrict__ dw, float* __restrict__ db,
@@ -287,8 +346,8 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
   unsigned char* raw_base = smem;
   unsigned char* op_base = smem + (bulk ? (uint32_t)raw_stages * raw_stage_bytes : 0u);
   uint64_t* raw_full = bars;                         // [raw_stages] bulk copies landed
-  uint64_t* raw_empty = bars + WT_MAX_RAW;           // [raw_stages] 256 converter threads
-  uint64_t* op_full = bars + 2 * WT_MAX_RAW;         // [2] 8 converter warps
+  uint64_t* raw_empty = bars + WT_MAX_RAW;           // [raw_stages] every converter thread
+  uint64_t* op_full = bars + 2 * WT_MAX_RAW;         // [2] the converter warps
   uint64_t* op_empty = op_full + WT_OPS;             // [2] tcgen05.commit
   uint64_t* done = op_empty + WT_OPS;
   const uint32_t x_bytes = (uint32_t)R * (uint32_t)k * 4u, d_bytes = (uint32_t)R * (uint32_t)n * 4u;
@@ -376,12 +435,17 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
     }
   } else {
     // ================================ converters ======================================
-    // unit = (8-row group g, 4 consecutive columns): lanes run over the row groups first, so
-    // with the skewed chunk pitch a quarter-warp's 16-byte stores spread over the bank groups
+    // unit = (8-row group g, W consecutive columns), W = 2 for operands up to 128 columns and 4
+    // above: every thread converts at most ONE unit of x and ONE of dy per stage, the x units
+    // on the first threads, the dy units on the threads after them (small shapes keep eight
+    // warps busy with one short pass each).  Lanes run over the row groups first, so with the
+    // skewed chunk pitch a quarter-warp's 16-byte stores spread over the bank groups.
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};   // this thread's columns of dy (loop invariant)
     const bool vec_k = (k % 4 == 0);
-    const int kq = k >> 2, nq = n >> 2;
-    const int tb = (t + WT_CONV / 2) & (WT_CONV - 1);
+    const int wa = k <= 64 ? 1 : k <= 128 ? 2 : 4, wb = n <= 64 ? 1 : n <= 128 ? 2 : 4;
+    const int ua = vec_k ? G * (k / wa) : 0, ub = G * (n / wb);        // units per stage, <= 256
+    const int toff = ua + ub <= WT_CONV ? ua : WT_CONV - ub;
+    const int ubi = (t - toff) & (WT_CONV - 1);                         // this thread's dy unit
     int s = 0;
     uint32_t nuse = 0;
 #pragma unroll 1
@@ -399,28 +463,14 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
       unsigned char* sb_ = st + 2 * a_half;
       // ---- A' = x^T -----------------------------------------------------------------------
       if (vec_k) {
-        for (int u = t; u < G * kq; u += WT_CONV) {
-          const int g = u & (G - 1), kk = (u >> gshift) * 4;
-          float4 v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int r = g * 8 + e;
-            v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r0 + r < rows)
-              v[e] = from_smem ? *reinterpret_cast<const float4*>(xs + r * k + kk)
-                               : ldg4(x + (size_t)(r0 + r) * ldx + kk);
-          }
-          const float* f = reinterpret_cast<const float*>(v);
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            uint4 h, l;
-            umma::split_bf16x2(f[0 * 4 + cc], f[1 * 4 + cc], h.x, l.x);
-            umma::split_bf16x2(f[2 * 4 + cc], f[3 * 4 + cc], h.y, l.y);
-            umma::split_bf16x2(f[4 * 4 + cc], f[5 * 4 + cc], h.z, l.z);
-            umma::split_bf16x2(f[6 * 4 + cc], f[7 * 4 + cc], h.w, l.w);
-            *reinterpret_cast<uint4*>(st + g * lbo_a + (kk + cc) * 16) = h;
-            *reinterpret_cast<uint4*>(st + a_half + g * lbo_a + (kk + cc) * 16) = l;
-          }
+        if (t < ua) {
+          const int g = t & (G - 1), kk = (t >> gshift) * wa;
+          const float* src = from_smem ? xs : x + (size_t)r0 * ldx;
+          const size_t pitch = from_smem ? (size_t)k : (size_t)ldx;
+          unsigned char* dst = st + g * lbo_a + kk * 16;
+          if (wa == 1) wt_convert_unit<1>(src, nullptr, pitch, kk, g * 8, rows - r0 - g * 8, dst, a_half, nullptr);
+          else if (wa == 2) wt_convert_unit<2>(src, nullptr, pitch, kk, g * 8, rows - r0 - g * 8, dst, a_half, nullptr);
+          else wt_convert_unit<4>(src, nullptr, pitch, kk, g * 8, rows - r0 - g * 8, dst, a_half, nullptr);
         }
       } else {
         for (int u = t; u < G * k; u += WT_CONV) {      // k = 9 raw pair features
@@ -442,42 +492,15 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
         }
       }
       // ---- B' = (dy . relu')^T ----------------------------------------------------------------
-      // (the dy units start at the other half of the converter threads, so that small shapes
-      // - 64 units per operand - keep four warps busy instead of two)
-      for (int u = tb; u < G * nq; u += WT_CONV) {
-        const int g = u & (G - 1), nn = (u >> gshift) * 4;
-        float4 v[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int r = g * 8 + e;
-          v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r0 + r < rows) {
-            float4 m = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (from_smem) {
-              v[e] = *reinterpret_cast<const float4*>(ds + r * n + nn);
-              if (mask != nullptr) m = *reinterpret_cast<const float4*>(ms + r * n + nn);
-            } else {
-              v[e] = ldg4(dy + (size_t)(r0 + r) * ldy + nn);
-              if (mask != nullptr) m = ldg4(mask + (size_t)(r0 + r) * ldy + nn);
-            }
-            v[e].x = m.x > 0.f ? v[e].x : 0.f;
-            v[e].y = m.y > 0.f ? v[e].y : 0.f;
-            v[e].z = m.z > 0.f ? v[e].z : 0.f;
-            v[e].w = m.w > 0.f ? v[e].w : 0.f;
-          }
-          bsum[0] += v[e].x; bsum[1] += v[e].y; bsum[2] += v[e].z; bsum[3] += v[e].w;
-        }
-        const float* f = reinterpret_cast<const float*>(v);
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          uint4 h, l;
-          umma::split_bf16x2(f[0 * 4 + cc], f[1 * 4 + cc], h.x, l.x);
-          umma::split_bf16x2(f[2 * 4 + cc], f[3 * 4 + cc], h.y, l.y);
-          umma::split_bf16x2(f[4 * 4 + cc], f[5 * 4 + cc], h.z, l.z);
-          umma::split_bf16x2(f[6 * 4 + cc], f[7 * 4 + cc], h.w, l.w);
-          *reinterpret_cast<uint4*>(sb_ + g * lbo_b + (nn + cc) * 16) = h;
-          *reinterpret_cast<uint4*>(sb_ + b_half + g * lbo_b + (nn + cc) * 16) = l;
-        }
+      if (ubi < ub) {
+        const int g = ubi & (G - 1), nn = (ubi >> gshift) * wb;
+        const float* src = from_smem ? ds : dy + (size_t)r0 * ldy;
+        const float* msk = mask == nullptr ? nullptr : (from_smem ? ms : mask + (size_t)r0 * ldy);
+        const size_t pitch = from_smem ? (size_t)n : (size_t)ldy;
+        unsigned char* dst = sb_ + g * lbo_b + nn * 16;
+        if (wb == 1) wt_convert_unit<1>(src, msk, pitch, nn, g * 8, rows - r0 - g * 8, dst, b_half, bsum);
+        else if (wb == 2) wt_convert_unit<2>(src, msk, pitch, nn, g * 8, rows - r0 - g * 8, dst, b_half, bsum);
+        else wt_convert_unit<4>(src, msk, pitch, nn, g * 8, rows - r0 - g * 8, dst, b_half, bsum);
       }
       umma::fence_smem_to_async();
       if (bulk) umma::mbar_arrive(&raw_empty[s]);     // this thread's reads of the raw stage are done
@@ -485,12 +508,9 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
       if (lane == 0) umma::mbar_arrive(&op_full[o]);
       if (++s == raw_stages) { s = 0; ++nuse; }
     }
-    if (db != nullptr) {
-      // this thread's column quad: (u >> gshift) % (n / 4) with u = t + 256 i; n / 4 divides
-      // 256 >> gshift, so it does not depend on i
-      const int nn = ((tb >> gshift) % nq) * 4;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
+    if (db != nullptr && ubi < ub) {
+      const int nn = (ubi >> gshift) * wb;
+      for (int c = 0; c < wb; ++c)
         if (bsum[c] != 0.f) atomicAdd(db + nn + c, bsum[c]);
     }
     // ---- epilogue: accumulator rows (= weight rows) into dW ------------------------------
@@ -498,7 +518,7 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
     umma::tc_fence_after();
     const int quad = warp & 3, half = warp >> 2;
     const uint32_t tlane = (uint32_t)(quad * 32) << 16;
-    for (int mt = 0; mt < mt_count; ++mt) {
+    for (int mt = 0; mt < mt_count && warp < 8; ++mt) {      // warps 0-7: two per lane quadrant
       const int kk = mt * 128 + quad * 32 + lane;
       for (int c0 = half * 32; c0 < n; c0 += 64) {       // the two warps of a quadrant alternate
         float v[32];
