@@ -100,12 +100,43 @@ class GnetEngine(object):
         # bumped whenever a workspace buffer is reallocated: captured CUDA graphs hold raw
         # pointers into the workspace and must be dropped when this changes (session.py)
         self.ws_generation = 0
+        # Everything derived from the weights alone (operand images, the folded predict head)
+        # is rebuilt only when the weights changed: `flat._version` counts torch-side in-place
+        # writes (load_state_dict, Variable.value.copy_), `weights_version` is bumped by callers
+        # that write through the C ABI (the optimizer step).  A captured CUDA graph does not
+        # contain these launches; InferenceSession refreshes them before a replay when the key
+        # moved (refresh_weight_images).
+        self.weights_version = 0
+        self._derived_key = {}
         # the predict head's hidden layers are linear (network.py:263): apply it as one folded
         # affine map instead of three FC launches (False: the staged FCs)
         self.collapse_predict = True
         # neighbor build through per-row hit masks (division-free threshold test in the count
         # pass, exact IoU only for the hits in the fill pass); False: both passes recompute
         self.use_neighbor_masks = True
+
+    # ------------------------------------------------------- weight-derived buffers
+    def weights_key(self):
+        return (self.flat._version, self.weights_version, self.pair_mode, self.bf16)
+
+    def _stale(self, what):
+        """True (and marks `what` fresh) when the weights changed since `what` was last built."""
+        key = self.weights_key()
+        if self._derived_key.get(what) == key:
+            return False
+        self._derived_key[what] = key
+        return True
+
+    def refresh_weight_images(self):
+        """Rebuild every weight-derived buffer of the fused forward now (on the current stream)
+        if the weights moved; returns True when anything was launched.  For callers that
+        replay a captured forward."""
+        done = False
+        if self.fused_det and self.use_fused and self.use_tensor_cores and self.g['num_blocks'] > 0:
+            done |= self._prepare_block_images()
+        if self.use_fused and self.collapse_predict:
+            done |= self._prepare_predict()
+        return done
 
     # ------------------------------------------------------------------ workspace
     def _buf(self, name, shape, dtype=torch.float32):
@@ -304,6 +335,7 @@ class GnetEngine(object):
         image = torch.zeros(off, dtype=torch.uint8, device=self.device)
         self._ws[key] = (image, table, (pair_off, det_off, pair_b, det_b))
         self.ws_generation += 1
+        self._derived_key.pop('block_images', None)      # a fresh buffer: rebuild
         return self._ws[key]
 
     def _tma_images(self):
@@ -319,7 +351,20 @@ class GnetEngine(object):
                                 device=self.device)
             self._ws['wimg_tma'] = (image, table)
             self.ws_generation += 1
+            self._derived_key.pop('block_images', None)
         return self._ws['wimg_tma']
+
+    def _prepare_block_images(self):
+        """Operand images of all blocks from the flat parameter buffer (two launches), skipped
+        while the weights have not changed."""
+        if not self._stale('block_images'):
+            return False
+        image, table, _ = self._operand_images()
+        ops.prepare_operands(self.flat, table, image)
+        if self._tma_path():
+            tma_image, tma_table = self._tma_images()
+            ops.prepare_pair_tma_image(self.flat, tma_table, tma_image)
+        return True
 
     def _blocks_fused(self, feats, pair_c, pair_n, num_pairs, cap, pw, block_feats):
         """All blocks with two launches each: the tensor-core pair stage and the fused
@@ -346,12 +391,11 @@ class GnetEngine(object):
             red_all[T].zero_()
             inter_hl = red_all[:T]
             tma_image, tma_table = self._tma_images()
-            ops.prepare_pair_tma_image(self.flat, tma_table, tma_image)
             tma_b = ops.pair_tma_image_bytes()
         elif not ab_mode:
             inter = self._buf('red_hl', (T, 2 * g['reduced_dim']), torch.bfloat16)
         image, table, (pair_off, det_off, pair_b, det_b) = self._operand_images()
-        ops.prepare_operands(self.flat, table, image)
+        self._prepare_block_images()
         nb = g['num_blocks']
 
         def det(b, pooled_in, feats_in, out):
@@ -416,9 +460,9 @@ class GnetEngine(object):
                        out=self._buf('logits', (T, 1)))
         return out.view(-1)
 
-    def _predict_collapsed(self, feats):
-        """The head's hidden layers are linear, so it is ONE affine map: fold the chain
-        (every forward: parameters move during training), then one dot product per row."""
+    def _prepare_predict(self):
+        """The head's hidden layers are linear, so it is ONE affine map: fold the chain into
+        w_eff / b_eff (one small launch), skipped while the weights have not changed."""
         g = self.g
         if 'pred_table' not in self._ws:
             names = ['gnet/predict/fc%d/fully_connected' % i for i in range(1, g['num_predict_fc'])]
@@ -429,12 +473,21 @@ class GnetEngine(object):
                 rows.append([w.offset, b.offset, w.shape[0], w.shape[1]])
             self._ws['pred_table'] = torch.tensor(rows, dtype=torch.int32, device=self.device)
             self._ws['pred_maxdim'] = max(max(r[2], r[3]) for r in rows)
+            self._ws['pred_weff'] = torch.empty(g['shortcut_dim'], dtype=torch.float32, device=self.device)
+            self._ws['pred_beff'] = torch.empty(1, dtype=torch.float32, device=self.device)
+            self._derived_key.pop('predict', None)
+        if not self._stale('predict'):
+            return False
         table, md = self._ws['pred_table'], self._ws['pred_maxdim']
-        d = feats.shape[1]
-        w_eff = self._buf('pred_weff', (d,))
-        b_eff = self._buf('pred_beff', (1,))
-        ops.predict_collapse(self.flat, table, md, self._buf('pred_scratch', (2 * md,)), w_eff, b_eff)
-        return ops.rowdot_fwd(feats, w_eff, b_eff, self._buf('logits', (feats.shape[0],)))
+        ops.predict_collapse(self.flat, table, md, self._buf('pred_scratch', (2 * md,)),
+                             self._ws['pred_weff'], self._ws['pred_beff'])
+        return True
+
+    def _predict_collapsed(self, feats):
+        """One dot product per row with the folded head (network.py:257-273)."""
+        self._prepare_predict()
+        return ops.rowdot_fwd(feats, self._ws['pred_weff'], self._ws['pred_beff'],
+                              self._buf('logits', (feats.shape[0],)))
 
     def _empty_result(self):
         """A batch without a single detection (every image empty): nothing to launch."""

@@ -113,6 +113,7 @@ class InferenceSession(object):
         forward alone (bench's resident measurement) and the whole host-buffer step."""
         for _ in range(2):
             self._warm(buf)
+        self.engine.refresh_weight_images()     # fresh now: the captures below skip them
         n0 = _lib.CALLS[0]
         self._forward(buf)
         self.launches_per_forward = _lib.CALLS[0] - n0
@@ -181,6 +182,9 @@ class InferenceSession(object):
                         self._states.popitem(last=False)
                 if want_graph:
                     self._graph = state[1]
+                    # the captured forward does not contain the weight-derived launches
+                    # (operand images, folded predict head): redo them if the weights moved
+                    self.engine.refresh_weight_images()
                     state[2].replay()
                 else:
                     self._graph = False if not self.use_graph else None

@@ -287,6 +287,7 @@ class Trainer(object):
         n_images = float(self.gradbuf[-1].item())
         scale = 1.0 / max(n_images, 1.0)
         self.global_step += 1
+        self.eng.weights_version += 1        # the optimizer kernel writes the flat buffer in place
         if self.optimizer == 'adam':
             ops.adam_step(self.eng.flat, self.grad, self.state1, self.state2, self.decay, lr,
                           self.beta1, self.beta2, self.eps, self.global_step, scale)

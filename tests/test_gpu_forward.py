@@ -202,3 +202,36 @@ def test_bf16_arithmetic_mode(n, blocks, exp, C, oracle_built):
     cfg.gnet.compute_dtype = 'fp32'
     net32 = Gnet(C, params=flat)
     assert rel_err(net32(test_img).cpu().numpy(), ref['prediction']) < LOGIT_TOL
+
+
+def test_weight_derived_buffers_follow_weight_changes():
+    """Operand images and the folded predict head are cached across forwards; an in-place
+    change of the weights (TF-style variable assignment, a checkpoint load, an optimizer step)
+    must rebuild them - in eager forwards and before the replay of a captured graph."""
+    from gossipnet_b200.session import InferenceSession
+    from gossipnet_b200.trainer import Trainer
+    load_experiment('coco_person', num_blocks=3)
+    img = synthetic.make_image(300, 1, image_index=5)
+    test_batch = {k: img[k] for k in ('dets', 'det_scores', 'det_classes')}
+    net = Gnet(1)
+    p0 = net(test_batch).clone()
+    assert torch.equal(net(test_batch), p0)                      # cached path: same result
+    var = [v for v in net.trainable_variables if v.op_name == 'gnet/block2/pw_fc2/weights'][0]
+    var.value.mul_(1.5)                                          # in-place assignment
+    head = [v for v in net.trainable_variables if v.op_name == 'gnet/predict/logits/fully_connected/weights'][0]
+    head.value.mul_(0.5)
+    p1 = net(test_batch).clone()
+    fresh = Gnet(1, params=net.engine.flat.cpu().numpy())        # same weights, nothing cached
+    assert not torch.equal(p1, p0) and torch.equal(fresh(test_batch), p1)
+    # captured graph: two runs capture it, then the weights move
+    sess = InferenceSession(net)
+    off = np.array([0, 300], np.int32)
+    args = (img['dets'], img['det_scores'], img['det_classes'], off)
+    for _ in range(3):
+        g1 = sess.run(*args).copy()
+    assert sess._graph and np.array_equal(g1, p1.cpu().numpy())
+    tr = Trainer(net)
+    tr.step([img], 1e-2)                                         # optimizer writes through the C ABI
+    g2 = sess.run(*args).copy()
+    assert not np.array_equal(g2, g1)
+    assert np.array_equal(g2, Gnet(1, params=net.engine.flat.cpu().numpy())(test_batch).cpu().numpy())
