@@ -52,17 +52,29 @@ def test_run(test_imdb, images_per_call=64, model=None, allow_random_init=False)
     output_detections = []
     forward_timer = tools.Timer()
     num_dets = num_images = 0
-    for i in range(0, len(rois), images_per_call):
-        chunk = rois[i:i + images_per_call]
-        sizes = [r['dets'].shape[0] for r in chunk]
-        off = np.zeros(len(chunk) + 1, dtype=np.int32)
-        np.cumsum(sizes, out=off[1:])
-        dets = np.concatenate([r['dets'] for r in chunk]).astype(np.float32)
-        scores = np.concatenate([r['det_scores'] for r in chunk]).astype(np.float32)
-        classes = np.concatenate([r['det_classes'] for r in chunk]).astype(np.int32)
-        forward_timer.tic()
-        new_scores = sess.run(dets, scores, classes, off).copy()
-        forward_timer.toc()
+    def chunks():
+        for i in range(0, len(rois), images_per_call):
+            chunk = rois[i:i + images_per_call]
+            sizes = [r['dets'].shape[0] for r in chunk]
+            off = np.zeros(len(chunk) + 1, dtype=np.int32)
+            np.cumsum(sizes, out=off[1:])
+            yield chunk, off, (np.concatenate([r['dets'] for r in chunk]).astype(np.float32),
+                               np.concatenate([r['det_scores'] for r in chunk]).astype(np.float32),
+                               np.concatenate([r['det_classes'] for r in chunk]).astype(np.int32), off)
+
+    # the session runs one chunk ahead: while the GPU rescored chunk i the host has already
+    # staged chunk i+1 (InferenceSession.run_pipelined); results come back in order
+    meta = []
+
+    def inputs():
+        for chunk, off, args in chunks():
+            meta.append((chunk, off))
+            yield args
+
+    forward_timer.tic()
+    for k_chunk, new_scores in enumerate(sess.run_pipelined(inputs())):
+        chunk, off = meta[k_chunk]
+        new_scores = new_scores.copy()
         for k, roi in enumerate(chunk):
             output_detections.append({
                 'id': roi['id'],
@@ -72,6 +84,7 @@ def test_run(test_imdb, images_per_call=64, model=None, allow_random_init=False)
             })
         num_dets += int(off[-1])
         num_images += len(chunk)
+    forward_timer.toc()
     if num_images:
         print('{:.6f}s per image with {:.1f} detections per image'.format(
             forward_timer.total_time / num_images, num_dets / num_images))

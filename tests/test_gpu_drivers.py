@@ -147,3 +147,36 @@ def test_session_graphs_repeated_shapes_and_runs_new_shapes_eagerly():
     assert len(sess._states) == 2
     assert sess.run(np.zeros((0, 4), np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32),
                     np.zeros(1, np.int32)).shape == (0,)
+
+
+def test_pipelined_session_equals_blocking_calls():
+    """InferenceSession.run_pipelined (one batch ahead, two staging slots) returns, in order,
+    exactly what the blocking run() returns - for repeated shapes (captured graphs), a shape
+    change in the middle, an empty batch, and a batch denser than the workspace."""
+    from gossipnet_b200 import synthetic
+    from gossipnet_b200.session import InferenceSession
+    small_cfg()
+    net = Gnet(1)
+
+    def batch(sizes, first):
+        imgs = [synthetic.make_image(n, 1, image_index=first + i) for i, n in enumerate(sizes)]
+        off = np.zeros(len(sizes) + 1, np.int32)
+        np.cumsum(sizes, out=off[1:])
+        return (np.concatenate([i['dets'] for i in imgs]), np.concatenate([i['det_scores'] for i in imgs]),
+                np.concatenate([i['det_classes'] for i in imgs]), off)
+
+    seq = [batch([120, 80], 0), batch([120, 80], 2), batch([120, 80], 4), batch([50], 6),
+           batch([120, 80], 7), (np.zeros((0, 4), np.float32), np.zeros(0, np.float32),
+                                 np.zeros(0, np.int32), np.zeros(1, np.int32)),
+           batch([120, 80], 9), batch([900, 900], 11), batch([120, 80], 13)]
+    ref_sess = InferenceSession(net, use_graph=False)
+    want = [ref_sess.run(*b).copy() for b in seq]
+    # a second engine with the same weights: its workspace has to grow on the dense batch
+    sess = InferenceSession(Gnet(1, params=net.engine.flat.cpu().numpy()), graph_after=1)
+    got = [o.copy() for o in sess.run_pipelined(seq)]
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    got2 = [o.copy() for o in sess.run_pipelined(seq)]       # second pass: everything captured
+    for a, b in zip(got2, want):
+        assert np.array_equal(a, b)
