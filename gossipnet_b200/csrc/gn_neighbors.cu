@@ -257,7 +257,7 @@ neighbor_fill_mask_kernel(const float* __restrict__ dets, const int32_t* __restr
 // n is at most a few hundred thousand detections, the scan is latency-bound and
 // a single pass over L2-resident data; one CTA of 1024 threads x 4 items.
 constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_ITEMS = 16;   // per thread and round: 64 k degrees = 4 rounds of one 1024-thread CTA
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 exclusive_scan_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out) {
@@ -270,11 +270,18 @@ exclusive_scan_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict
     const int i0 = base + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
     int tsum = 0;
+    if (i0 + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-      v[j] = (i0 + j < n) ? in[i0 + j] : 0;
-      tsum += v[j];
+      for (int j = 0; j < SCAN_ITEMS; j += 4) {      // i0 is a multiple of 16: aligned int4 loads
+        const int4 q = *reinterpret_cast<const int4*>(in + i0 + j);
+        v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = (i0 + j < n) ? in[i0 + j] : 0;
     }
+#pragma unroll
+    for (int j = 0; j < SCAN_ITEMS; ++j) tsum += v[j];
     int incl = tsum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
