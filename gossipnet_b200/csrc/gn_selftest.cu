@@ -406,7 +406,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256)
 store_bw_kernel(float* __restrict__ dst, size_t n16) {   // n16 = number of 16-byte units
   const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
-  if (MODE == 4) {
+  if constexpr (MODE == 4) {
     extern __shared__ __align__(128) unsigned char sm[];
     for (int i = threadIdx.x; i < 16384 / 16; i += blockDim.x) reinterpret_cast<float4*>(sm)[i] = v;
     umma::fence_smem_to_async();
@@ -424,9 +424,7 @@ store_bw_kernel(float* __restrict__ dst, size_t n16) {   // n16 = number of 16-b
       }
       umma::bulk_wait_group0();
     }
-    return;
-  }
-  if (MODE == 2 || MODE == 5) {
+  } else if constexpr (MODE == 2 || MODE == 5) {
     uint64_t pol = 0;
     if (MODE == 5) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     const size_t n32 = n16 / 2;
@@ -440,14 +438,14 @@ store_bw_kernel(float* __restrict__ dst, size_t n16) {   // n16 = number of 16-b
         asm volatile("st.global.L2::cache_hint.v8.f32 [%0], {%1, %2, %3, %4, %1, %2, %3, %4}, %5;"
                      ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
     }
-    return;
-  }
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
-       i += (size_t)gridDim.x * blockDim.x) {
-    float4* p = reinterpret_cast<float4*>(dst) + i;
-    if (MODE == 0) *p = v;
-    else if (MODE == 1) __stcs(p, v);
-    else __stwt(p, v);
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (size_t)gridDim.x * blockDim.x) {
+      float4* p = reinterpret_cast<float4*>(dst) + i;
+      if (MODE == 0) *p = v;
+      else if (MODE == 1) __stcs(p, v);
+      else __stwt(p, v);
+    }
   }
 }
 }  // namespace gn
