@@ -88,33 +88,31 @@ def make_inputs(n_images, n_dets, first_index):
 
 
 # ------------------------------------------------------------------ CPU baseline
-def blas_threads():
-    """Threads the BLAS behind numpy uses (the FCs of the CPU restatement run there)."""
-    try:
-        from threadpoolctl import threadpool_info
-        n = [int(i.get('num_threads', 0)) for i in threadpool_info() if i.get('user_api') == 'blas']
-        return max(n) if n else None
-    except Exception:
-        return None
+def cpu_threads():
+    """Threads of the PyTorch-CPU restatement: every host core."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    return torch.get_num_threads()
 
 
 def cpu_forward_rate(cfg, n_dets, seconds, max_images=64, first_index=0, warm=True):
-    """Reference formulation on the host cores, one image per call like
-    test.py:63-71 (numpy float32 restatement, BLAS threads = all cores).  `warm`: one
-    untimed forward first (callers that time several calls warm up once themselves)."""
+    """Reference formulation on the host cores, one image per call like test.py:63-71:
+    the PyTorch-CPU float32 restatement (oracle/gnet_oracle_torch.py; about 3x the numpy
+    one, which spends its time in fancy indexing and reduceat), intra-op threads = all
+    cores.  `warm`: one untimed forward first (callers that time several calls warm up
+    once themselves)."""
     from gossipnet_b200 import params as P
     from gossipnet_b200 import synthetic
-    from oracle import gnet_oracle
+    from oracle import gnet_oracle_torch
+    cpu_threads()
     layout, total = P.param_layout(1, cfg)
-    pv = P.views(layout, P.init_flat(layout, total, cfg, seed=1))
-    keys = ('dets', 'det_scores', 'det_classes')
+    net = gnet_oracle_torch.TorchGnet(P.views(layout, P.init_flat(layout, total, cfg, seed=1)),
+                                      cfg, 1)
     if warm:
-        img = synthetic.make_image(n_dets, 1, image_index=first_index)
-        gnet_oracle.gnet_forward({k: img[k] for k in keys}, pv, cfg, 1, keep_intermediates=False)
+        net.forward(synthetic.make_image(n_dets, 1, image_index=first_index))
     done, t0 = 0, time.perf_counter()
     while done < max_images:
-        img = synthetic.make_image(n_dets, 1, image_index=first_index + done)
-        gnet_oracle.gnet_forward({k: img[k] for k in keys}, pv, cfg, 1, keep_intermediates=False)
+        net.forward(synthetic.make_image(n_dets, 1, image_index=first_index + done))
         done += 1
         if time.perf_counter() - t0 > seconds:
             break
@@ -128,7 +126,7 @@ def run_reference(args):
         return
     cfg = setup_cfg(args.blocks)
     cores = os.cpu_count()
-    per_step = 2  # images per step: a bounded sample of the workload
+    per_step = 4  # images per step: a bounded sample of the workload
     for _ in range(args.warmup):
         cpu_forward_rate(cfg, args.n_dets, 1e9, max_images=1)
     t0 = time.perf_counter()
@@ -138,8 +136,8 @@ def run_reference(args):
                          warm=False)
     dt = time.perf_counter() - t0
     value = args.steps * per_step * args.n_dets / dt
-    sample = ('%d images x N=%d per step, one image per call, %s BLAS threads'
-              % (per_step, args.n_dets, blas_threads()))
+    sample = ('%d images x N=%d per step, one image per call, %d torch intra-op threads'
+              % (per_step, args.n_dets, cpu_threads()))
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
@@ -148,8 +146,8 @@ def run_reference(args):
         'config': {'workload': workload_name(args.n_dets, args.blocks),
                    'images_per_step': per_step},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': sample + '; numpy float32 restatement of the reference '
-                         '(oracle/gnet_oracle.py; TensorFlow 0.12 is not installable here)'},
+                         'sample': sample + '; PyTorch-CPU float32 restatement of the reference '
+                         '(oracle/gnet_oracle_torch.py; TensorFlow 0.12 is not installable here)'},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }))
 
@@ -643,9 +641,9 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, n_img, dt = cpu_forward_rate(cfg, N, args.cpu_seconds)
         cpu = {'value': rate, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-               'sample': '%d images x N=%d, one image per call, %.1f s, %s BLAS threads; numpy '
-                         'float32 restatement of the reference (oracle/gnet_oracle.py)'
-                         % (n_img, N, dt, blas_threads())}
+               'sample': '%d images x N=%d, one image per call, %.1f s, %d torch intra-op threads; '
+                         'PyTorch-CPU float32 restatement of the reference '
+                         '(oracle/gnet_oracle_torch.py)' % (n_img, N, dt, cpu_threads())}
     # ---- BASELINE configs[2] (extra key; single GPU, default run) -------------------
     if rank == 0 and world == 1 and not args.quick and not bf16:
         extra2 = run_config2(torch, ops, stream, flush, peaks, peak_src, max(5, args.steps // 2),
