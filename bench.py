@@ -359,13 +359,24 @@ def kernel_rooflines(torch, ops, eng, sess, stream, flush, P, T, blocks, bf16, p
             args_ = (pooled, feats, image[det_off[1]:det_off[1] + det_b], p['gnet/block1/fc1/biases'],
                      p['gnet/block1/fc2/biases'], p['gnet/block2/reduce_dim/biases'])
             if u is not None:
-                ops.block_det_fwd_img_u(*args_, outb, inter, p['gnet/block2/pw_fc1/biases'], u,
-                                        bf16=bf16)
+                fn = ops.block_det_fwd_tma if eng.det_tma else ops.block_det_fwd_img_u
+                fn(*args_, outb, inter, p['gnet/block2/pw_fc1/biases'], u, bf16=bf16)
             else:
                 ops.block_det_fwd_img(*args_, feats_out=outb, red_hl=inter, bf16=bf16)
         ms = med(_events(torch, stream, det, 10, before=pre))
-        out['roofline_det'] = entry('block_det_tc_kernel', ms, 32768.0 * T, blocks + 1,
-                                    'det_dram_bytes_per_launch')
+        e = entry('block_det_tma_kernel' if (u is not None and eng.det_tma)
+                  else 'block_det_tc_kernel', ms, 32768.0 * T, blocks + 1,
+                  'det_dram_bytes_per_launch')
+        # this kernel moves 1920 B per detection for 32 768 flop (reads: pooled 256 + shortcut
+        # 512; writes: block output 512 + U 256 + red 128 + re-zeroed pooled 256): it sits on
+        # the memory side of the roofline, so it is quoted against the copy bandwidth
+        hbm = float(peaks.get('hbm_gbs', 6650.0))
+        gbs = 1920.0 * T / (ms * 1e-3) / 1e9
+        e.update({'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm,
+                  'algorithmic_bytes_per_launch': 1920.0 * T, 'tensor_tflops': e['achieved'],
+                  'peak_source': '%s copy bandwidth (read+write); L2 flushed before the launch'
+                                 % peak_src})
+        out['roofline_det'] = e
     return out
 
 

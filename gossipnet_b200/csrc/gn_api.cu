@@ -50,19 +50,32 @@ tmap_encode_fn tmap_encoder() {
   return fn;
 }
 
-int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
-                        uint64_t pitch_bytes, uint32_t box_rows, uint32_t box_cols) {
+static int encode_tmap_2d(CUtensorMap* map, CUtensorMapDataType dtype, const void* base,
+                          uint64_t rows, uint64_t cols, uint64_t pitch_bytes, uint32_t box_rows,
+                          uint32_t box_cols) {
   const tmap_encode_fn enc = tmap_encoder();
   if (enc == nullptr) return -1;
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {pitch_bytes};
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+  const CUresult r = enc(map, dtype, 2, const_cast<void*>(base), dims,
                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;
+}
+
+int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                        uint64_t pitch_bytes, uint32_t box_rows, uint32_t box_cols) {
+  return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rows, cols, pitch_bytes,
+                        box_rows, box_cols);
+}
+
+int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                       uint64_t pitch_bytes, uint32_t box_rows, uint32_t box_cols) {
+  return encode_tmap_2d(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rows, cols, pitch_bytes,
+                        box_rows, box_cols);
 }
 
 }  // namespace gn

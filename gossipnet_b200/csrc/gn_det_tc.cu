@@ -125,6 +125,13 @@ __device__ __forceinline__ void dt_gemm(uint32_t tmem_d, uint64_t d_ah, uint64_t
   }
 }
 
+#ifdef DT_TRACE
+__device__ long long dt_trace[32];
+#define DT_TR(i) do { if (blockIdx.x == 0 && t == 0 && tile == (int)(2 * gridDim.x)) dt_trace[i] = clock64(); } while (0)
+#else
+#define DT_TR(i) do { } while (0)
+#endif
+
 template <bool X3>
 __global__ void __launch_bounds__(DT_THREADS, 1)
 block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_in,
@@ -208,14 +215,17 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
     const int row0 = tile * DT_TILE;
     const int grow = row0 + erow;
     const bool live = grow < num_dets;
+    DT_TR(0);
 
     if (stage_a) {
       // ---- pooled tile -> A (K = 64); pooled <- 0 for the next block ----------------
       dt_load_tile<DT_F>(pooled, row0, num_dets, a_hi, a_lo, warp, lane, pooled);
+      DT_TR(1);
       if (weights_pending) { umma::mbar_wait(wbar, 0); weights_pending = false; }
       umma::fence_smem_to_async();
       umma::tc_fence_before();
       __syncthreads();
+      DT_TR(2);
       if (t == 0) {
         umma::tc_fence_after();
         dt_gemm<DT_F / 16, X3>(tm1, d_ah, d_al, d_w1h, d_w1l, DT_F * 16, umma::idesc_bf16_f32(DT_TILE, DT_F));
@@ -224,6 +234,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       umma::mbar_wait(bar, par);
       par ^= 1;
       umma::tc_fence_after();
+      DT_TR(3);
       // ---- d1 = relu(acc + b_fc1) -> A (K = 64) ---------------------------------------
 #pragma unroll
       for (int cc = 0; cc < 32; cc += 16) {
@@ -246,9 +257,11 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
           *reinterpret_cast<uint4*>(a_lo + off) = l;
         }
       }
+      DT_TR(4);
       umma::fence_smem_to_async();
       umma::tc_fence_before();
       __syncthreads();
+      DT_TR(5);
       if (t == 0) {
         umma::tc_fence_after();
         dt_gemm<DT_F / 16, X3>(tm2, d_ah, d_al, d_w2h, d_w2l, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, DT_D));
@@ -269,11 +282,14 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
         for (int g = 0; g < 16; ++g)
           *reinterpret_cast<float4*>(stage + (g * 8 + warp) * DT_STAGE_PITCH + lane * 16) = rowv[g];
       }
+      DT_TR(6);
       __syncthreads();
+      DT_TR(7);
       float* srow = reinterpret_cast<float*>(stage + erow * DT_STAGE_PITCH) + ehalf * 64;
       umma::mbar_wait(bar, par);
       par ^= 1;
       umma::tc_fence_after();
+      DT_TR(8);
       // ---- feats_out = relu(feats_in + acc + b_fc2) -> staging (in place), and -> A (K = 128)
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {
@@ -331,18 +347,22 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       store_feats_tile();
     }
     if (stage_b) {
+      DT_TR(9);
       umma::fence_smem_to_async();
       umma::tc_fence_before();
       __syncthreads();
+      DT_TR(10);
       if (t == 0) {
         umma::tc_fence_after();
         dt_gemm<DT_D / 16, X3>(tmr, d_ah, d_al, d_wrh, d_wrl, DT_R * 16, umma::idesc_bf16_f32(DT_TILE, DT_R));
         umma::mma_commit(bar);
       }
       if (stage_a) store_feats_tile();      // while the reduce_dim UMMAs run
+      DT_TR(11);
       umma::mbar_wait(bar, par);
       par ^= 1;
       umma::tc_fence_after();
+      DT_TR(12);
       // ---- red = relu(acc + b_rd): 16 columns per thread --------------------------------
       {
         const int col0 = ehalf * 16;
@@ -392,9 +412,11 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
       if (stage_ab) {
         // AB[d, 0:64] = red @ W1[32:64] + b1 ; AB[d, 64:128] = red @ W1[64:96]   (gn_block_ab.cu)
         // ab_cols = 64: only the first half (gn_block_tma.cu gathers the neighbor rows itself)
+        DT_TR(13);
         umma::fence_smem_to_async();
         umma::tc_fence_before();
         __syncthreads();
+        DT_TR(14);
         if (t == 0) {
           umma::tc_fence_after();
           dt_gemm<DT_R / 16, X3>(tm2, d_ah, d_al, d_wabh, d_wabl, DT_D * 16, umma::idesc_bf16_f32(DT_TILE, ab_cols));
@@ -403,6 +425,7 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
         umma::mbar_wait(bar, par);
         par ^= 1;
         umma::tc_fence_after();
+        DT_TR(15);
         const int per = ab_cols >> 1;          // columns per warp half: 64 or 32
         for (int cc = 0; cc < per; cc += 32) {
           const int col0 = ehalf * per + cc;
@@ -423,8 +446,10 @@ block_det_tc_kernel(float* __restrict__ pooled, const float* __restrict__ feats_
         }
       }
     }
+    DT_TR(16);
     umma::tc_fence_before();
     __syncthreads();   // A region and TMEM columns are reused by the next tile
+    DT_TR(17);
   }
 
   umma::tc_fence_before();
@@ -538,6 +563,12 @@ extern "C" int gn_block_det_fwd_img_u(float* pooled, const float* feats_in, cons
                           nullptr, red_hl, b_u, u_out, 64, num_dets, shortcut_dim, pairfeat_dim,
                           reduced_dim, stream);
 }
+
+#ifdef DT_TRACE
+extern "C" int gn_block_det_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, gn::dt_trace, sizeof(long long) * 32) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int64_t gn_block_det_image_bytes(void) { return (int64_t)gn::DT_OFF_A; }
 

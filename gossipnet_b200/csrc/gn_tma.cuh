@@ -23,5 +23,8 @@ tmap_encode_fn tmap_encoder();
 // Returns 0 on success, the CUresult otherwise (-1: no encoder).
 int encode_tmap_2d_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                         uint64_t pitch_bytes, uint32_t box_rows, uint32_t box_cols);
+// the same for a float32 matrix (box_cols * 4 <= 128 bytes)
+int encode_tmap_2d_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                       uint64_t pitch_bytes, uint32_t box_rows, uint32_t box_cols);
 
 }  // namespace gn

@@ -121,6 +121,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
       ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1),
         "r"(smem_u32(bar)), "l"(hint) : "memory");
 }
+// shared -> global 2D tile store (bulk async-group completion; rows / columns outside the
+// tensor are clipped).  The source box must have been made visible with fence_smem_to_async.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int32_t c0, int32_t c1,
+                                             uint32_t src_smem) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(src_smem) : "memory");
+}
 // gather4 (sm_100): four rows r0..r3 of a 2D tensor (box {box0, 1}) land as four consecutive
 // box0-wide rows at dst_smem, swizzled like a tile load
 __device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const void* tmap, int32_t c0,

@@ -94,6 +94,9 @@ class GnetEngine(object):
         # gather4 of the neighbor's reduced row), the detection-level third of pw_fc1 hoisted
         # into the det kernel (gn_block_tma.cu).
         self.pair_mode = 'tma'
+        # detection-level kernel of the 'tma' path: tile transfers on the copy engine
+        # (gn_det_tma.cu); False: the eight-warp kernel of gn_det_tc.cu (same results)
+        self.det_tma = True
         # fp32 pw_feats next to the bf16 (hi|lo) operand rows the 'tma' pair stage consumes
         # (the `pw_feats` attribute of the reference surface); False on the inference hot path
         self.want_pw_f32 = True
@@ -403,6 +406,14 @@ class GnetEngine(object):
             s = 'gnet/block%d/' % b
             nxt = 'gnet/block%d/' % (b + 1)
             last = b == nb
+            if tma_mode and b >= 1 and self.det_tma:
+                ops.block_det_fwd_tma(
+                    pooled_in, feats_in, image[det_off[b]:det_off[b] + det_b],
+                    p[s + 'fc1/biases'], p[s + 'fc2/biases'],
+                    None if last else p[nxt + 'reduce_dim/biases'], out,
+                    None if last else inter_hl, None if last else p[nxt + 'pw_fc1/biases'],
+                    None if last else inter, bf16=self.bf16)
+                return
             if tma_mode:
                 ops.block_det_fwd_img_u(
                     pooled_in, feats_in, image[det_off[b]:det_off[b] + det_b],

@@ -433,6 +433,17 @@ int gn_block_det_fwd_img_u(float* pooled, const float* feats_in, const void* wim
                            const float* b_u, float* u_out, int plain_bf16, int num_dets,
                            int shortcut_dim, int pairfeat_dim, int reduced_dim, gn_stream_t stream);
 
+/* gn_block_det_fwd_img_u with stage A always present, on the copy-engine kernel (gn_det_tma.cu):
+ * the shortcut tile comes in and the block output, u_out and red_hl leave by tensor-map TMA from a
+ * dedicated warp, the pooled rows of the next tile are prefetched, so the eight epilogue warps
+ * only run the four dependent GEMM epilogues (network.py:390-408, :348-354, :376-386).  Same
+ * results bit for bit.  has_stage_b = 0: only feats_out (after the last block). */
+int gn_block_det_fwd_tma(float* pooled, const float* feats_in, const void* wimg,
+                         const float* b_fc1, const float* b_fc2, const float* b_rd,
+                         int has_stage_b, float* feats_out, void* red_hl, const float* b_u,
+                         float* u_out, int plain_bf16, int num_dets, int shortcut_dim,
+                         int pairfeat_dim, int reduced_dim, gn_stream_t stream);
+
 /* Store-bandwidth micro-benchmark: writes `bytes` (multiple of 16384) bytes of constants with
  * mode 0 st.global.v4 | 1 st.global.cs.v4 | 2 st.global.v8 (256-bit) | 3 st.global.wt.v4 |
  * 4 cp.async.bulk shared->global (16 KB copies) | 5 st.global.v8 + L2 evict-first policy,

@@ -186,3 +186,39 @@ def test_fused_det_level_kernel(n):
     out3 = torch.empty((n, 128), device='cuda')
     ops.block_det_fwd(dev(pooled), dev(feats), dv(fc1), dv(fc2), None, feats_out=out3)
     assert rel_err(out3.cpu().numpy(), out) < 3e-5
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+@pytest.mark.parametrize('n', [1, 127, 129, 1000, 20011])
+def test_det_copy_engine_kernel_bit_identical(n, bf16):
+    """gn_block_det_fwd_tma (tile transfers by tensor-map TMA from a dedicated warp, pooled
+    rows prefetched; 20011 rows = more tiles than SMs, so the per-CTA tile pipeline runs)
+    against gn_block_det_fwd_img_u: feats_out, red_hl, u and the re-zeroed pooled buffer,
+    with and without stage B."""
+    from gossipnet_b200.nms_net.network import Gnet
+    load_experiment('coco_person', num_blocks=2)
+    eng = Gnet(1).engine
+    image, _, (_, det_off, _, det_b) = eng._operand_images()
+    eng._prepare_block_images()
+    p = eng.p
+    rs = np.random.RandomState(n)
+    pooled0 = dev(np.maximum(rs.normal(0, 1, (n, 64)), 0).astype(F32))
+    feats = dev(np.maximum(rs.normal(0, 1, (n, 128)), 0).astype(F32))
+    for b, last in ((1, False), (2, True)):
+        wimg = image[det_off[b]:det_off[b] + det_b]
+        s, nxt = 'gnet/block%d/' % b, 'gnet/block%d/' % (b + 1)
+        got = []
+        for fn in (ops.block_det_fwd_img_u, ops.block_det_fwd_tma):
+            pooled = pooled0.clone()
+            out = torch.full((n, 128), -1.0, device='cuda')
+            red = torch.full((n + 1, 64), -1.0, device='cuda').to(torch.bfloat16)
+            u = torch.full((n, 64), -1.0, device='cuda')
+            fn(pooled, feats, wimg, p[s + 'fc1/biases'], p[s + 'fc2/biases'],
+               None if last else p[nxt + 'reduce_dim/biases'], out, None if last else red[:n],
+               None if last else p[nxt + 'pw_fc1/biases'], None if last else u, bf16=bf16)
+            assert torch.all(pooled == 0)
+            got.append((out, red, u))
+        for a, c in zip(*got):
+            assert torch.equal(a, c)
+        assert float(got[1][0].abs().sum()) > 0
+        assert torch.all(got[1][1][n] == -1.0)        # the row behind the last detection is not touched
