@@ -16,7 +16,8 @@
 //              to the activations, so it is streamed per k-step (16 KB) from a pre-split
 //              operand image in global memory (L2 resident) through a cp.async.bulk ring
 //              (mbarrier complete_tx / tcgen05.commit);
-//   layer 3  : [128 x 256] x [256 x 32] -> the first 32 columns of the layer-2 accumulator,
+//   layer 3  : [128 x 256] x [256 x (32 hi | 32 lo)] -> the first 64 columns of the layer-2
+//              accumulator (hi and lo weight parts stacked along N, added by the epilogue),
 //              again quarter by quarter as the epilogue drains it.
 // Only pw_out[P,32] goes back to HBM (whole 128-byte rows through a padded staging tile);
 // the [P,256] activations never leave the SM.
@@ -33,7 +34,7 @@ constexpr int PT_H = 256, PT_O = 32;
 constexpr uint32_t PT_SBO = 128;
 constexpr uint32_t PT_LBO_A = PT_TILE * 16;      // activation / A1 chunk pitch (2048)
 constexpr uint32_t PT_LBO_W = PT_H * 16;         // 256-row weight chunk pitch (4096)
-constexpr uint32_t PT_LBO_W3 = PT_O * 16;        // 32-row weight chunk pitch (512)
+constexpr uint32_t PT_LBO_W3 = 2 * PT_O * 16;    // W3 chunk pitch (1024): 32 hi rows, then 32 lo rows
 constexpr uint32_t PT_STAGE = 2 * 2 * PT_LBO_W;  // one W2 k-step: (hi, lo) x 2 chunks = 16 KB
 
 // prepared weight image (global workspace), bytes
@@ -44,7 +45,7 @@ constexpr int PT_W2_COPIES = 1;
 constexpr uint32_t PT_IMG_W2 = 0;                            // COPIES x 16 k-steps x 16 KB
 constexpr uint32_t PT_IMG_B1 = PT_IMG_W2 + PT_W2_COPIES * 16 * PT_STAGE;   // hi 8 KB, lo 8 KB
 constexpr uint32_t PT_IMG_B3 = PT_IMG_B1 + 2 * 2 * PT_LBO_W; // hi 16 KB, lo 16 KB
-constexpr uint32_t PT_IMG_BYTES = PT_IMG_B3 + 2 * 32 * PT_LBO_W3;
+constexpr uint32_t PT_IMG_BYTES = PT_IMG_B3 + 32 * PT_LBO_W3;
 
 
 // ---------------------------------------------------------------------------------
@@ -84,11 +85,12 @@ __global__ void pwfeat_prepare_kernel(const float* __restrict__ w1, const float*
     unsigned char* st = img + PT_IMG_B1;
     put_split(st, st + 2 * PT_LBO_W, (k >> 3) * PT_LBO_W + n * 16, k & 7, x);
   }
-  // B3: W3^T, 32 chunks x 32 rows
+  // B3: W3^T, 32 chunks x (32 hi rows | 32 lo rows): the hi and lo parts stacked along N, so
+  // that one N = 64 UMMA forms a_hi * [b_hi | b_lo] (layer 3 below)
   for (int i = tid; i < PT_H * PT_O; i += nth) {
     const int k = i / PT_O, n = i - k * PT_O;
     unsigned char* st = img + PT_IMG_B3;
-    put_split(st, st + 32 * PT_LBO_W3, (k >> 3) * PT_LBO_W3 + n * 16, k & 7, __ldg(w3 + i));
+    put_split(st, st + PT_O * 16, (k >> 3) * PT_LBO_W3 + n * 16, k & 7, __ldg(w3 + i));
   }
 }
 
@@ -113,7 +115,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
 //   warps 18-21 geometry : one thread per pair, one tile ahead (A1 double-buffered)
 //
 // TMEM (512 columns): L1 accumulators 2 x 64 | activation operands H[2] (K = 64 each:
-// 32 columns bf16 hi + 32 lo) | layer-2 accumulator 256 (its first 32 columns are reused
+// 32 columns bf16 hi + 32 lo) | layer-2 accumulator 256 (its first 64 columns are reused
 // as the layer-3 accumulator once the first quarter has been drained).
 // Hand-offs are mbarriers: a1_full/a1_empty (geometry <-> MMA), l1_done (MMA -> epilogue),
 // h_full/h_empty (epilogue <-> MMA), acc2_done, acc3_done, tab_free (epilogue -> geometry).
@@ -131,7 +133,7 @@ constexpr uint32_t PP_OUT_PITCH = 144;                // output staging row pitc
 constexpr uint32_t PQ_RING = 0;
 constexpr uint32_t PQ_B1 = PQ_RING + PP_RING * PT_STAGE;
 constexpr uint32_t PQ_B3 = PQ_B1 + 2 * 2 * PT_LBO_W;
-constexpr uint32_t PQ_A1 = PQ_B3 + 2 * 32 * PT_LBO_W3;            // 2 buffers x (hi 4 KB + lo 4 KB)
+constexpr uint32_t PQ_A1 = PQ_B3 + 32 * PT_LBO_W3;                // 2 buffers x (hi 4 KB + lo 4 KB)
 constexpr uint32_t PQ_BIAS = PQ_A1 + 2 * 2 * 2 * PT_LBO_A;
 constexpr uint32_t PQ_ROW = PQ_BIAS + (2 * PT_H + PT_O) * 4;      // 2 x (sc, sn, rc, rn)[128]
 constexpr uint32_t PQ_OUT = PQ_ROW + 2 * 4 * PT_TILE * 4;          // output staging tile
@@ -202,7 +204,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
   }
   for (int i = t; i < (int)(2 * 2 * PT_LBO_W) / 16; i += PP_THREADS)
     reinterpret_cast<uint4*>(smem + PQ_B1)[i] = __ldg(reinterpret_cast<const uint4*>(img + PT_IMG_B1) + i);
-  for (int i = t; i < (int)(2 * 32 * PT_LBO_W3) / 16; i += PP_THREADS)
+  for (int i = t; i < (int)(32 * PT_LBO_W3) / 16; i += PP_THREADS)
     reinterpret_cast<uint4*>(smem + PQ_B3)[i] = __ldg(reinterpret_cast<const uint4*>(img + PT_IMG_B3) + i);
   for (int i = t; i < PT_H; i += PP_THREADS) {
     bias1[i] = __ldg(b1 + i);
@@ -217,7 +219,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
   const uint32_t tmem = tmem_base_s;
   const uint32_t tm_l1 = tmem;              // L1 accumulator buffers: +0, +64
   const uint32_t tm_h = tmem + 128;         // H[b] at +64 b: hi 32 columns, lo 32 columns
-  const uint32_t tm_l2 = tmem + 256;        // layer-2 accumulator (256), layer-3 in its first 32
+  const uint32_t tm_l2 = tmem + 256;        // layer-2 accumulator (256), layer-3 in its first 64
 
   if (warp < PP_EPI_WARPS) {
     // =========================== epilogue warps =====================================
@@ -306,7 +308,15 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         // whole 128-byte rows (a row-per-thread store would cost one L1 wavefront per lane)
         float v[8];
         umma::tmem_ld8(tm_l2 + tlane + (uint32_t)cg * 8, v);
-        umma::tmem_ld_wait();
+        if (X3) {
+          float v2[8];
+          umma::tmem_ld8(tm_l2 + tlane + (uint32_t)(PT_O + cg * 8), v2);
+          umma::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] += v2[e];
+        } else {
+          umma::tmem_ld_wait();
+        }
         if (t == 0) PP_TR(47);
         const float* bb = bias3 + cg * 8;
         unsigned char* stage = smem + PQ_OUT;
@@ -363,11 +373,11 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       const uint32_t s_ring = umma::smem_u32(smem + PQ_RING);
       const uint32_t s_a1 = umma::smem_u32(smem + PQ_A1);
       const uint32_t s_b1h = umma::smem_u32(smem + PQ_B1), s_b1l = s_b1h + 2 * PT_LBO_W;
-      const uint32_t s_b3h = umma::smem_u32(smem + PQ_B3), s_b3l = s_b3h + 32 * PT_LBO_W3;
+      const uint32_t s_b3 = umma::smem_u32(smem + PQ_B3);
       const uint64_t d_b1h = umma::smem_desc(s_b1h, PT_LBO_W, PT_SBO), d_b1l = umma::smem_desc(s_b1l, PT_LBO_W, PT_SBO);
       const uint64_t d_ringh = umma::smem_desc(s_ring, PT_LBO_W, PT_SBO);
       const uint64_t d_ringl = umma::smem_desc(s_ring + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
-      const uint64_t d_b3h = umma::smem_desc(s_b3h, PT_LBO_W3, PT_SBO), d_b3l = umma::smem_desc(s_b3l, PT_LBO_W3, PT_SBO);
+      const uint64_t d_b3 = umma::smem_desc(s_b3, PT_LBO_W3, PT_SBO);
       uint32_t cons = 0, ring_k = 0;
       // layer 1 of quarter q of the tile whose A1 sits in buffer ab -> L1 accumulator q % 2
       auto issue_l1 = [&](int ab, int q) {
@@ -437,11 +447,13 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
             const uint32_t boff = (uint32_t)((q * 4 + ksl) * 2) * (PT_LBO_W3 >> 4);
             const uint32_t acc = (q | ksl) != 0;
             if (X3) {
-              umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_b3h + boff, idesc32, acc);
-              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3l + boff, idesc32, 1);
-              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3h + boff, idesc32, 1);
+              // a_hi * [b_hi | b_lo] -> columns [0,32) | [32,64), a_lo * b_hi -> [0,32): two reads
+              // of the activation operand through the TMEM port instead of three (the port
+              // bounds this phase); the epilogue adds the two column blocks
+              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3 + boff, idesc64, acc);
+              umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_b3 + boff, idesc32, 1);
             } else {
-              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3h + boff, idesc32, acc);
+              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3 + boff, idesc32, acc);
             }
           }
           umma::mma_commit(&h_empty[hb]);
