@@ -246,6 +246,52 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       if (lane == 0) umma::mbar_arrive(&h_full[b]);
       ++prod;
     };
+    // The output tile of the previous iteration: its values wait in registers (o) while the
+    // first two layer-1 quarters of the next tile are handed to the tensor core, and go out
+    // through the padded staging tile as whole 128-byte rows (a row-per-thread store would
+    // cost one L1 wavefront per lane) while the layer-2 UMMAs of that tile run - the epilogue
+    // warps are idle there, and layer 2 starts without waiting for these stores.
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int o_tile = -1;
+    auto store_output = [&]() {
+      unsigned char* stage = smem + PQ_OUT;
+      if (pw_out != nullptr) {
+        float4* dst = reinterpret_cast<float4*>(stage + erow * PP_OUT_PITCH + cg * 32);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int idx = i * (PP_EPI_WARPS * 32) + t;       // 1024 chunks of 16 bytes
+          const int r = idx >> 3, ch = idx & 7;
+          const int p = o_tile * PT_TILE + r;
+          const float4 x = *reinterpret_cast<const float4*>(stage + r * PP_OUT_PITCH + ch * 16);
+          if (p < P) *reinterpret_cast<float4*>(pw_out + (size_t)p * PT_O + ch * 4) = x;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");   // staging reusable
+      }
+      if (pw_hl != nullptr) {
+        // the same row as the block kernels' tensor-core operand: [32 bf16 hi | 32 bf16 lo]
+        // (128 bytes per pair, gn_block_tma.cu loads it with one tensor-map TMA per tile)
+        uint4 h, l;
+        umma::split_bf16x2(o[0], o[1], h.x, l.x);
+        umma::split_bf16x2(o[2], o[3], h.y, l.y);
+        umma::split_bf16x2(o[4], o[5], h.z, l.z);
+        umma::split_bf16x2(o[6], o[7], h.w, l.w);
+        *reinterpret_cast<uint4*>(stage + erow * PP_OUT_PITCH + cg * 16) = h;
+        *reinterpret_cast<uint4*>(stage + erow * PP_OUT_PITCH + 64 + cg * 16) = l;
+        asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int idx = i * (PP_EPI_WARPS * 32) + t;
+          const int r = idx >> 3, ch = idx & 7;
+          const int p = o_tile * PT_TILE + r;
+          const uint4 x = *reinterpret_cast<const uint4*>(stage + r * PP_OUT_PITCH + ch * 16);
+          if (p < P) pw_hl[(size_t)p * 8 + ch] = x;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
+      }
+    };
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = blockIdx.x + it * gridDim.x;
       const int tb = it & 1;
@@ -284,6 +330,10 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         }
         produce(v, bias1 + col);
         if (t == 0) PP_TR(33 + 2 * q);
+        if (q == 1 && it > 0) {   // both operand buffers are queued: idle until l1_done q2
+          store_output();
+          if (t == 0) PP_TR(46);
+        }
       }
       umma::mbar_arrive(&tab_free[tb]);   // this thread's score-table reads of the tile are done
       // ---- layer-2 accumulator quarters -> H --------------------------------------------
@@ -299,13 +349,12 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         produce(v, bias2 + col);
         if (t == 0) PP_TR(41 + q);
       }
-      // ---- output: relu(acc3 + b3) -> pw_out[p, 32]; this warp owns 8 columns -------------
+      // ---- output: relu(acc3 + b3), this thread's 8 columns of its row, into registers; the
+      //      stores are deferred into the next tile (store_output above) ----------------------
       umma::mbar_wait_relaxed(acc3_done, (uint32_t)it & 1u);
       umma::tc_fence_after();
       if (t == 0) PP_TR(45);
       {
-        // this thread's 8 columns of its row -> padded staging tile; then every warp writes
-        // whole 128-byte rows (a row-per-thread store would cost one L1 wavefront per lane)
         float v[8];
         umma::tmem_ld8(tm_l2 + tlane + (uint32_t)cg * 8, v);
         if (X3) {
@@ -319,51 +368,14 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         }
         if (t == 0) PP_TR(47);
         const float* bb = bias3 + cg * 8;
-        unsigned char* stage = smem + PQ_OUT;
-        float o[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaxf(v[e] + bb[e], 0.f);
-        if (pw_out != nullptr) {
-          float4* dst = reinterpret_cast<float4*>(stage + erow * PP_OUT_PITCH + cg * 32);
-          dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-          asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int idx = i * (PP_EPI_WARPS * 32) + t;       // 1024 chunks of 16 bytes
-            const int r = idx >> 3, ch = idx & 7;
-            const int p = tile * PT_TILE + r;
-            const float4 x = *reinterpret_cast<const float4*>(stage + r * PP_OUT_PITCH + ch * 16);
-            if (p < P) *reinterpret_cast<float4*>(pw_out + (size_t)p * PT_O + ch * 4) = x;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");   // staging reusable
-        }
-        if (pw_hl != nullptr) {
-          // the same row as the block kernels' tensor-core operand: [32 bf16 hi | 32 bf16 lo]
-          // (128 bytes per pair, gn_block_tma.cu loads it with one tensor-map TMA per tile)
-          uint4 h, l;
-          umma::split_bf16x2(o[0], o[1], h.x, l.x);
-          umma::split_bf16x2(o[2], o[3], h.y, l.y);
-          umma::split_bf16x2(o[4], o[5], h.z, l.z);
-          umma::split_bf16x2(o[6], o[7], h.w, l.w);
-          *reinterpret_cast<uint4*>(stage + erow * PP_OUT_PITCH + cg * 16) = h;
-          *reinterpret_cast<uint4*>(stage + erow * PP_OUT_PITCH + 64 + cg * 16) = l;
-          asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int idx = i * (PP_EPI_WARPS * 32) + t;
-            const int r = idx >> 3, ch = idx & 7;
-            const int p = tile * PT_TILE + r;
-            const uint4 x = *reinterpret_cast<const uint4*>(stage + r * PP_OUT_PITCH + ch * 16);
-            if (p < P) pw_hl[(size_t)p * 8 + ch] = x;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(PP_EPI_WARPS * 32) : "memory");
-        }
+        o_tile = tile;
       }
-      if (t == 0) PP_TR(46);
       umma::tc_fence_before();   // the next production's arrive orders these loads before the
                                  // UMMAs that overwrite the accumulator
     }
+    store_output();              // the last tile's
   } else if (warp == PP_WARP_MMA) {
     // =============================== MMA issuer =======================================
     if (lane == 0) {
