@@ -10,7 +10,7 @@
 // gn_det_tc.cu spends ~18 000 of its ~23 000 cycles per 128-detection tile waiting for memory:
 // the pooled tile, the shortcut rows, the block output and the U rows are moved by the same
 // eight warps that run the epilogues, one phase after the other (clock64 trace,
-// profiles/r2_det_tma.md).  Here the four dependent GEMMs and their epilogues are all those
+// profiles/r2_det_pwfeat.md).  Here the four dependent GEMMs and their epilogues are all those
 // warps do:
 //   * a ninth warp drives tensor-map TMA: the shortcut tile of the NEXT tile is loaded while
 //     this one computes (4 boxes of 128 rows x 32 floats, SWIZZLE_128B - the row-per-thread
