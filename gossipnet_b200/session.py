@@ -39,6 +39,10 @@ class _Buffers(object):
         self.d_in = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
         self.h_pred_all = torch.empty((max(T, 1),), dtype=torch.float32, pin_memory=True)
         self.h_np = torch.empty((1,), dtype=torch.int32, pin_memory=True)
+        # per-slot device copy of the results (run_pipelined: the D2H of batch i runs on its
+        # own stream while the next forward already overwrites the engine's logits)
+        self.d_pred_all = torch.empty((max(T, 1),), dtype=torch.float32, device=device)
+        self.d_np = torch.empty((1,), dtype=torch.int32, device=device)
         self.bind(T, B)
 
     def bind(self, T, B):
@@ -52,6 +56,7 @@ class _Buffers(object):
             setattr(self, pre + 'cls', view(buf, 'cls', T * 4, torch.int32, (T,)))
             setattr(self, pre + 'off', view(buf, 'off', (B + 1) * 4, torch.int32, (B + 1,)))
         self.h_pred = self.h_pred_all[:T]
+        self.d_pred = self.d_pred_all[:T]
         self.T, self.B = T, B
         # bytes that matter (the aligned staging buffer carries a little padding on top)
         self.h2d_bytes = T * (16 + 4 + 4) + (B + 1) * 4
@@ -69,6 +74,10 @@ class InferenceSession(object):
         self.use_graph = use_graph
         self.graph_after = graph_after       # capture a shape when it is seen this many times
         self.stream = torch.cuda.Stream(device=self.device)
+        # copy streams of run_pipelined: inputs of batch i+1 go up and logits of batch i-1 come
+        # down while the forward of batch i runs
+        self.h2d_stream = torch.cuda.Stream(device=self.device)
+        self.d2h_stream = torch.cuda.Stream(device=self.device)
         self.launches_per_forward = None
         self._seen = collections.Counter()
         self._states = collections.OrderedDict()    # shape key -> (buffers, graph, graph_io)
@@ -109,9 +118,11 @@ class InferenceSession(object):
             except CapacityOverflow:
                 continue
 
-    def _capture(self, buf):
+    def _capture(self, buf, pipelined=False):
         """Warm up on the real inputs (already in buf.d_in), count launches, capture the
-        forward alone (bench's resident measurement) and the whole host-buffer step."""
+        forward alone (bench's resident measurement) and the whole host-buffer step
+        (pipelined: the forward + device copies of its results into the slot; the host
+        copies run on the copy streams)."""
         for _ in range(2):
             self._warm(buf)
         self.engine.refresh_weight_images()     # fresh now: the captures below skip them
@@ -124,10 +135,15 @@ class InferenceSession(object):
             self._forward(buf)
         gio = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gio, stream=self.stream):
-            buf.d_in[:buf.copy_bytes].copy_(buf.h_in[:buf.copy_bytes], non_blocking=True)
-            self._forward(buf)
-            buf.h_pred.copy_(self._pred, non_blocking=True)
-            buf.h_np.copy_(self._num_pairs, non_blocking=True)
+            if pipelined:
+                self._forward(buf)
+                buf.d_pred.copy_(self._pred.view(-1), non_blocking=True)
+                buf.d_np.copy_(self._num_pairs.view(-1), non_blocking=True)
+            else:
+                buf.d_in[:buf.copy_bytes].copy_(buf.h_in[:buf.copy_bytes], non_blocking=True)
+                self._forward(buf)
+                buf.h_pred.copy_(self._pred, non_blocking=True)
+                buf.h_np.copy_(self._num_pairs, non_blocking=True)
         return g, gio
 
     def _eager_buffers(self, T, B):
@@ -212,8 +228,8 @@ class InferenceSession(object):
 
     # ------------------------------------------------------------- pipelined run
     def _pipe_state(self, key, slot):
-        """Staging buffers + captured step (H2D, forward, D2H) of one pipeline slot.  The two
-        slots of a shape have their own pinned and device staging; both graphs run on the
+        """Staging buffers + captured forward of one pipeline slot.  The two slots of a shape
+        have their own pinned and device staging (inputs and results); both graphs run on the
         session's stream, one after the other, over the engine's single workspace."""
         st = self._pipe.get((key, slot))
         if st is not None and st[2] == self.engine.ws_generation:
@@ -225,12 +241,13 @@ class InferenceSession(object):
     def run_pipelined(self, batches):
         """Generator over batches (dets, det_scores, det_classes, img_off) -> new scores per
         batch, in order.  One batch ahead: while the GPU works on batch i the host stages
-        batch i+1 into the other slot's pinned buffer and enqueues its step (H2D, forward,
-        D2H as one captured graph), so per-batch cost is max(host staging, GPU step) instead
-        of their sum.  Every batch's inputs still travel pinned host -> device and its logits
-        device -> pinned host.  A yielded array is a view of the slot's pinned result buffer:
-        valid until two more batches have been yielded.  Shapes seen for the first time (or
-        with use_graph=False) go through `run`."""
+        batch i+1 into the other slot's pinned buffer, its inputs go up on the H2D stream and
+        the logits of batch i-1 come down on the D2H stream, so the compute stream runs the
+        captured forwards back to back and per-batch cost is max(host staging, forward)
+        instead of the sum of staging, copies and forward.  Every batch's inputs still travel
+        pinned host -> device and its logits device -> pinned host.  A yielded array is a view
+        of the slot's pinned result buffer: valid until two more batches have been yielded.
+        Shapes seen for the first time (or with use_graph=False) go through `run`."""
         pending = None          # (buf, event, args)
         slot = 0
 
@@ -262,23 +279,36 @@ class InferenceSession(object):
                 self._fill(buf, args)
                 with torch.cuda.stream(self.stream):
                     buf.d_in[:buf.copy_bytes].copy_(buf.h_in[:buf.copy_bytes], non_blocking=True)
-                    _, gio = self._capture(buf)
+                    _, gio = self._capture(buf, pipelined=True)
+                self.stream.synchronize()
                 self._pipe[(key, slot)] = (buf, gio, self.engine.ws_generation)
                 st = self._pipe[(key, slot)]
             buf, gio, _ = st
+            # the slot's previous batch (two back) has been yielded: its copies are complete
             self._fill(buf, args)
             self._cur = buf
+            with torch.cuda.stream(self.h2d_stream):
+                buf.d_in[:buf.copy_bytes].copy_(buf.h_in[:buf.copy_bytes], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(self.h2d_stream)
             with torch.cuda.stream(self.stream):
+                self.stream.wait_event(ev_in)
                 self.engine.refresh_weight_images()
                 gio.replay()
+                ev_fwd = torch.cuda.Event()
+                ev_fwd.record(self.stream)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(ev_fwd)
+                buf.h_pred.copy_(buf.d_pred, non_blocking=True)
+                buf.h_np.copy_(buf.d_np, non_blocking=True)
                 ev = torch.cuda.Event()
-                ev.record(self.stream)
+                ev.record(self.d2h_stream)
             if pending is not None:
                 out = finish(pending)
                 if out is None:
                     # capacity overflow: everything in flight was computed with too small a
                     # workspace - grow, drop the captures, redo both batches synchronously
-                    self.stream.synchronize()
+                    ev.synchronize()
                     self.engine.capacity = int(int(pending[0].h_np[0]) * 1.25) + 256
                     self._states.clear()
                     self._pipe.clear()
