@@ -254,64 +254,86 @@ neighbor_fill_mask_kernel(const float* __restrict__ dets, const int32_t* __restr
 }
 
 // Single-CTA exclusive scan with a running carry: out[0..n] (out[n] = total).
-// n is at most a few hundred thousand detections, the scan is latency-bound and
-// a single pass over L2-resident data; one CTA of 1024 threads x 4 items.
+// n is at most a few hundred thousand detections and the data is L2 resident, so the scan is
+// bound by latency and by how the one CTA touches memory.  A round covers 32 768 elements as
+// eight segments of 4 096; thread t owns elements [4t, 4t + 4) of every segment, so each load /
+// store of a round is ONE coalesced 16-byte access per thread and the eight loads are in flight
+// together (a thread that owns 16 consecutive elements stores with a 64-byte stride between
+// lanes: 32 sectors per instruction, ~9 us per round).  The segment scans share one pair of
+// barriers; the 64 k degrees of the bench batch are two rounds (42 -> ~10 us).
 constexpr int SCAN_THREADS = 1024;
-constexpr int SCAN_ITEMS = 16;   // per thread and round: 64 k degrees = 4 rounds of one 1024-thread CTA
+constexpr int SCAN_SEGS = 8;
+constexpr int SCAN_ROUND = SCAN_THREADS * 4 * SCAN_SEGS;
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 exclusive_scan_kernel(const int32_t* __restrict__ in, int n, int32_t* __restrict__ out) {
-  __shared__ int warp_sums[SCAN_THREADS / 32];
-  __shared__ int carry_s;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += SCAN_THREADS * SCAN_ITEMS) {
-    const int i0 = base + threadIdx.x * SCAN_ITEMS;
-    int v[SCAN_ITEMS];
-    int tsum = 0;
-    if (i0 + SCAN_ITEMS <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+  __shared__ int warp_sums[SCAN_SEGS][SCAN_THREADS / 32];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  int carry = 0;                       // every thread keeps the same running total
+  for (int base = 0; base < n; base += SCAN_ROUND) {
+    int4 q[SCAN_SEGS];
+    int incl[SCAN_SEGS], own[SCAN_SEGS];
 #pragma unroll
-      for (int j = 0; j < SCAN_ITEMS; j += 4) {      // i0 is a multiple of 16: aligned int4 loads
-        const int4 q = *reinterpret_cast<const int4*>(in + i0 + j);
-        v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+    for (int j = 0; j < SCAN_SEGS; ++j) {
+      const int i0 = base + (j * SCAN_THREADS + t) * 4;
+      if (vec && i0 + 4 <= n) {
+        q[j] = *reinterpret_cast<const int4*>(in + i0);
+      } else {
+        q[j].x = i0 < n ? in[i0] : 0;
+        q[j].y = i0 + 1 < n ? in[i0 + 1] : 0;
+        q[j].z = i0 + 2 < n ? in[i0 + 2] : 0;
+        q[j].w = i0 + 3 < n ? in[i0 + 3] : 0;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < SCAN_ITEMS; ++j) v[j] = (i0 + j < n) ? in[i0 + j] : 0;
+      own[j] = q[j].x + q[j].y + q[j].z + q[j].w;
+      incl[j] = own[j];
     }
-#pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) tsum += v[j];
-    int incl = tsum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+#pragma unroll
+      for (int j = 0; j < SCAN_SEGS; ++j) {
+        const int u = __shfl_up_sync(0xffffffffu, incl[j], d);
+        if (lane >= d) incl[j] += u;
+      }
     }
-    if (lane == 31) warp_sums[warp] = incl;
+    if (lane == 31) {
+#pragma unroll
+      for (int j = 0; j < SCAN_SEGS; ++j) warp_sums[j][warp] = incl[j];
+    }
     __syncthreads();
-    if (warp == 0) {
-      int w = warp_sums[lane];
+    if (warp < SCAN_SEGS) {            // warp j scans the 32 warp totals of segment j
+      int w = warp_sums[warp][lane];
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, w, d);
-        if (lane >= d) w += t;
+        const int u = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += u;
       }
-      warp_sums[lane] = w;  // inclusive over warps
+      warp_sums[warp][lane] = w;
     }
     __syncthreads();
-    const int carry = carry_s;
-    int excl = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + incl - tsum;
+    int seg_off = carry;
 #pragma unroll
-    for (int j = 0; j < SCAN_ITEMS; ++j) {
-      if (i0 + j < n) out[i0 + j] = excl;
-      excl += v[j];
+    for (int j = 0; j < SCAN_SEGS; ++j) {
+      const int i0 = base + (j * SCAN_THREADS + t) * 4;
+      int4 o;
+      o.x = seg_off + (warp > 0 ? warp_sums[j][warp - 1] : 0) + incl[j] - own[j];
+      o.y = o.x + q[j].x;
+      o.z = o.y + q[j].y;
+      o.w = o.z + q[j].z;
+      if (vec && i0 + 4 <= n) {
+        *reinterpret_cast<int4*>(out + i0) = o;
+      } else {
+        if (i0 < n) out[i0] = o.x;
+        if (i0 + 1 < n) out[i0 + 1] = o.y;
+        if (i0 + 2 < n) out[i0 + 2] = o.z;
+        if (i0 + 3 < n) out[i0 + 3] = o.w;
+      }
+      seg_off += warp_sums[j][SCAN_THREADS / 32 - 1];
     }
-    __syncthreads();
-    if (threadIdx.x == SCAN_THREADS - 1) carry_s = carry + warp_sums[SCAN_THREADS / 32 - 1];
-    __syncthreads();
+    carry = seg_off;
+    __syncthreads();                   // warp_sums are rewritten by the next round
   }
-  if (threadIdx.x == 0) out[n] = carry_s;
+  if (t == 0) out[n] = carry;
 }
 
 }  // namespace gn

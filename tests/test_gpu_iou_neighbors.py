@@ -236,3 +236,20 @@ def test_argument_validation():
         ops.iou_dense(a, a)  # CPU tensor: no CPU fallback
     with pytest.raises(ValueError):
         ops.iou_dense(a.cuda().double(), a.cuda().double())
+
+
+@pytest.mark.parametrize('n', [1, 5, 4095, 4096, 16383, 16384, 16385, 64000, 200001])
+@pytest.mark.parametrize('shift', [0, 1])
+def test_exclusive_scan(n, shift):
+    """gn_exclusive_scan (row_ptr of the neighbor lists, network.py:192-195's ordering) against
+    numpy, over round / segment boundaries and with buffers that are not 16-byte aligned."""
+    rs = np.random.RandomState(n)
+    deg = rs.randint(0, 90, size=n).astype(np.int32)
+    src = torch.zeros(n + shift, dtype=torch.int32, device='cuda')
+    src[shift:] = torch.from_numpy(deg).cuda()
+    dst = torch.full((n + 1 + shift,), -7, dtype=torch.int32, device='cuda')
+    got = ops.exclusive_scan(src[shift:], out=dst[shift:]).cpu().numpy()
+    ref = np.concatenate([[0], np.cumsum(deg.astype(np.int64))]).astype(np.int32)
+    assert np.array_equal(got, ref)
+    if shift:
+        assert int(dst[0]) == -7
