@@ -118,6 +118,7 @@ SIGNATURES = {
     'gn_block_det_fwd_tma': [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_int, c_void_p],
+    'gn_set_pdl': [c_int],
     'gn_prepare_fc_images': [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     'gn_fc_fwd_tc': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                      c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],

@@ -22,9 +22,18 @@ int sm_count() {
   return n;
 }
 
+static int g_pdl = 1;
+bool pdl_enabled() { return g_pdl != 0; }
+
 }  // namespace gn
 
 extern "C" {
+
+int gn_set_pdl(int enable) {
+  const int old = gn::g_pdl;
+  gn::g_pdl = enable != 0;
+  return old;
+}
 
 const char* gn_last_error(void) { return gn::g_err; }
 int gn_abi_version(void) { return 1; }

@@ -136,10 +136,14 @@ block_pair_tma_kernel(const __grid_constant__ CUtensorMap tm_pw,
     umma::bulk_copy_g2s(sbase + BT_OFF_W, wimg, BT_W_BYTES, wbar);
   }
   if (t == BT_WARP_LOAD * 32) umma::tma_prefetch_desc(&tm_pw);
+  umma::griddep_launch_dependents();   // the next kernel's CTAs may be placed as ours retire
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // everything above touched only this launch's own constants (pair count, weight image);
+  // red_hl, u and pooled come from the det kernel in front of us
+  umma::griddep_wait();
 
   if (warp >= BT_WARP_LOAD && warp < BT_WARP_MMA) {
     // ================================== producer ======================================
@@ -536,13 +540,21 @@ static int launch_pair_tma(const char* name, bool x3, const void* pw_hl, const v
   const int sms = gn::sm_count();
   if (grid > sms) grid = sms;
   if (x3)
-    gn::block_pair_tma_kernel<true><<<grid, gn::BT_THREADS, gn::BT_SMEM, (cudaStream_t)stream>>>(
-        tm_pw, static_cast<const unsigned char*>(red_hl), u, u_pitch, pair_c, pair_n, num_pairs,
-        capacity, num_dets, b2, static_cast<const unsigned char*>(wimg), pooled);
+    e = gn::launch_kernel(gn::block_pair_tma_kernel<true>, grid, gn::BT_THREADS, gn::BT_SMEM,
+                          (cudaStream_t)stream, gn::pdl_enabled(), tm_pw,
+                          static_cast<const unsigned char*>(red_hl), u, u_pitch, pair_c, pair_n,
+                          num_pairs, capacity, num_dets, b2, static_cast<const unsigned char*>(wimg),
+                          pooled);
   else
-    gn::block_pair_tma_kernel<false><<<grid, gn::BT_THREADS, gn::BT_SMEM, (cudaStream_t)stream>>>(
-        tm_pw, static_cast<const unsigned char*>(red_hl), u, u_pitch, pair_c, pair_n, num_pairs,
-        capacity, num_dets, b2, static_cast<const unsigned char*>(wimg), pooled);
+    e = gn::launch_kernel(gn::block_pair_tma_kernel<false>, grid, gn::BT_THREADS, gn::BT_SMEM,
+                          (cudaStream_t)stream, gn::pdl_enabled(), tm_pw,
+                          static_cast<const unsigned char*>(red_hl), u, u_pitch, pair_c, pair_n,
+                          num_pairs, capacity, num_dets, b2, static_cast<const unsigned char*>(wimg),
+                          pooled);
+  if (e != cudaSuccess) {
+    gn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
   GN_CHECK_LAUNCH(name);
   return GN_OK;
 }

@@ -30,6 +30,27 @@ void set_error(const char* fmt, ...);
 
 int sm_count();
 
+// gn_set_pdl (gossipnet_b200.h): launch the persistent block kernels with programmatic stream
+// serialization, so that each one's prologue overlaps the tail of its predecessor
+bool pdl_enabled();
+
+// <<<grid, block, smem, stream>>> with the programmatic-serialization attribute when `pdl`
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), int grid, int block, size_t smem,
+                                        cudaStream_t stream, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -134,10 +134,14 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
   if (t < NT_D) bias2[t] = __ldg(b_fc2 + t);
   if (stage_b && t < NT_R) biasr[t] = __ldg(b_rd + t);
   if (stage_b && t < NT_F) biasu[t] = __ldg(b_u + t);
+  umma::griddep_launch_dependents();   // the next kernel's CTAs may be placed as ours retire
   umma::tc_fence_before();
   __syncthreads();
   umma::tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+  // up to here only parameters and the weight image were read: pooled (pair kernel in front of
+  // us) and feats_in are touched below
+  umma::griddep_wait();
 
   if (warp == NT_EPI_THREADS / 32) {
     // ================================ copy-engine warp ====================================
@@ -462,13 +466,19 @@ static int launch_block_det_tma(const char* name, bool x3, float* pooled, const 
   const int sms = gn::sm_count();
   if (grid > sms) grid = sms;
   if (x3)
-    gn::block_det_tma_kernel<true><<<grid, gn::NT_THREADS, gn::NT_SMEM, (cudaStream_t)stream>>>(
-        tm_in, tm_out, tm_u, tm_red, pooled, static_cast<const unsigned char*>(wimg), b_fc1, b_fc2,
-        b_rd, b_u, num_dets, has_b);
+    e = gn::launch_kernel(gn::block_det_tma_kernel<true>, grid, gn::NT_THREADS, gn::NT_SMEM,
+                          (cudaStream_t)stream, gn::pdl_enabled(), tm_in, tm_out, tm_u, tm_red, pooled,
+                          static_cast<const unsigned char*>(wimg), b_fc1, b_fc2, b_rd, b_u, num_dets,
+                          has_b);
   else
-    gn::block_det_tma_kernel<false><<<grid, gn::NT_THREADS, gn::NT_SMEM, (cudaStream_t)stream>>>(
-        tm_in, tm_out, tm_u, tm_red, pooled, static_cast<const unsigned char*>(wimg), b_fc1, b_fc2,
-        b_rd, b_u, num_dets, has_b);
+    e = gn::launch_kernel(gn::block_det_tma_kernel<false>, grid, gn::NT_THREADS, gn::NT_SMEM,
+                          (cudaStream_t)stream, gn::pdl_enabled(), tm_in, tm_out, tm_u, tm_red, pooled,
+                          static_cast<const unsigned char*>(wimg), b_fc1, b_fc2, b_rd, b_u, num_dets,
+                          has_b);
+  if (e != cudaSuccess) {
+    gn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e));
+    return GN_ERR_CUDA;
+  }
   GN_CHECK_LAUNCH(name);
   return GN_OK;
 }

@@ -344,6 +344,12 @@ def block_det_fwd_tma(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out, red
               64, 32, _stream())
 
 
+def set_pdl(enable):
+    """Programmatic dependent launch of the persistent block kernels (gn_set_pdl); returns the
+    previous setting.  A captured CUDA graph keeps the setting it was captured with."""
+    return bool(_lib.load().gn_set_pdl(1 if enable else 0))
+
+
 def predict_collapse(flat, table, max_dim, scratch, w_eff, b_eff):
     """Fold the linear predict head into (w_eff, b_eff) (see gn_predict_collapse)."""
     f32 = torch.float32

@@ -444,6 +444,12 @@ int gn_block_det_fwd_tma(float* pooled, const float* feats_in, const void* wimg,
                          float* u_out, int plain_bf16, int num_dets, int shortcut_dim,
                          int pairfeat_dim, int reduced_dim, gn_stream_t stream);
 
+/* Programmatic dependent launch of the persistent block kernels (gn_block_pair_fwd_tma,
+ * gn_block_det_fwd_tma): each starts while its predecessor in the stream drains, runs its
+ * prologue (barriers, tensor memory, weight image) and waits with griddepcontrol.wait before it
+ * touches anything the predecessor wrote.  On by default; returns the previous setting. */
+int gn_set_pdl(int enable);
+
 /* Store-bandwidth micro-benchmark: writes `bytes` (multiple of 16384) bytes of constants with
  * mode 0 st.global.v4 | 1 st.global.cs.v4 | 2 st.global.v8 (256-bit) | 3 st.global.wt.v4 |
  * 4 cp.async.bulk shared->global (16 KB copies) | 5 st.global.v8 + L2 evict-first policy,
