@@ -38,6 +38,13 @@ struct LessFlag {
   __device__ bool operator()(int32_t i, int32_t j) const { return (k[i] != 0) < (k[j] != 0); }
 };
 
+#ifdef DM_TRACE
+__device__ long long dm_trace[8];
+#define DM_TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) dm_trace[i] = clock64(); } while (0)
+#else
+#define DM_TR(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(DM_THREADS)
 detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restrict__ iou_off,
                           const float* __restrict__ score, const uint8_t* __restrict__ ignore,
@@ -58,6 +65,7 @@ detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restri
   __shared__ int has_ties;
   const int t = threadIdx.x;
 
+  DM_TR(0);
   if (t == 0) has_ties = 0;
   for (int i = t; i < n; i += DM_THREADS) {
     labels[d0 + i] = 0.f;
@@ -70,6 +78,7 @@ detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restri
   }
   __syncthreads();
 
+  DM_TR(1);
   // ---- 1. visiting order ------------------------------------------------------
   for (int i = t; i < n; i += DM_THREADS) {
     const float si = sc[i];
@@ -82,6 +91,7 @@ detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restri
     order[rank < n ? rank : n - 1] = i;
     if (ties > 1) has_ties = 1;
   }
+  DM_TR(2);
   if (t == 0 && G > 1) {
     IntroSorter<LessFlag> s{gt_order, LessFlag{ign}};
     s.sort(G);
@@ -99,6 +109,7 @@ detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restri
     }
     __syncthreads();
   }
+  DM_TR(3);
   if (G == 0) return;
 
   // number of regular GTs = first crowd position in gt_order (block-uniform)
@@ -142,6 +153,7 @@ detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restri
     rec[(size_t)i * DM_REC + DM_K + 1] = fc;
   }
   __syncthreads();
+  DM_TR(4);
   if (t >= 32) return;
 
   // ---- 3b. greedy, in visiting order: warp 0 stages 32 records, lane 0 walks them --------
@@ -191,6 +203,7 @@ detection_matching_kernel(const float* __restrict__ iou, const int64_t* __restri
     }
     __syncwarp();
   }
+  DM_TR(5);
 }
 
 // ---------------------------------------------------------------------------
@@ -299,3 +312,9 @@ extern "C" int gn_loss_fwd(const float* prediction, const float* labels, float* 
   GN_CHECK_LAUNCH("gn_loss_fwd");
   return GN_OK;
 }
+
+#ifdef DM_TRACE
+extern "C" int gn_detection_matching_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, gn::dm_trace, sizeof(long long) * 8) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -1,7 +1,7 @@
 """SASS evidence per kernel of libgossipnet_b200.so (run here, no GPU needed):
     python profiles/sass_histogram.py > profiles/r2_sass_histogram.txt
 Counts the Blackwell-specific mnemonics per kernel: UTC*MMA (tcgen05.mma), LDTM / STTM
-(tcgen05.ld / st), UTMALDG (cp.async.bulk.tensor, tensor-map TMA), UBLKCP (cp.async.bulk),
+(tcgen05.ld / st), UTMALDG / UTMASTG (cp.async.bulk.tensor loads / stores, tensor-map TMA), UBLKCP (cp.async.bulk),
 LDGSTS (cp.async), SYNCS (mbarrier), RED / ATOMG."""
 import collections
 import os
@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'gossipnet_b200', 'csrc', 'libgossipnet_b200.so')
-KEYS = ['UTCHMMA', 'LDTM', 'STTM', 'UTMALDG', 'UBLKCP', 'LDGSTS', 'SYNCS', 'UTCBAR', 'HMMA',
+KEYS = ['UTCHMMA', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UBLKCP', 'LDGSTS', 'SYNCS', 'UTCBAR', 'HMMA',
         'FFMA', 'RED', 'ATOMG', 'STG', 'LDG', 'STS', 'LDS', 'MUFU']
 
 
