@@ -378,7 +378,9 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
     store_output();              // the last tile's
   } else if (warp == PP_WARP_MMA) {
     // =============================== MMA issuer =======================================
-    if (lane == 0) {
+    // the whole warp runs the issue sequence with warp-uniform operands; elect.sync inside the
+    // *_elect forms picks the issuing lane (gn_umma.cuh)
+    {
       const uint32_t idesc64 = umma::idesc_bf16_f32(PT_TILE, PP_Q);
       const uint32_t idesc256 = umma::idesc_bf16_f32(PT_TILE, PT_H);
       const uint32_t idesc32 = umma::idesc_bf16_f32(PT_TILE, PT_O);
@@ -390,18 +392,18 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
       const uint64_t d_ringh = umma::smem_desc(s_ring, PT_LBO_W, PT_SBO);
       const uint64_t d_ringl = umma::smem_desc(s_ring + 2 * PT_LBO_W, PT_LBO_W, PT_SBO);
       const uint64_t d_b3 = umma::smem_desc(s_b3, PT_LBO_W3, PT_SBO);
-      uint32_t cons = 0, ring_k = 0;
+      uint32_t cons = 0;
       // layer 1 of quarter q of the tile whose A1 sits in buffer ab -> L1 accumulator q % 2
       auto issue_l1 = [&](int ab, int q) {
         const uint64_t d_ah = umma::smem_desc(s_a1 + (uint32_t)ab * (4 * PT_LBO_A), PT_LBO_A, PT_SBO);
         const uint64_t d_al = umma::smem_desc(s_a1 + (uint32_t)ab * (4 * PT_LBO_A) + 2 * PT_LBO_A, PT_LBO_A, PT_SBO);
         if (X3)
-          umma::mma_bf16x3(tm_l1 + (uint32_t)(q & 1) * 64, d_ah, d_al, d_b1h, d_b1l, 0,
+          umma::mma_bf16x3_elect(tm_l1 + (uint32_t)(q & 1) * 64, d_ah, d_al, d_b1h, d_b1l, 0,
                            (uint32_t)q * (PP_Q * 16 >> 4), idesc64, 0);
         else
-          umma::mma_bf16_ss(tm_l1 + (uint32_t)(q & 1) * 64, d_ah,
+          umma::mma_bf16_ss_elect(tm_l1 + (uint32_t)(q & 1) * 64, d_ah,
                             d_b1h + (uint32_t)q * (PP_Q * 16 >> 4), idesc64, 0);
-        umma::mma_commit(&l1_done[q & 1]);
+        umma::mma_commit_elect(&l1_done[q & 1]);
       };
       umma::mbar_wait(&a1_full[0], 0);
       umma::tc_fence_after();
@@ -412,40 +414,60 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         const int ab = it & 1;
         PP_TR(0);
         // ---- layer 2: quarter q of K as soon as its operand is there -------------------
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t hb = cons & 1u;
-          umma::mbar_wait(&h_full[hb], (cons >> 1) & 1u);
+        // The issuing thread is the pace maker of this phase (48 N = 256 UMMAs of 128 cycles each
+        // against ~90 cycles of issue path per UMMA plus ~125 per mbarrier poll), so the whole
+        // sequence is unrolled: 16 k-steps per tile over a ring of 8 stages make the stage and
+        // the parity of every wait compile-time constants (and so every descriptor), and the
+        // four ring stages of a quarter are polled together instead of one round trip each.
+        static_assert(PP_RING == 8, "stage / parity constants below assume 16 k-steps over 8 stages");
+        // operand q + 1 and its ring stages are polled right AFTER quarter q has been issued:
+        // the ~12 x 128 cycles of queued UMMAs cover the polls' round trips
+        auto acquire = [&](int q) {
+          const uint32_t hb = (uint32_t)q & 1u, hpar = ((uint32_t)q >> 1) & 1u;   // cons = 8 it + q
+          umma::mbar_wait(&h_full[hb], hpar);
+#ifndef PP_NORING
+          const uint32_t s0 = (4u * q) & 7u, par = (4u * q) >> 3;                 // g = 16 it + 4 q + ksl
+          bool ok = umma::mbar_try_wait(&full[s0], par);
+          ok &= umma::mbar_try_wait(&full[s0 + 1], par);
+          ok &= umma::mbar_try_wait(&full[s0 + 2], par);
+          ok &= umma::mbar_try_wait(&full[s0 + 3], par);
+          if (!ok) {
+#pragma unroll
+            for (int ksl = 0; ksl < 4; ++ksl) umma::mbar_wait(&full[s0 + ksl], par);
+          }
+#endif
           umma::tc_fence_after();
+        };
+        acquire(0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t hb = (uint32_t)q & 1u;
           PP_TR(1 + 2 * q);
           const uint32_t a_hi = tm_h + hb * 64, a_lo = a_hi + 32;
-#pragma unroll 1
+#pragma unroll
           for (int ksl = 0; ksl < 4; ++ksl) {
-            const uint32_t g = ring_k++, s = g % PP_RING;
-#ifndef PP_NORING
-            umma::mbar_wait(&full[s], (g / PP_RING) & 1u);
-#endif
-            umma::tc_fence_after();
+            const uint32_t s = (4u * q + ksl) & 7u;
             const uint32_t boff = s * (PT_STAGE >> 4);
             const uint32_t acc = (q | ksl) != 0;
             if (X3) {
-              umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_ringh + boff, idesc256, acc);
-              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringl + boff, idesc256, 1);
-              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringh + boff, idesc256, 1);
+              umma::mma_bf16_ts_elect(tm_l2, a_lo + ksl * 8, d_ringh + boff, idesc256, acc);
+              umma::mma_bf16_ts_elect(tm_l2, a_hi + ksl * 8, d_ringl + boff, idesc256, 1);
+              umma::mma_bf16_ts_elect(tm_l2, a_hi + ksl * 8, d_ringh + boff, idesc256, 1);
             } else {
-              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_ringh + boff, idesc256, acc);
+              umma::mma_bf16_ts_elect(tm_l2, a_hi + ksl * 8, d_ringh + boff, idesc256, acc);
             }
-            umma::mma_commit(&empty[s]);
+            umma::mma_commit_elect(&empty[s]);
           }
-          umma::mma_commit(&h_empty[hb]);
+          umma::mma_commit_elect(&h_empty[hb]);
           PP_TR(2 + 2 * q);
-          ++cons;
           if (q < 2) {
             issue_l1(ab, q + 2);
-            if (q == 1) umma::mma_commit(&a1_empty[ab]);   // A1[ab] has been read for the last time
+            if (q == 1) umma::mma_commit_elect(&a1_empty[ab]);   // A1[ab] has been read for the last time
           }
+          if (q < 3) acquire(q + 1);
         }
-        umma::mma_commit(acc2_done);
+        cons += 4;
+        umma::mma_commit_elect(acc2_done);
         // ---- layer 3 ------------------------------------------------------------------------
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
@@ -462,16 +484,16 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
               // a_hi * [b_hi | b_lo] -> columns [0,32) | [32,64), a_lo * b_hi -> [0,32): two reads
               // of the activation operand through the TMEM port instead of three (the port
               // bounds this phase); the epilogue adds the two column blocks
-              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3 + boff, idesc64, acc);
-              umma::mma_bf16_ts(tm_l2, a_lo + ksl * 8, d_b3 + boff, idesc32, 1);
+              umma::mma_bf16_ts_elect(tm_l2, a_hi + ksl * 8, d_b3 + boff, idesc64, acc);
+              umma::mma_bf16_ts_elect(tm_l2, a_lo + ksl * 8, d_b3 + boff, idesc32, 1);
             } else {
-              umma::mma_bf16_ts(tm_l2, a_hi + ksl * 8, d_b3 + boff, idesc32, acc);
+              umma::mma_bf16_ts_elect(tm_l2, a_hi + ksl * 8, d_b3 + boff, idesc32, acc);
             }
           }
-          umma::mma_commit(&h_empty[hb]);
+          umma::mma_commit_elect(&h_empty[hb]);
           ++cons;
         }
-        umma::mma_commit(acc3_done);
+        umma::mma_commit_elect(acc3_done);
         PP_TR(20);
         // ---- the next tile's first two layer-1 quarters queue up behind layer 3 ---------------
         if (it + 1 < my_tiles) {

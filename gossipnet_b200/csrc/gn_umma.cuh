@@ -271,6 +271,45 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Warp-converged forms: the WHOLE warp executes the statement with warp-uniform operands and
+// elect.sync picks the lane that issues.  With `if (lane == 0)` around the plain forms the
+// operands live in per-thread registers and the compiler wraps every tcgen05 instruction in a
+// waterfall loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~9 instructions per UMMA); uniform
+// operands stay in uniform registers.  elect.sync with a full mask always picks the same lane,
+// so mma_commit_elect tracks the UMMAs issued through these forms.
+__device__ __forceinline__ void mma_bf16_ss_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ts_elect(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
+                                                  uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_bf16x3_elect(uint32_t tmem_d, uint64_t a_hi, uint64_t a_lo,
+                                                 uint64_t b_hi, uint64_t b_lo, uint32_t a_off16,
+                                                 uint32_t b_off16, uint32_t idesc, uint32_t accumulate) {
+  mma_bf16_ss_elect(tmem_d, a_lo + a_off16, b_hi + b_off16, idesc, accumulate);
+  mma_bf16_ss_elect(tmem_d, a_hi + a_off16, b_lo + b_off16, idesc, 1);
+  mma_bf16_ss_elect(tmem_d, a_hi + a_off16, b_hi + b_off16, idesc, 1);
+}
+
 // 8 consecutive 32-bit columns of this thread's TMEM lane (32x32b.x8)
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile(
