@@ -211,7 +211,7 @@ block_pair_tma_kernel(const __grid_constant__ CUtensorMap tm_pw,
     // Two issuing threads (this one and the FC2 issuer below) keep the in-order tensor pipe
     // fed: FC1 is bound by shared-memory operand reads, FC2 by the TMEM read of its A
     // operand, and a single issuer would idle the pipe across its own mbarrier waits.
-    if (lane == 0) {
+    {   // whole warp, warp-uniform operands; elect.sync picks the issuing lane (gn_umma.cuh)
       const uint32_t idesc64 = umma::idesc_bf16_f32(BT_TILE, 64);
       const uint32_t idesc128 = umma::idesc_bf16_f32(BT_TILE, 128);
       const uint64_t d_w1 = umma::smem_desc_sw128(sbase + BT_OFF_W);
@@ -245,25 +245,25 @@ block_pair_tma_kernel(const __grid_constant__ CUtensorMap tm_pw,
           const int j = q & 1;
           if (X3 && BT_STACK) {
             // x_hi . [W_hi | W_lo] -> columns [0,64) | [64,128);  x_lo . W_hi -> [0,64)
-            umma::mma_bf16_ss(d1, da + j * 2, d_w1 + q * 2, idesc128, q > 0);
-            umma::mma_bf16_ss(d1, da + (2 + j) * 2, d_w1 + q * 2, idesc64, 1);
+            umma::mma_bf16_ss_elect(d1, da + j * 2, d_w1 + q * 2, idesc128, q > 0);
+            umma::mma_bf16_ss_elect(d1, da + (2 + j) * 2, d_w1 + q * 2, idesc64, 1);
           } else if (X3) {
-            umma::mma_bf16_ss(d1, da + (2 + j) * 2, d_w1 + q * 2, idesc64, q > 0);            // lo . hi
-            umma::mma_bf16_ss(d1, da + j * 2, d_w1 + (BT_WATOM >> 4) + q * 2, idesc64, 1);     // hi . lo
-            umma::mma_bf16_ss(d1, da + j * 2, d_w1 + q * 2, idesc64, 1);                       // hi . hi
+            umma::mma_bf16_ss_elect(d1, da + (2 + j) * 2, d_w1 + q * 2, idesc64, q > 0);            // lo . hi
+            umma::mma_bf16_ss_elect(d1, da + j * 2, d_w1 + (BT_WATOM >> 4) + q * 2, idesc64, 1);     // hi . lo
+            umma::mma_bf16_ss_elect(d1, da + j * 2, d_w1 + q * 2, idesc64, 1);                       // hi . hi
           } else {
-            umma::mma_bf16_ss(d1, da + j * 2, d_w1 + q * 2, idesc64, q > 0);
+            umma::mma_bf16_ss_elect(d1, da + j * 2, d_w1 + q * 2, idesc64, q > 0);
           }
         }
-        umma::mma_commit(&fc1_done[b]);
-        umma::mma_commit(&a_empty[s]);
+        umma::mma_commit_elect(&fc1_done[b]);
+        umma::mma_commit_elect(&a_empty[s]);
         BT_TR(3);
       }
       BT_ACC_FLUSH(4);
     }
   } else if (warp == BT_WARP_MMA + 1) {
     // ============================== FC2 issuer ==========================================
-    if (lane == 0) {
+    {   // whole warp, warp-uniform operands; elect.sync picks the issuing lane (gn_umma.cuh)
       const uint32_t idesc64 = umma::idesc_bf16_f32(BT_TILE, 64);
       const uint64_t d_w2h = umma::smem_desc_sw128(sbase + BT_OFF_W + 2 * BT_WATOM);
       const uint64_t d_w2l = umma::smem_desc_sw128(sbase + BT_OFF_W + 3 * BT_WATOM);
@@ -282,14 +282,14 @@ block_pair_tma_kernel(const __grid_constant__ CUtensorMap tm_pw,
 #pragma unroll
         for (int ks = 0; ks < BT_F / 16; ++ks) {
           if (X3) {
-            umma::mma_bf16_ts(d2, hl + ks * 8, d_w2h + ks * 2, idesc64, ks > 0);
-            umma::mma_bf16_ts(d2, hh + ks * 8, d_w2l + ks * 2, idesc64, 1);
-            umma::mma_bf16_ts(d2, hh + ks * 8, d_w2h + ks * 2, idesc64, 1);
+            umma::mma_bf16_ts_elect(d2, hl + ks * 8, d_w2h + ks * 2, idesc64, ks > 0);
+            umma::mma_bf16_ts_elect(d2, hh + ks * 8, d_w2l + ks * 2, idesc64, 1);
+            umma::mma_bf16_ts_elect(d2, hh + ks * 8, d_w2h + ks * 2, idesc64, 1);
           } else {
-            umma::mma_bf16_ts(d2, hh + ks * 8, d_w2h + ks * 2, idesc64, ks > 0);
+            umma::mma_bf16_ts_elect(d2, hh + ks * 8, d_w2h + ks * 2, idesc64, ks > 0);
           }
         }
-        umma::mma_commit(&fc2_done[b]);
+        umma::mma_commit_elect(&fc2_done[b]);
         BT_TR(1);
       }
       BT_ACC_FLUSH(8);
