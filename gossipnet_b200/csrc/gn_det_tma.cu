@@ -58,17 +58,18 @@ __device__ long long nt_trace[32];
 #define NT_TR(i) do { } while (0)
 #endif
 
+// issued by a whole converged warp: elect.sync picks the lane (gn_umma.cuh)
 template <int KSTEPS, bool X3>
 __device__ __forceinline__ void nt_gemm(uint32_t tmem_d, uint64_t d_ah, uint64_t d_al, uint64_t d_bh,
                                         uint64_t d_bl, uint32_t lbo_b, uint32_t idesc) {
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) {
     if (X3)
-      umma::mma_bf16x3(tmem_d, d_ah, d_al, d_bh, d_bl, ks * (2 * NT_LBO_A >> 4),
-                       ks * (2 * lbo_b >> 4), idesc, ks > 0);
+      umma::mma_bf16x3_elect(tmem_d, d_ah, d_al, d_bh, d_bl, ks * (2 * NT_LBO_A >> 4),
+                             ks * (2 * lbo_b >> 4), idesc, ks > 0);
     else
-      umma::mma_bf16_ss(tmem_d, d_ah + ks * (2 * NT_LBO_A >> 4), d_bh + ks * (2 * lbo_b >> 4), idesc,
-                        ks > 0);
+      umma::mma_bf16_ss_elect(tmem_d, d_ah + ks * (2 * NT_LBO_A >> 4), d_bh + ks * (2 * lbo_b >> 4),
+                              idesc, ks > 0);
   }
 }
 
@@ -245,11 +246,11 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       umma::tc_fence_before();
       nt_epi_sync();
       NT_TR(1);
-      if (t == 0) {
+      if (warp == 0) {
         if (weights_pending) umma::mbar_wait(wbar, 0);
         umma::tc_fence_after();
         nt_gemm<NT_F / 16, X3>(tm1, d_a64h, d_a64l, d_w1h, d_w1l, NT_F * 16, umma::idesc_bf16_f32(NT_TILE, NT_F));
-        umma::mma_commit(bar_mma);
+        umma::mma_commit_elect(bar_mma);
       }
       weights_pending = false;
       // pooled <- 0 for the next block.  After the hand-off: fence.proxy.async waits for the
@@ -291,10 +292,10 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       umma::tc_fence_before();
       nt_epi_sync();
       NT_TR(3);
-      if (t == 0) {
+      if (warp == 0) {
         umma::tc_fence_after();
         nt_gemm<NT_F / 16, X3>(tm2, d_a64h, d_a64l, d_w2h, d_w2l, NT_D * 16, umma::idesc_bf16_f32(NT_TILE, NT_D));
-        umma::mma_commit(bar_mma);
+        umma::mma_commit_elect(bar_mma);
       }
       umma::mbar_wait(sc_full, (uint32_t)it & 1u);                     // shortcut rows are in the boxes
       if (stage_b && it > 0) umma::mbar_wait(u_free, (uint32_t)(it - 1) & 1u);   // U boxes of the last tile are out
@@ -343,13 +344,12 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       umma::tc_fence_before();
       nt_epi_sync();
       NT_TR(6);
-      if (t == 0) {
-        umma::mbar_arrive(feats_ready);          // the copy-engine warp stores the block output
-        if (stage_b) {
-          umma::tc_fence_after();
-          nt_gemm<NT_D / 16, X3>(tmr, d_a128h, d_a128l, d_wrh, d_wrl, NT_R * 16, umma::idesc_bf16_f32(NT_TILE, NT_R));
-          umma::mma_commit(bar_mma);
-        }
+      if (t == 0) umma::mbar_arrive(feats_ready);          // the copy-engine warp stores the block output
+      if (warp == 0 && stage_b) {
+        __syncwarp();
+        umma::tc_fence_after();
+        nt_gemm<NT_D / 16, X3>(tmr, d_a128h, d_a128l, d_wrh, d_wrl, NT_R * 16, umma::idesc_bf16_f32(NT_TILE, NT_R));
+        umma::mma_commit_elect(bar_mma);
       }
       if (it + 1 < my_tiles) load_pooled(row0 + (int)gridDim.x * NT_TILE);
       if (stage_b) {
@@ -383,10 +383,10 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         umma::tc_fence_before();
         nt_epi_sync();
         NT_TR(8);
-        if (t == 0) {
+        if (warp == 0) {
           umma::tc_fence_after();
           nt_gemm<NT_R / 16, X3>(tm2, d_a32h, d_a32l, d_wuh, d_wul, NT_WU_PITCH, umma::idesc_bf16_f32(NT_TILE, NT_F));
-          umma::mma_commit(bar_mma);
+          umma::mma_commit_elect(bar_mma);
         }
         umma::mbar_wait(bar_mma, par);
         par ^= 1;

@@ -162,13 +162,13 @@ fc_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ mas
       umma::fence_smem_to_async();
       umma::tc_fence_before();
       __syncthreads();
-      if (t == 0) {
+      if (t < 32) {      // warp 0, converged: elect.sync picks the issuing lane (gn_umma.cuh)
         umma::mbar_wait(wbar, wpar);
         umma::tc_fence_after();
         for (int ks = 0; ks < ksteps; ++ks)
-          umma::mma_bf16x3(tmem, d_ah, d_al, d_bh, d_bl, ks * (2 * FT_LBO_A >> 4),
-                           ks * (2 * (uint32_t)n * 16 >> 4), idesc, (kc | ks) != 0);
-        umma::mma_commit(bar);
+          umma::mma_bf16x3_elect(tmem, d_ah, d_al, d_bh, d_bl, ks * (2 * FT_LBO_A >> 4),
+                                 ks * (2 * (uint32_t)n * 16 >> 4), idesc, (kc | ks) != 0);
+        umma::mma_commit_elect(bar);
       }
       wpar ^= 1;
       umma::mbar_wait(bar, par);        // the UMMAs have consumed the chunk: buffers reusable
@@ -411,7 +411,7 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
     }
   } else if (warp == WT_CONV_WARPS) {
     // ================================ MMA issuer =======================================
-    if (lane == 0) {
+    {   // whole warp, warp-uniform operands; elect.sync picks the issuing lane (gn_umma.cuh)
       const uint32_t idesc = umma::idesc_bf16_f32(128, n);
       const uint32_t sbase = umma::smem_u32(op_base);
 #pragma unroll 1
@@ -426,12 +426,12 @@ fc_wgrad_tc_kernel(const float* __restrict__ x, int ldx, const float* __restrict
           const uint64_t d_ah = umma::smem_desc(sa + mt * 128 * 16, lbo_a, 128);
           const uint64_t d_al = umma::smem_desc(sa + a_half + mt * 128 * 16, lbo_a, 128);
           for (int ks = 0; ks < R / 16; ++ks)
-            umma::mma_bf16x3(tmem + (uint32_t)(mt * n), d_ah, d_al, d_bh, d_bl, ks * (2 * lbo_a >> 4),
-                             ks * (2 * lbo_b >> 4), idesc, (it | ks) != 0);
+            umma::mma_bf16x3_elect(tmem + (uint32_t)(mt * n), d_ah, d_al, d_bh, d_bl, ks * (2 * lbo_a >> 4),
+                                   ks * (2 * lbo_b >> 4), idesc, (it | ks) != 0);
         }
-        umma::mma_commit(&op_empty[o]);
+        umma::mma_commit_elect(&op_empty[o]);
       }
-      umma::mma_commit(done);
+      umma::mma_commit_elect(done);
     }
   } else {
     // ================================ converters ======================================
