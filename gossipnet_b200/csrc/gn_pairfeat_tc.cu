@@ -424,8 +424,8 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         // the ~12 x 128 cycles of queued UMMAs cover the polls' round trips
         auto acquire = [&](int q) {
           const uint32_t hb = (uint32_t)q & 1u, hpar = ((uint32_t)q >> 1) & 1u;   // cons = 8 it + q
-          umma::mbar_wait(&h_full[hb], hpar);
 #ifndef PP_NORING
+          // the ring stages first (they are there long before the operand is)
           const uint32_t s0 = (4u * q) & 7u, par = (4u * q) >> 3;                 // g = 16 it + 4 q + ksl
           bool ok = umma::mbar_try_wait(&full[s0], par);
           ok &= umma::mbar_try_wait(&full[s0 + 1], par);
@@ -436,6 +436,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
             for (int ksl = 0; ksl < 4; ++ksl) umma::mbar_wait(&full[s0 + ksl], par);
           }
 #endif
+          umma::mbar_wait(&h_full[hb], hpar);
           umma::tc_fence_after();
         };
         acquire(0);
