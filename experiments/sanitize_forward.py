@@ -31,6 +31,9 @@ sess = InferenceSession(net)
 d = np.concatenate([im['dets'] for im in imgs]); s = np.concatenate([im['det_scores'] for im in imgs])
 c = np.concatenate([im['det_classes'] for im in imgs]); off = np.array([0, 300, 301, 358, 998], np.int32)
 print('session       ', float(sess.run(d, s, c, off).sum()))
+# pipelined session: copy streams + captured forwards (two slots), three batches
+outs = [o.copy() for o in sess.run_pipelined([(d, s, c, off)] * 3)]
+print('pipelined     ', float(outs[-1].sum()), bool(np.array_equal(outs[0], outs[2])))
 # plain bf16
 setup('coco_person', 3, compute_dtype='bf16')
 print('bf16          ', float(Gnet(1)(imgs[0]).sum()))
