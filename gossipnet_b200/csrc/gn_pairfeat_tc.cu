@@ -126,7 +126,10 @@ constexpr int PP_EPI_WARPS = 16;
 constexpr int PP_WARP_MMA = 16, PP_WARP_LOAD = 17, PP_WARP_GEO = 18;
 constexpr int PP_THREADS = (PP_WARP_GEO + 4) * 32;   // 704
 constexpr int PP_Q = 64;                              // hidden columns per quarter
-constexpr int PP_RING = 8;                            // W2 k-step stages in flight
+#ifndef PP_RING_N
+#define PP_RING_N 8
+#endif
+constexpr int PP_RING = PP_RING_N;                    // W2 k-step stages in flight
 constexpr uint32_t PP_OUT_PITCH = 144;                // output staging row pitch (bytes): 128 + 16,
                                                       // so 8 consecutive rows hit 8 distinct 16-byte bank groups
 
@@ -419,14 +422,15 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
         // sequence is unrolled: 16 k-steps per tile over a ring of 8 stages make the stage and
         // the parity of every wait compile-time constants (and so every descriptor), and the
         // four ring stages of a quarter are polled together instead of one round trip each.
-        static_assert(PP_RING == 8, "stage / parity constants below assume 16 k-steps over 8 stages");
+        static_assert(PP_RING == 8 || PP_RING == 4, "stage / parity constants below assume 16 k-steps over 8 or 4 stages");
         // operand q + 1 and its ring stages are polled right AFTER quarter q has been issued:
         // the ~12 x 128 cycles of queued UMMAs cover the polls' round trips
         auto acquire = [&](int q) {
           const uint32_t hb = (uint32_t)q & 1u, hpar = ((uint32_t)q >> 1) & 1u;   // cons = 8 it + q
 #ifndef PP_NORING
           // the ring stages first (they are there long before the operand is)
-          const uint32_t s0 = (4u * q) & 7u, par = (4u * q) >> 3;                 // g = 16 it + 4 q + ksl
+          // g = 16 it + 4 q + ksl: stage g % RING, parity (g / RING) & 1 - both independent of it
+          const uint32_t s0 = (4u * q) & (PP_RING - 1), par = ((4u * q) / PP_RING) & 1u;
           bool ok = umma::mbar_try_wait(&full[s0], par);
           ok &= umma::mbar_try_wait(&full[s0 + 1], par);
           ok &= umma::mbar_try_wait(&full[s0 + 2], par);
@@ -447,7 +451,7 @@ pwfeat_pipe_kernel(const float* __restrict__ dets, const float* __restrict__ sco
           const uint32_t a_hi = tm_h + hb * 64, a_lo = a_hi + 32;
 #pragma unroll
           for (int ksl = 0; ksl < 4; ++ksl) {
-            const uint32_t s = (4u * q + ksl) & 7u;
+            const uint32_t s = (4u * q + ksl) & (PP_RING - 1);
             const uint32_t boff = s * (PT_STAGE >> 4);
             const uint32_t acc = (q | ksl) != 0;
             if (X3) {
