@@ -91,14 +91,15 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                      float* pooled, const unsigned char* __restrict__ wimg,
                      const float* __restrict__ b_fc1, const float* __restrict__ b_fc2,
                      const float* __restrict__ b_rd, const float* __restrict__ b_u, int num_dets,
-                     int has_b) {
+                     int has_a, int has_b) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   const int num_tiles = (num_dets + NT_TILE - 1) / NT_TILE;
   if ((int)blockIdx.x >= num_tiles) return;
   const int my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const bool stage_b = has_b != 0;
+  // stage_a = false (block 1): feats_in goes straight into reduce_dim, nothing is stored back
+  const bool stage_a = has_a != 0, stage_b = has_b != 0;
 
   const uint32_t sbase = (umma::smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* smem = smem_raw + (sbase - umma::smem_u32(smem_raw));
@@ -131,8 +132,8 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                           NT_WU_PITCH, wbar);
     }
   }
-  if (t < NT_F) bias1[t] = __ldg(b_fc1 + t);
-  if (t < NT_D) bias2[t] = __ldg(b_fc2 + t);
+  if (stage_a && t < NT_F) bias1[t] = __ldg(b_fc1 + t);
+  if (stage_a && t < NT_D) bias2[t] = __ldg(b_fc2 + t);
   if (stage_b && t < NT_R) biasr[t] = __ldg(b_rd + t);
   if (stage_b && t < NT_F) biasu[t] = __ldg(b_u + t);
   umma::griddep_launch_dependents();   // the next kernel's CTAs may be placed as ours retire
@@ -163,9 +164,11 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       for (int it = 0; it < my_tiles; ++it) {
         const int row0 = (blockIdx.x + it * gridDim.x) * NT_TILE;
         umma::mbar_wait_relaxed(feats_ready, (uint32_t)it & 1u);
-        for (int b = 0; b < 4; ++b) umma::tma_store_2d(&tm_out, b * 32, row0, s_feats + b * NT_BOX);
-        umma::bulk_commit_group();
-        umma::bulk_wait_group_read0();          // the boxes may be overwritten
+        if (stage_a) {
+          for (int b = 0; b < 4; ++b) umma::tma_store_2d(&tm_out, b * 32, row0, s_feats + b * NT_BOX);
+          umma::bulk_commit_group();
+          umma::bulk_wait_group_read0();        // the boxes may be overwritten
+        }
         if (it + 1 < my_tiles) load_shortcut(row0 + (int)gridDim.x * NT_TILE);
         if (stage_b) {
           umma::mbar_wait_relaxed(u_ready, (uint32_t)it & 1u);
@@ -223,11 +226,12 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         }
       }
     };
-    load_pooled(blockIdx.x * NT_TILE);
+    if (stage_a) load_pooled(blockIdx.x * NT_TILE);
 
     for (int it = 0; it < my_tiles; ++it) {
       const int row0 = (blockIdx.x + it * gridDim.x) * NT_TILE;
       NT_TR(0);
+      if (stage_a) {
       // ---- pooled (prefetched) -> A (K = 64) ----------------------------------------------
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -297,12 +301,15 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         nt_gemm<NT_F / 16, X3>(tm2, d_a64h, d_a64l, d_w2h, d_w2l, NT_D * 16, umma::idesc_bf16_f32(NT_TILE, NT_D));
         umma::mma_commit_elect(bar_mma);
       }
+      }   // stage_a
       umma::mbar_wait(sc_full, (uint32_t)it & 1u);                     // shortcut rows are in the boxes
       if (stage_b && it > 0) umma::mbar_wait(u_free, (uint32_t)(it - 1) & 1u);   // U boxes of the last tile are out
       NT_TR(4);
-      umma::mbar_wait(bar_mma, par);
-      par ^= 1;
-      umma::tc_fence_after();
+      if (stage_a) {
+        umma::mbar_wait(bar_mma, par);
+        par ^= 1;
+        umma::tc_fence_after();
+      }
       NT_TR(5);
       // ---- feats_out = relu(feats_in + acc + b_fc2): in place in the boxes, and -> A (K = 128)
 #pragma unroll
@@ -311,24 +318,31 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         unsigned char* brow = feats + (uint32_t)(col0 >> 5) * NT_BOX + rowoff;
         const uint32_t ch0 = (uint32_t)(col0 & 31) >> 2;               // first 16-byte chunk: 0 or 4
         float v[16];
-        umma::tmem_ld16(tm2 + tlane + col0, v);
+        if (stage_a) umma::tmem_ld16(tm2 + tlane + col0, v);
         float4 res[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           res[g] = *reinterpret_cast<const float4*>(brow + (((ch0 + g) ^ sw) << 4));
-        umma::tmem_ld_wait();
+        if (stage_a) umma::tmem_ld_wait();
         float x[16];
+        if (stage_a) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          x[g * 4 + 0] = fmaxf(res[g].x + (v[g * 4 + 0] + bias2[col0 + g * 4 + 0]), 0.f);
-          x[g * 4 + 1] = fmaxf(res[g].y + (v[g * 4 + 1] + bias2[col0 + g * 4 + 1]), 0.f);
-          x[g * 4 + 2] = fmaxf(res[g].z + (v[g * 4 + 2] + bias2[col0 + g * 4 + 2]), 0.f);
-          x[g * 4 + 3] = fmaxf(res[g].w + (v[g * 4 + 3] + bias2[col0 + g * 4 + 3]), 0.f);
+          for (int g = 0; g < 4; ++g) {
+            x[g * 4 + 0] = fmaxf(res[g].x + (v[g * 4 + 0] + bias2[col0 + g * 4 + 0]), 0.f);
+            x[g * 4 + 1] = fmaxf(res[g].y + (v[g * 4 + 1] + bias2[col0 + g * 4 + 1]), 0.f);
+            x[g * 4 + 2] = fmaxf(res[g].z + (v[g * 4 + 2] + bias2[col0 + g * 4 + 2]), 0.f);
+            x[g * 4 + 3] = fmaxf(res[g].w + (v[g * 4 + 3] + bias2[col0 + g * 4 + 3]), 0.f);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(brow + (((ch0 + g) ^ sw) << 4)) =
+                make_float4(x[g * 4 + 0], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            x[g * 4 + 0] = res[g].x; x[g * 4 + 1] = res[g].y; x[g * 4 + 2] = res[g].z; x[g * 4 + 3] = res[g].w;
+          }
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          *reinterpret_cast<float4*>(brow + (((ch0 + g) ^ sw) << 4)) =
-              make_float4(x[g * 4 + 0], x[g * 4 + 1], x[g * 4 + 2], x[g * 4 + 3]);
         if (stage_b) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -347,11 +361,13 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       if (t == 0) umma::mbar_arrive(feats_ready);          // the copy-engine warp stores the block output
       if (warp == 0 && stage_b) {
         __syncwarp();
+        if (weights_pending) umma::mbar_wait(wbar, 0);     // block 1: the first GEMM of the kernel
         umma::tc_fence_after();
         nt_gemm<NT_D / 16, X3>(tmr, d_a128h, d_a128l, d_wrh, d_wrl, NT_R * 16, umma::idesc_bf16_f32(NT_TILE, NT_R));
         umma::mma_commit_elect(bar_mma);
       }
-      if (it + 1 < my_tiles) load_pooled(row0 + (int)gridDim.x * NT_TILE);
+      weights_pending = false;
+      if (stage_a && it + 1 < my_tiles) load_pooled(row0 + (int)gridDim.x * NT_TILE);
       if (stage_b) {
         umma::mbar_wait(bar_mma, par);
         par ^= 1;
@@ -423,7 +439,7 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
 
 static int launch_block_det_tma(const char* name, bool x3, float* pooled, const float* feats_in,
                                 const void* wimg, const float* b_fc1, const float* b_fc2,
-                                const float* b_rd, int has_b, float* feats_out, void* red_hl,
+                                const float* b_rd, int has_a, int has_b, float* feats_out, void* red_hl,
                                 const float* b_u, float* u_out, int num_dets, int shortcut_dim,
                                 int pairfeat_dim, int reduced_dim, gn_stream_t stream) {
   GN_REQUIRE(num_dets >= 0, "%s: negative size", name);
@@ -433,7 +449,10 @@ static int launch_block_det_tma(const char* name, bool x3, float* pooled, const 
     return GN_ERR_UNSUPPORTED;
   }
   if (num_dets == 0) return GN_OK;
-  GN_REQUIRE(pooled && feats_in && wimg && b_fc1 && b_fc2 && feats_out, "%s: null pointer", name);
+  GN_REQUIRE(feats_in && wimg, "%s: null pointer", name);
+  GN_REQUIRE(has_a || has_b, "%s: nothing to do", name);
+  GN_REQUIRE(!has_a || (pooled && b_fc1 && b_fc2 && feats_out),
+             "%s: stage A needs pooled, fc1 / fc2 biases and feats_out", name);
   GN_REQUIRE(!has_b || (b_rd && red_hl && b_u && u_out),
              "%s: stage B needs reduce_dim / pw_fc1 biases, red_hl and u_out", name);
   GN_REQUIRE((((uintptr_t)pooled | (uintptr_t)feats_in | (uintptr_t)feats_out | (uintptr_t)wimg |
@@ -442,7 +461,11 @@ static int launch_block_det_tma(const char* name, bool x3, float* pooled, const 
   CUtensorMap tm_in, tm_out, tm_u, tm_red;
   const uint64_t rows = (uint64_t)num_dets;
   int r = gn::encode_tmap_2d_f32(&tm_in, feats_in, rows, gn::NT_D, gn::NT_D * 4, gn::NT_TILE, 32);
-  if (r == 0) r = gn::encode_tmap_2d_f32(&tm_out, feats_out, rows, gn::NT_D, gn::NT_D * 4, gn::NT_TILE, 32);
+  if (has_a) {
+    if (r == 0) r = gn::encode_tmap_2d_f32(&tm_out, feats_out, rows, gn::NT_D, gn::NT_D * 4, gn::NT_TILE, 32);
+  } else {
+    tm_out = tm_in;     // not used
+  }
   if (has_b) {
     if (r == 0) r = gn::encode_tmap_2d_f32(&tm_u, u_out, rows, gn::NT_F, gn::NT_F * 4, gn::NT_TILE, 32);
     if (r == 0) r = gn::encode_tmap_2d_bf16(&tm_red, red_hl, rows, 2 * gn::NT_R, 4 * gn::NT_R, gn::NT_TILE, 2 * gn::NT_R);
@@ -469,12 +492,12 @@ static int launch_block_det_tma(const char* name, bool x3, float* pooled, const 
     e = gn::launch_kernel(gn::block_det_tma_kernel<true>, grid, gn::NT_THREADS, gn::NT_SMEM,
                           (cudaStream_t)stream, gn::pdl_enabled(), tm_in, tm_out, tm_u, tm_red, pooled,
                           static_cast<const unsigned char*>(wimg), b_fc1, b_fc2, b_rd, b_u, num_dets,
-                          has_b);
+                          has_a, has_b);
   else
     e = gn::launch_kernel(gn::block_det_tma_kernel<false>, grid, gn::NT_THREADS, gn::NT_SMEM,
                           (cudaStream_t)stream, gn::pdl_enabled(), tm_in, tm_out, tm_u, tm_red, pooled,
                           static_cast<const unsigned char*>(wimg), b_fc1, b_fc2, b_rd, b_u, num_dets,
-                          has_b);
+                          has_a, has_b);
   if (e != cudaSuccess) {
     gn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e));
     return GN_ERR_CUDA;
@@ -483,7 +506,8 @@ static int launch_block_det_tma(const char* name, bool x3, float* pooled, const 
   return GN_OK;
 }
 
-// Stage A (+ stage B when has_stage_b) of gn_block_det_fwd_img_u on the copy-engine kernel.
+// gn_block_det_fwd_img_u on the copy-engine kernel (stage A when pooled is given, stage B when
+// has_stage_b; pooled == NULL: block 1, feats_in straight into reduce_dim).
 // feats_in and feats_out may not alias partially (equal or disjoint); u_out is [T, 64] fp32,
 // red_hl [>= T, 64] bf16.  plain_bf16 != 0: the bf16 arithmetic.
 extern "C" int gn_block_det_fwd_tma(float* pooled, const float* feats_in, const void* wimg,
@@ -493,7 +517,7 @@ extern "C" int gn_block_det_fwd_tma(float* pooled, const float* feats_in, const 
                                     int shortcut_dim, int pairfeat_dim, int reduced_dim,
                                     gn_stream_t stream) {
   return launch_block_det_tma("gn_block_det_fwd_tma", plain_bf16 == 0, pooled, feats_in, wimg, b_fc1,
-                              b_fc2, b_rd, has_stage_b, feats_out, red_hl, b_u, u_out, num_dets,
+                              b_fc2, b_rd, pooled != nullptr, has_stage_b, feats_out, red_hl, b_u, u_out, num_dets,
                               shortcut_dim, pairfeat_dim, reduced_dim, stream);
 }
 

@@ -406,10 +406,10 @@ class GnetEngine(object):
             s = 'gnet/block%d/' % b
             nxt = 'gnet/block%d/' % (b + 1)
             last = b == nb
-            if tma_mode and b >= 1 and self.det_tma:
+            if tma_mode and self.det_tma:
                 ops.block_det_fwd_tma(
                     pooled_in, feats_in, image[det_off[b]:det_off[b] + det_b],
-                    p[s + 'fc1/biases'], p[s + 'fc2/biases'],
+                    p[s + 'fc1/biases'] if b >= 1 else None, p[s + 'fc2/biases'] if b >= 1 else None,
                     None if last else p[nxt + 'reduce_dim/biases'], out,
                     None if last else inter_hl, None if last else p[nxt + 'pw_fc1/biases'],
                     None if last else inter, bf16=self.bf16)

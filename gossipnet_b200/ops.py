@@ -332,14 +332,16 @@ def block_det_fwd_img_u(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out, r
 
 def block_det_fwd_tma(pooled, feats_in, wimg, b_fc1, b_fc2, b_rd, feats_out, red_hl, b_u, u_out,
                       bf16=False):
-    """block_det_fwd_img_u (stage A present) on the copy-engine kernel: tile transfers by
-    tensor-map TMA from a dedicated warp (gn_det_tma.cu).  b_rd None: only feats_out."""
+    """block_det_fwd_img_u on the copy-engine kernel: tile transfers by tensor-map TMA from a
+    dedicated warp (gn_det_tma.cu).  b_rd None: only feats_out (after the last block);
+    pooled None: block 1, feats_in straight into reduce_dim."""
     f32 = torch.float32
     T, d = feats_in.shape
-    _lib.call('gn_block_det_fwd_tma', _chk(pooled, f32, 'pooled'), _chk(feats_in, f32, 'feats_in'),
-              _chk(wimg, torch.uint8, 'wimg'), _chk(b_fc1, f32, 'b_fc1'), _chk(b_fc2, f32, 'b_fc2'),
-              _chk(b_rd, f32, 'b_rd', True), 1 if b_rd is not None else 0,
-              _chk(feats_out, f32, 'feats_out'), _chk(red_hl, torch.bfloat16, 'red_hl', True),
+    _lib.call('gn_block_det_fwd_tma', _chk(pooled, f32, 'pooled', True), _chk(feats_in, f32, 'feats_in'),
+              _chk(wimg, torch.uint8, 'wimg'), _chk(b_fc1, f32, 'b_fc1', True),
+              _chk(b_fc2, f32, 'b_fc2', True), _chk(b_rd, f32, 'b_rd', True),
+              1 if b_rd is not None else 0, _chk(feats_out, f32, 'feats_out', True),
+              _chk(red_hl, torch.bfloat16, 'red_hl', True),
               _chk(b_u, f32, 'b_u', True), _chk(u_out, f32, 'u_out', True), 1 if bf16 else 0, T, d,
               64, 32, _stream())
 

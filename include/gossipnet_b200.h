@@ -437,7 +437,8 @@ int gn_block_det_fwd_img_u(float* pooled, const float* feats_in, const void* wim
  * the shortcut tile comes in and the block output, u_out and red_hl leave by tensor-map TMA from a
  * dedicated warp, the pooled rows of the next tile are prefetched, so the eight epilogue warps
  * only run the four dependent GEMM epilogues (network.py:390-408, :348-354, :376-386).  Same
- * results bit for bit.  has_stage_b = 0: only feats_out (after the last block). */
+ * results bit for bit.  has_stage_b = 0: only feats_out (after the last block); pooled == NULL:
+ * block 1, feats_in goes straight into reduce_dim and nothing is stored back. */
 int gn_block_det_fwd_tma(float* pooled, const float* feats_in, const void* wimg,
                          const float* b_fc1, const float* b_fc2, const float* b_rd,
                          int has_stage_b, float* feats_out, void* red_hl, const float* b_u,

@@ -204,21 +204,24 @@ def test_det_copy_engine_kernel_bit_identical(n, bf16):
     rs = np.random.RandomState(n)
     pooled0 = dev(np.maximum(rs.normal(0, 1, (n, 64)), 0).astype(F32))
     feats = dev(np.maximum(rs.normal(0, 1, (n, 128)), 0).astype(F32))
-    for b, last in ((1, False), (2, True)):
+    for b, last in ((0, False), (1, False), (2, True)):      # block 1's reduce only / both stages / last block
         wimg = image[det_off[b]:det_off[b] + det_b]
         s, nxt = 'gnet/block%d/' % b, 'gnet/block%d/' % (b + 1)
         got = []
         for fn in (ops.block_det_fwd_img_u, ops.block_det_fwd_tma):
-            pooled = pooled0.clone()
+            pooled = pooled0.clone() if b >= 1 else None
             out = torch.full((n, 128), -1.0, device='cuda')
             red = torch.full((n + 1, 64), -1.0, device='cuda').to(torch.bfloat16)
             u = torch.full((n, 64), -1.0, device='cuda')
-            fn(pooled, feats, wimg, p[s + 'fc1/biases'], p[s + 'fc2/biases'],
-               None if last else p[nxt + 'reduce_dim/biases'], out, None if last else red[:n],
-               None if last else p[nxt + 'pw_fc1/biases'], None if last else u, bf16=bf16)
-            assert torch.all(pooled == 0)
+            fn(pooled, feats, wimg, p[s + 'fc1/biases'] if b >= 1 else None,
+               p[s + 'fc2/biases'] if b >= 1 else None,
+               None if last else p[nxt + 'reduce_dim/biases'], out if b >= 1 else None,
+               None if last else red[:n], None if last else p[nxt + 'pw_fc1/biases'],
+               None if last else u, bf16=bf16)
+            if b >= 1:
+                assert torch.all(pooled == 0)
             got.append((out, red, u))
         for a, c in zip(*got):
             assert torch.equal(a, c)
-        assert float(got[1][0].abs().sum()) > 0
+        assert float(got[1][0 if b >= 1 else 2].abs().sum()) > 0
         assert torch.all(got[1][1][n] == -1.0)        # the row behind the last detection is not touched
