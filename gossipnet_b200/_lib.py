@@ -119,6 +119,7 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                              c_int, c_void_p],
     'gn_set_pdl': [c_int],
+    'gn_clip_gradients': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p],
     'gn_prepare_fc_images': [c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     'gn_fc_fwd_tc': [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                      c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],

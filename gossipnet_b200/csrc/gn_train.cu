@@ -298,6 +298,56 @@ extern "C" int gn_gather_concat_bwd(const float* dx, int w, int r, const int32_t
   return GN_OK;
 }
 
+// ---------------------------------------------------------------------------
+// clip_gradient_norm of slim.learning.create_train_op (train.py:73-76): every variable's
+// gradient is clipped by its OWN l2 norm (tf.clip_by_norm: t * clip / max(||t||, clip)).  The
+// gradient that is clipped is the one of the total loss, i.e. grad_scale * grad + decay * theta
+// (train.py:238, get_total_loss includes the l2 regularizer).  One CTA per parameter entry;
+// table = (offset, size) int32 pairs.  Writes the clipped full gradient back into grads, so the
+// optimizer kernels run with grad_scale = 1 and without their decay term afterwards.
+// ---------------------------------------------------------------------------
+namespace gn {
+__global__ void __launch_bounds__(256)
+clip_gradients_kernel(float* __restrict__ grads, const float* __restrict__ params,
+                      const float* __restrict__ decay, const int32_t* __restrict__ table,
+                      float grad_scale, float clip_norm) {
+  __shared__ float red[8];
+  __shared__ float factor_s;
+  const int off = table[2 * blockIdx.x], size = table[2 * blockIdx.x + 1];
+  const int t = threadIdx.x;
+  float ss = 0.f;
+  for (int i = t; i < size; i += 256) {
+    const float g = grad_scale * grads[off + i] + (decay != nullptr ? decay[off + i] * params[off + i] : 0.f);
+    grads[off + i] = g;
+    ss += g * g;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+  if ((t & 31) == 0) red[t >> 5] = ss;
+  __syncthreads();
+  if (t == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    factor_s = clip_norm / fmaxf(sqrtf(tot), clip_norm);
+  }
+  __syncthreads();
+  const float f = factor_s;
+  for (int i = t; i < size; i += 256) grads[off + i] *= f;
+}
+}  // namespace gn
+
+extern "C" int gn_clip_gradients(float* grads, const float* params, const float* decay,
+                                 const int32_t* table, int entries, float grad_scale,
+                                 float clip_norm, gn_stream_t stream) {
+  GN_REQUIRE(entries >= 0 && clip_norm > 0.f, "gn_clip_gradients: bad arguments");
+  if (entries == 0) return GN_OK;
+  GN_REQUIRE(grads && params && table, "gn_clip_gradients: null pointer");
+  gn::clip_gradients_kernel<<<entries, 256, 0, (cudaStream_t)stream>>>(grads, params, decay, table,
+                                                                       grad_scale, clip_norm);
+  GN_CHECK_LAUNCH("gn_clip_gradients");
+  return GN_OK;
+}
+
 extern "C" int gn_adam_step(float* params, const float* grads, float* m, float* v,
                             const float* decay, int64_t n, float lr, float beta1, float beta2,
                             float eps, int64_t step, float grad_scale, gn_stream_t stream) {

@@ -523,6 +523,15 @@ def adam_step(params, grads, m, v, decay, lr, beta1, beta2, eps, step, grad_scal
               float(grad_scale), _stream())
 
 
+def clip_gradients(grads, params, decay, table, grad_scale, clip_norm):
+    """grads <- clip_by_norm(grad_scale * grads + decay * params) per parameter entry
+    (table: int32 [entries, 2] = offset, size), the reference's clip_gradient_norm."""
+    _lib.call('gn_clip_gradients', _chk(grads, torch.float32, 'grads'),
+              _chk(params, torch.float32, 'params'), _chk(decay, torch.float32, 'decay', True),
+              _chk(table, torch.int32, 'table'), table.shape[0], float(grad_scale),
+              float(clip_norm), _stream())
+
+
 def momentum_step(params, grads, accum, decay, lr, momentum, grad_scale):
     _lib.call('gn_momentum_step', _chk(params, torch.float32, 'params'),
               _chk(grads, torch.float32, 'grads'), _chk(accum, torch.float32, 'accum'),

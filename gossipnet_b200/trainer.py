@@ -36,11 +36,9 @@ class Trainer(object):
             raise ValueError('unknown optimizer {}'.format(self.optimizer))   # train.py:73
         self.momentum = cfg.train.momentum if momentum is None else momentum
         self.beta1, self.beta2, self.eps = beta1, beta2, eps
-        if float(cfg.train.gradient_clipping) > 0:
-            # slim.learning.create_train_op(clip_gradient_norm=...) clips every variable's
-            # gradient by its own norm (train.py:73-76); the shipped configs leave it at -1
-            raise NotImplementedError('cfg.train.gradient_clipping > 0 is not implemented in the '
-                                      'fused optimizer step; set it to -1 (the reference default)')
+        # slim.learning.create_train_op(clip_gradient_norm=...) clips every variable's gradient
+        # by its own norm (train.py:73-76); <= 0 (the shipped configs: -1) disables it
+        self.clip_norm = float(cfg.train.gradient_clipping)
         wd = cfg.train.weight_decay if weight_decay is None else weight_decay
         dev = eng.device
         # flat gradient buffer + one trailing slot carrying the image count, so a
@@ -54,6 +52,8 @@ class Trainer(object):
             if e.regularized:
                 decay[e.offset:e.offset + e.size] = wd
         self.decay = torch.from_numpy(decay).to(dev)
+        self.clip_table = torch.tensor([[e.offset, e.size] for e in eng.layout.values()],
+                                       dtype=torch.int32, device=dev)
         self.state1 = torch.zeros(eng.total, dtype=torch.float32, device=dev)   # Adam m / momentum
         self.state2 = torch.zeros(eng.total, dtype=torch.float32, device=dev)   # Adam v
         self.global_step = 0
@@ -288,11 +288,17 @@ class Trainer(object):
         scale = 1.0 / max(n_images, 1.0)
         self.global_step += 1
         self.eng.weights_version += 1        # the optimizer kernel writes the flat buffer in place
+        decay = self.decay
+        if self.clip_norm > 0:
+            # the clipped gradient of the total loss (data term + l2 regularizer) replaces grad
+            ops.clip_gradients(self.grad, self.eng.flat, self.decay, self.clip_table, scale,
+                               self.clip_norm)
+            scale, decay = 1.0, None
         if self.optimizer == 'adam':
-            ops.adam_step(self.eng.flat, self.grad, self.state1, self.state2, self.decay, lr,
+            ops.adam_step(self.eng.flat, self.grad, self.state1, self.state2, decay, lr,
                           self.beta1, self.beta2, self.eps, self.global_step, scale)
         else:
-            ops.momentum_step(self.eng.flat, self.grad, self.state1, self.decay, lr,
+            ops.momentum_step(self.eng.flat, self.grad, self.state1, decay, lr,
                               self.momentum, scale)
         return n_images
 

@@ -317,6 +317,14 @@ int gn_loss_fwd(const float* prediction, const float* labels, float* weights_io,
                 const float* class_weights, int normalize, float loss_multiplier,
                 float* loss_out, float* dlogit, gn_stream_t stream);
 
+/* clip_gradient_norm of slim.learning.create_train_op (reference train.py:73-76): every
+ * parameter entry's gradient of the TOTAL loss, grad_scale * grads + decay * params (decay may be
+ * NULL), is clipped by its own l2 norm (tf.clip_by_norm) and written back into grads.  table:
+ * `entries` (offset, size) int32 pairs into the flat buffers.  Afterwards the optimizer steps run
+ * with grad_scale = 1 and decay = NULL. */
+int gn_clip_gradients(float* grads, const float* params, const float* decay, const int32_t* table,
+                      int entries, float grad_scale, float clip_norm, gn_stream_t stream);
+
 /* ---- A11: training step ----------------------------------------------------------
  * Backward pieces of the graph TF autodiff builds for nms_net/network.py and the
  * optimizer update of train.py:64-77.  The training forward runs the unfused

@@ -154,3 +154,64 @@ def test_learning_rate_schedule_matches_reference_semantics():
     lr = LearningRate()
     got = [lr.get_lr(i) for i in range(1, 8)]
     assert got == [0.1, 0.1, 0.1, 0.01, 0.01, 0.01, 0.01]
+
+
+def test_clip_gradients_per_variable_norm():
+    """gn_clip_gradients = slim's clip_gradient_norm (reference train.py:73-76): every entry's
+    gradient of the total loss, scale * grad + decay * theta, times clip / max(||.||, clip)."""
+    rs = np.random.RandomState(3)
+    sizes = [1, 7, 256, 4096, 65536, 33]
+    offs = np.concatenate([[0], np.cumsum([(s + 3) // 4 * 4 for s in sizes])]).astype(np.int64)
+    total = int(offs[-1])
+    grad = rs.normal(0, 1, total).astype(np.float32)
+    theta = rs.normal(0, 1, total).astype(np.float32)
+    decay = np.where(rs.rand(total) < 0.5, 1e-2, 0.0).astype(np.float32)
+    grad[offs[2]:offs[2] + sizes[2]] *= 1e-4          # an entry whose norm stays under the clip
+    table = np.stack([offs[:-1], sizes], axis=1).astype(np.int32)
+    scale, clip = 0.125, 2.0
+    ref = grad.astype(np.float64).copy()
+    for o, n in table:
+        g = scale * grad[o:o + n].astype(np.float64) + decay[o:o + n].astype(np.float64) * theta[o:o + n]
+        ref[o:o + n] = g * clip / max(np.sqrt(np.sum(g * g)), clip)
+    d = lambda a: torch.from_numpy(a).cuda()
+    g_dev = d(grad.copy())
+    ops.clip_gradients(g_dev, d(theta), d(decay), d(table), scale, clip)
+    got = g_dev.cpu().numpy()
+    for o, n in table:
+        assert np.allclose(got[o:o + n], ref[o:o + n], rtol=2e-5, atol=1e-7)
+        assert np.sqrt(np.sum(got[o:o + n].astype(np.float64) ** 2)) <= clip * (1 + 1e-5)
+    pad = np.ones(total, bool)
+    for o, n in table:
+        pad[o:o + n] = False
+    assert np.array_equal(got[pad], grad[pad])         # alignment padding between entries untouched
+
+
+def test_trainer_gradient_clipping():
+    """cfg.train.gradient_clipping: a norm nobody reaches leaves the step unchanged; a small one
+    bounds every variable's Adam input (first step: |update| = lr for every touched element, so
+    compare the second moments instead)."""
+    load_experiment('coco_person', num_blocks=2)
+    imgs = [synthetic.make_image(120, 1, image_index=i) for i in range(2)]
+    v2, init = [], None
+    for clip in (-1.0, 1e9, 1e-3):
+        cfg.train.gradient_clipping = clip
+        try:
+            tr = Trainer(Gnet(1))
+            if init is None:
+                init = tr.eng.flat.clone()
+            tr.eng.flat.copy_(init)               # the same starting point for the three steps
+            tr.eng.weights_version += 1
+            tr.step(imgs, 1e-3)
+            v2.append(tr.state2.clone())
+        finally:
+            cfg.train.gradient_clipping = -1.0
+    # the gradient itself is summed with atomics (order varies run to run): compare |g| recovered
+    # from Adam's second moment, (1 - beta2) g^2, in the l2 norm instead of the +-lr first-step update
+    g0, g1 = torch.sqrt(v2[0] / (1 - 0.999)), torch.sqrt(v2[1] / (1 - 0.999))
+    assert float((g0 - g1).norm() / g0.norm()) < 1e-5
+    # Adam's v after one step = (1 - beta2) g^2: per entry sum(g^2) <= clip^2 once clipped
+    tr_layout = tr.eng.layout
+    for e in tr_layout.values():
+        gsq = float(v2[2][e.offset:e.offset + e.size].sum()) / (1 - 0.999)
+        assert gsq <= (1e-3) ** 2 * (1 + 1e-3), e.name
+    assert float((v2[0] / (1 - 0.999)).sum()) > 1e-4     # the unclipped step was far above that
