@@ -45,6 +45,39 @@ __global__ void gather_concat_kernel(const float* __restrict__ pw, int w,
   }
 }
 
+// the same with one 16-byte chunk per thread (w, r multiples of 4, 16-byte aligned rows):
+// four times fewer index computations and memory instructions - this op moves 160 MB per block
+// of the training step
+__global__ void gather_concat_vec4_kernel(const float4* __restrict__ pw, int w4,
+                                          const float4* __restrict__ feats,
+                                          const float4* __restrict__ nfeats, int r4,
+                                          const int32_t* __restrict__ pair_c,
+                                          const int32_t* __restrict__ pair_n,
+                                          const int32_t* __restrict__ num_pairs, int capacity,
+                                          float4* __restrict__ x) {
+  const int P = min(__ldg(num_pairs), capacity);
+  const int width4 = w4 + 2 * r4;
+  const int64_t total = (int64_t)P * width4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int p = (int)(i / width4);
+    const int j = (int)(i - (int64_t)p * width4);
+    float4 v;
+    if (j < w4) {
+      v = __ldg(pw + (size_t)p * w4 + j);
+    } else if (j < w4 + r4) {
+      v = __ldg(feats + (size_t)__ldg(pair_c + p) * r4 + (j - w4));
+    } else {
+      const int c = __ldg(pair_c + p), n = __ldg(pair_n + p);
+      v = (c == n) ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(nfeats + (size_t)n * r4 + (j - w4 - r4));
+    }
+    x[i] = v;
+  }
+}
+
+// (segment_max itself stays one column per thread: it is a serial walk over each detection's
+// pairs, bound by latency, and a 16-byte version has four times fewer threads - measured 48 us
+// against 27.)
 __global__ void segment_max_kernel(const float* __restrict__ x, int f,
                                    const int32_t* __restrict__ row_ptr, int num_dets,
                                    float* __restrict__ out) {
@@ -219,8 +252,18 @@ extern "C" int gn_block_gather_concat(const float* pw, int w, const float* feats
   GN_REQUIRE(pw && feats && nfeats && pair_c && pair_n && num_pairs && x,
              "gn_block_gather_concat: null pointer");
   const int threads = 256;
-  int64_t blocks = gn::ceil_div64((int64_t)capacity * (w + 2 * r), threads);
   const int cap = 32 * gn::sm_count();
+  if (w % 4 == 0 && r % 4 == 0 &&
+      (((uintptr_t)pw | (uintptr_t)feats | (uintptr_t)nfeats | (uintptr_t)x) & 15) == 0) {
+    const int64_t blocks = gn::ceil_div64((int64_t)capacity * ((w + 2 * r) / 4), threads);
+    gn::gather_concat_vec4_kernel<<<(int)(blocks < cap ? blocks : cap), threads, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(pw), w / 4, reinterpret_cast<const float4*>(feats),
+        reinterpret_cast<const float4*>(nfeats), r / 4, pair_c, pair_n, num_pairs, capacity,
+        reinterpret_cast<float4*>(x));
+    GN_CHECK_LAUNCH("gn_block_gather_concat");
+    return GN_OK;
+  }
+  int64_t blocks = gn::ceil_div64((int64_t)capacity * (w + 2 * r), threads);
   const int grid = (int)(blocks < cap ? blocks : cap);
   gn::gather_concat_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(
       pw, w, feats, nfeats, r, pair_c, pair_n, num_pairs, capacity, x);
@@ -234,8 +277,8 @@ extern "C" int gn_segment_max(const float* x, int f, const int32_t* row_ptr, int
   if (num_dets == 0) return GN_OK;
   GN_REQUIRE(x && row_ptr && out, "gn_segment_max: null pointer");
   const int threads = 256;
-  int64_t blocks = gn::ceil_div64((int64_t)num_dets * f, threads);
   const int cap = 32 * gn::sm_count();
+  int64_t blocks = gn::ceil_div64((int64_t)num_dets * f, threads);
   const int grid = (int)(blocks < cap ? blocks : cap);
   gn::segment_max_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(x, f, row_ptr, num_dets, out);
   GN_CHECK_LAUNCH("gn_segment_max");

@@ -126,6 +126,32 @@ __global__ void segment_max_bwd_kernel(const float* __restrict__ h, const float*
   }
 }
 
+// four columns per thread (f multiple of 4, 16-byte aligned rows)
+__global__ void segment_max_bwd_vec4_kernel(const float4* __restrict__ h, const float4* __restrict__ pooled,
+                                            const float4* __restrict__ dpooled, int f4,
+                                            const int32_t* __restrict__ row_ptr, int num_dets,
+                                            float4* __restrict__ dh) {
+  const int64_t total = (int64_t)num_dets * f4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / f4), j = (int)(i - (int64_t)row * f4);
+    const int b = __ldg(row_ptr + row), e = __ldg(row_ptr + row + 1);
+    const float4 m = pooled[i], g = dpooled[i];
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int p = b; p < e; ++p) {
+      const float4 v = h[(size_t)p * f4 + j];
+      c0 += (v.x == m.x); c1 += (v.y == m.y); c2 += (v.z == m.z); c3 += (v.w == m.w);
+    }
+    const float4 share = make_float4(c0 > 0 ? g.x / (float)c0 : 0.f, c1 > 0 ? g.y / (float)c1 : 0.f,
+                                     c2 > 0 ? g.z / (float)c2 : 0.f, c3 > 0 ? g.w / (float)c3 : 0.f);
+    for (int p = b; p < e; ++p) {
+      const float4 v = h[(size_t)p * f4 + j];
+      dh[(size_t)p * f4 + j] = make_float4(v.x == m.x ? share.x : 0.f, v.y == m.y ? share.y : 0.f,
+                                           v.z == m.z ? share.z : 0.f, v.w == m.w ? share.w : 0.f);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // gradient of [pw | feats[c] | nfeats[n] (0 on self pairs)] (network.py:367-376)
 //   dpw_accum[p, :w]  += dx[p, :w]
@@ -155,6 +181,37 @@ __global__ void gather_concat_bwd_c_kernel(const float* __restrict__ dx, int w, 
     float s = 0.f;
     for (int p = b; p < e; ++p) s += dx[(size_t)p * width + w + j];
     dfeats[i] += s;
+  }
+}
+
+// The pair-parallel parts (dpw, dnfeats) in one pass, one thread per (pair, 16-byte chunk), the
+// neighbor part as vector atomics (red.global.add.v4.f32); w, r multiples of 4, 16-byte aligned
+// rows.  The per-detection segment sum (dfeats) keeps its own kernel: walking a detection's pairs
+// serially inside a fused kernel was measured 215 us against 132 for the three separate ones.
+__global__ void gather_concat_bwd_pairs_vec4_kernel(const float4* __restrict__ dx, int w4, int r4,
+                                                    const int32_t* __restrict__ pair_c,
+                                                    const int32_t* __restrict__ pair_n,
+                                                    const int32_t* __restrict__ num_pairs, int capacity,
+                                                    float4* __restrict__ dpw,
+                                                    float4* __restrict__ dnfeats) {
+  const int width4 = w4 + 2 * r4, per = w4 + r4;
+  const int64_t total = (int64_t)min(__ldg(num_pairs), capacity) * per;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / per;
+    const int j = (int)(i - p * per);
+    if (j < w4) {
+      const float4 g = dx[p * width4 + j];
+      float4 a = dpw[p * w4 + j];
+      a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+      dpw[p * w4 + j] = a;
+    } else {
+      const int c = __ldg(pair_c + p), n = __ldg(pair_n + p);
+      if (c == n) continue;   // tf.select zeroed these rows: no gradient
+      const float4 g = dx[p * width4 + r4 + j];
+      if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f)
+        atomicAdd(dnfeats + (size_t)n * r4 + (j - w4), g);
+    }
   }
 }
 
@@ -272,8 +329,13 @@ extern "C" int gn_segment_max_bwd(const float* h, const float* pooled, const flo
   GN_REQUIRE(f > 0 && num_dets >= 0, "gn_segment_max_bwd: bad sizes");
   if (num_dets == 0) return GN_OK;
   GN_REQUIRE(h && pooled && dpooled && row_ptr && dh, "gn_segment_max_bwd: null pointer");
-  gn::segment_max_bwd_kernel<<<gn::ew_grid((int64_t)num_dets * f), 256, 0, (cudaStream_t)stream>>>(
-      h, pooled, dpooled, f, row_ptr, num_dets, dh);
+  if (f % 4 == 0 && (((uintptr_t)h | (uintptr_t)pooled | (uintptr_t)dpooled | (uintptr_t)dh) & 15) == 0)
+    gn::segment_max_bwd_vec4_kernel<<<gn::ew_grid((int64_t)num_dets * (f / 4)), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(h), reinterpret_cast<const float4*>(pooled),
+        reinterpret_cast<const float4*>(dpooled), f / 4, row_ptr, num_dets, reinterpret_cast<float4*>(dh));
+  else
+    gn::segment_max_bwd_kernel<<<gn::ew_grid((int64_t)num_dets * f), 256, 0, (cudaStream_t)stream>>>(
+        h, pooled, dpooled, f, row_ptr, num_dets, dh);
   GN_CHECK_LAUNCH("gn_segment_max_bwd");
   return GN_OK;
 }
@@ -288,6 +350,16 @@ extern "C" int gn_gather_concat_bwd(const float* dx, int w, int r, const int32_t
              "gn_gather_concat_bwd: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   const int width = w + 2 * r;
+  if (w % 4 == 0 && r % 4 == 0 &&
+      (((uintptr_t)dx | (uintptr_t)dpw_accum | (uintptr_t)dnfeats) & 15) == 0) {
+    gn::gather_concat_bwd_c_kernel<<<gn::ew_grid((int64_t)num_dets * r), 256, 0, s>>>(
+        dx, w, r, width, row_ptr, num_dets, dfeats);
+    gn::gather_concat_bwd_pairs_vec4_kernel<<<gn::ew_grid((int64_t)capacity * ((w + r) / 4)), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(dx), w / 4, r / 4, pair_c, pair_n, num_pairs, capacity,
+        reinterpret_cast<float4*>(dpw_accum), reinterpret_cast<float4*>(dnfeats));
+    GN_CHECK_LAUNCH("gn_gather_concat_bwd");
+    return GN_OK;
+  }
   gn::gather_concat_bwd_pw_kernel<<<gn::ew_grid((int64_t)capacity * w), 256, 0, s>>>(
       dx, w, width, num_pairs, capacity, dpw_accum);
   gn::gather_concat_bwd_c_kernel<<<gn::ew_grid((int64_t)num_dets * r), 256, 0, s>>>(
