@@ -235,3 +235,33 @@ def test_weight_derived_buffers_follow_weight_changes():
     g2 = sess.run(*args).copy()
     assert not np.array_equal(g2, g1)
     assert np.array_equal(g2, Gnet(1, params=net.engine.flat.cpu().numpy())(test_batch).cpu().numpy())
+
+
+def test_launch_chain_switches_do_not_change_the_logits():
+    """Programmatic dependent launch on / off (gn_set_pdl) and the two detection-level kernels
+    (copy-engine kernel of gn_det_tma.cu / eight-warp kernel of gn_det_tc.cu) are pure
+    scheduling / data-movement choices: bit-identical logits, eager and as a replayed graph."""
+    from gossipnet_b200 import ops
+    from gossipnet_b200.session import InferenceSession
+    load_experiment('coco_person', num_blocks=4)
+    imgs = [synthetic.make_image(n, 1, image_index=i) for i, n in enumerate((700, 1, 333))]
+    dets = np.concatenate([im['dets'] for im in imgs]).astype(np.float32)
+    scores = np.concatenate([im['det_scores'] for im in imgs]).astype(np.float32)
+    classes = np.concatenate([im['det_classes'] for im in imgs]).astype(np.int32)
+    off = np.array([0, 700, 701, 1034], np.int32)
+    results = []
+    try:
+        for pdl in (True, False):
+            for det_tma in (True, False):
+                ops.set_pdl(pdl)
+                net = Gnet(1)
+                net.engine.det_tma = det_tma
+                sess = InferenceSession(net)
+                outs = [sess.run(dets, scores, classes, off).copy() for _ in range(3)]   # third run replays the graph
+                assert sess._graph
+                assert np.array_equal(outs[0], outs[2])
+                results.append(outs[2])
+    finally:
+        ops.set_pdl(True)
+    for r in results[1:]:
+        assert np.array_equal(r, results[0])
