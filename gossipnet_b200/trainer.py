@@ -57,6 +57,7 @@ class Trainer(object):
         self.state1 = torch.zeros(eng.total, dtype=torch.float32, device=dev)   # Adam m / momentum
         self.state2 = torch.zeros(eng.total, dtype=torch.float32, device=dev)   # Adam v
         self.global_step = 0
+        self._host_images = 0      # images accumulated into gradbuf since the last update (this rank)
         self._zero_bias = torch.zeros(1024, dtype=torch.float32, device=dev)
         # every FC and its gradients on the tensor cores (gn_fc_tc.cu, bf16x3); False: the fp32
         # CUDA-core kernels (gn_fc.cu / gn_train.cu), kept as the cross-check.  Forward and
@@ -154,6 +155,7 @@ class Trainer(object):
         T = dets.shape[0]
         if zero_grad:
             self.gradbuf.zero_()
+            self._host_images = 0
         if self.use_tc_fwd or self.use_tc_bwd:
             ops.prepare_fc_images(eng.flat, self._img_table, self._img)
 
@@ -277,6 +279,7 @@ class Trainer(object):
             d = self._fc_bwd(pw_acts[i - 1], d, 'gnet/pw_feats/fc%d' % i, rows_dev=num_pairs,
                              need_dx=i > 1, mask=pw_acts[i])
         self.gradbuf[-1] += float(len(batches))
+        self._host_images += len(batches)
         return res
 
     # ------------------------------------------------------------------- update
@@ -284,7 +287,11 @@ class Trainer(object):
         """All-reduce (sum) the flat gradient + image count, then the optimizer update
         with grad_scale = 1 / (images of the step over all ranks)."""
         parallel.allreduce_sum_(self.gradbuf)
-        n_images = float(self.gradbuf[-1].item())
+        if parallel.world() > 1:
+            n_images = float(self.gradbuf[-1].item())   # the other ranks' shards: read back (one sync)
+        else:
+            n_images = float(self._host_images)         # single process: known here, no host sync
+        self._host_images = 0
         scale = 1.0 / max(n_images, 1.0)
         self.global_step += 1
         self.eng.weights_version += 1        # the optimizer kernel writes the flat buffer in place
@@ -307,6 +314,7 @@ class Trainer(object):
         shard of a small step is empty still joins the all-reduce)."""
         if len(batches) == 0:
             self.gradbuf.zero_()
+            self._host_images = 0
             res = {'num_images': 0, 'loss_out': None}
         else:
             res = self.forward_backward(batches)
