@@ -91,11 +91,14 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
                      float* pooled, const unsigned char* __restrict__ wimg,
                      const float* __restrict__ b_fc1, const float* __restrict__ b_fc2,
                      const float* __restrict__ b_rd, const float* __restrict__ b_u, int num_dets,
-                     int has_a, int has_b) {
+                     int has_a, int has_b, int tile_rows) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ uint32_t tmem_base_s;
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int num_tiles = (num_dets + NT_TILE - 1) / NT_TILE;
+  // A tile covers tile_rows <= 128 detections (the UMMAs always run M = 128; rows beyond
+  // tile_rows are never loaded or stored): the launcher picks it so that every SM gets the same
+  // number of tiles - 500 tiles of 128 on 148 SMs are four rounds with the last one a quarter full.
+  const int num_tiles = (num_dets + tile_rows - 1) / tile_rows;
   if ((int)blockIdx.x >= num_tiles) return;
   const int my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   // stage_a = false (block 1): feats_in goes straight into reduce_dim, nothing is stored back
@@ -156,20 +159,20 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
       }
       const uint32_t s_feats = sbase + NT_OFF_FEATS;
       auto load_shortcut = [&](int row0) {
-        umma::mbar_expect_tx(sc_full, 4 * NT_BOX);
+        umma::mbar_expect_tx(sc_full, 4u * (uint32_t)tile_rows * 128u);   // 4 boxes of tile_rows x 128 B
         for (int b = 0; b < 4; ++b)
           umma::tma_load_2d(s_feats + b * NT_BOX, &tm_in, b * 32, row0, sc_full, umma::TMA_EVICT_FIRST);
       };
-      load_shortcut(blockIdx.x * NT_TILE);
+      load_shortcut(blockIdx.x * tile_rows);
       for (int it = 0; it < my_tiles; ++it) {
-        const int row0 = (blockIdx.x + it * gridDim.x) * NT_TILE;
+        const int row0 = (blockIdx.x + it * gridDim.x) * tile_rows;
         umma::mbar_wait_relaxed(feats_ready, (uint32_t)it & 1u);
         if (stage_a) {
           for (int b = 0; b < 4; ++b) umma::tma_store_2d(&tm_out, b * 32, row0, s_feats + b * NT_BOX);
           umma::bulk_commit_group();
           umma::bulk_wait_group_read0();        // the boxes may be overwritten
         }
-        if (it + 1 < my_tiles) load_shortcut(row0 + (int)gridDim.x * NT_TILE);
+        if (it + 1 < my_tiles) load_shortcut(row0 + (int)gridDim.x * tile_rows);
         if (stage_b) {
           umma::mbar_wait_relaxed(u_ready, (uint32_t)it & 1u);
           umma::tma_store_2d(&tm_u, 0, row0, sbase + NT_OFF_A);
@@ -219,17 +222,17 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         const int r = (i * 8 + warp) * 4 + (lane >> 3), q = lane & 7;
         pv[i][0] = make_float4(0.f, 0.f, 0.f, 0.f);
         pv[i][1] = pv[i][0];
-        if (row0 + r < num_dets) {
+        if (r < tile_rows && row0 + r < num_dets) {
           const float4* p = reinterpret_cast<const float4*>(pooled + (size_t)(row0 + r) * NT_F + q * 8);
           pv[i][0] = p[0];
           pv[i][1] = p[1];
         }
       }
     };
-    if (stage_a) load_pooled(blockIdx.x * NT_TILE);
+    if (stage_a) load_pooled(blockIdx.x * tile_rows);
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int row0 = (blockIdx.x + it * gridDim.x) * NT_TILE;
+      const int row0 = (blockIdx.x + it * gridDim.x) * tile_rows;
       NT_TR(0);
       if (stage_a) {
       // ---- pooled (prefetched) -> A (K = 64) ----------------------------------------------
@@ -265,7 +268,7 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         const int r = (i * 8 + warp) * 4 + (lane >> 4) * 2, q = lane & 15;
 #pragma unroll
         for (int j = 0; j < 2; ++j)
-          if (row0 + r + j < num_dets)
+          if (r + j < tile_rows && row0 + r + j < num_dets)
             *reinterpret_cast<float4*>(pooled + (size_t)(row0 + r + j) * NT_F + q * 4) =
                 make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -367,7 +370,7 @@ block_det_tma_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_con
         umma::mma_commit_elect(bar_mma);
       }
       weights_pending = false;
-      if (stage_a && it + 1 < my_tiles) load_pooled(row0 + (int)gridDim.x * NT_TILE);
+      if (stage_a && it + 1 < my_tiles) load_pooled(row0 + (int)gridDim.x * tile_rows);
       if (stage_b) {
         umma::mbar_wait(bar_mma, par);
         par ^= 1;
@@ -458,17 +461,28 @@ static int launch_block_det_tma(const char* name, bool x3, float* pooled, const 
   GN_REQUIRE((((uintptr_t)pooled | (uintptr_t)feats_in | (uintptr_t)feats_out | (uintptr_t)wimg |
                (uintptr_t)red_hl | (uintptr_t)u_out) & 15) == 0,
              "%s: pointers must be 16-byte aligned", name);
+  // rows per tile: the smallest that still gives every SM the same number of tiles
+  const int sms = gn::sm_count();
+  int tile_rows = gn::NT_TILE;
+  {
+    const int tiles128 = gn::ceil_div(num_dets, gn::NT_TILE);
+    if (tiles128 > sms) {
+      const int rounds = gn::ceil_div(tiles128, sms);
+      tile_rows = gn::ceil_div(num_dets, rounds * sms);
+      if (tile_rows > gn::NT_TILE) tile_rows = gn::NT_TILE;
+    }
+  }
   CUtensorMap tm_in, tm_out, tm_u, tm_red;
   const uint64_t rows = (uint64_t)num_dets;
-  int r = gn::encode_tmap_2d_f32(&tm_in, feats_in, rows, gn::NT_D, gn::NT_D * 4, gn::NT_TILE, 32);
+  int r = gn::encode_tmap_2d_f32(&tm_in, feats_in, rows, gn::NT_D, gn::NT_D * 4, tile_rows, 32);
   if (has_a) {
-    if (r == 0) r = gn::encode_tmap_2d_f32(&tm_out, feats_out, rows, gn::NT_D, gn::NT_D * 4, gn::NT_TILE, 32);
+    if (r == 0) r = gn::encode_tmap_2d_f32(&tm_out, feats_out, rows, gn::NT_D, gn::NT_D * 4, tile_rows, 32);
   } else {
     tm_out = tm_in;     // not used
   }
   if (has_b) {
-    if (r == 0) r = gn::encode_tmap_2d_f32(&tm_u, u_out, rows, gn::NT_F, gn::NT_F * 4, gn::NT_TILE, 32);
-    if (r == 0) r = gn::encode_tmap_2d_bf16(&tm_red, red_hl, rows, 2 * gn::NT_R, 4 * gn::NT_R, gn::NT_TILE, 2 * gn::NT_R);
+    if (r == 0) r = gn::encode_tmap_2d_f32(&tm_u, u_out, rows, gn::NT_F, gn::NT_F * 4, tile_rows, 32);
+    if (r == 0) r = gn::encode_tmap_2d_bf16(&tm_red, red_hl, rows, 2 * gn::NT_R, 4 * gn::NT_R, tile_rows, 2 * gn::NT_R);
   } else {
     tm_u = tm_out;
     tm_red = tm_out;
@@ -485,19 +499,18 @@ static int launch_block_det_tma(const char* name, bool x3, float* pooled, const 
     gn::set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
     return GN_ERR_CUDA;
   }
-  int grid = gn::ceil_div(num_dets, gn::NT_TILE);
-  const int sms = gn::sm_count();
+  int grid = gn::ceil_div(num_dets, tile_rows);
   if (grid > sms) grid = sms;
   if (x3)
     e = gn::launch_kernel(gn::block_det_tma_kernel<true>, grid, gn::NT_THREADS, gn::NT_SMEM,
                           (cudaStream_t)stream, gn::pdl_enabled(), tm_in, tm_out, tm_u, tm_red, pooled,
                           static_cast<const unsigned char*>(wimg), b_fc1, b_fc2, b_rd, b_u, num_dets,
-                          has_a, has_b);
+                          has_a, has_b, tile_rows);
   else
     e = gn::launch_kernel(gn::block_det_tma_kernel<false>, grid, gn::NT_THREADS, gn::NT_SMEM,
                           (cudaStream_t)stream, gn::pdl_enabled(), tm_in, tm_out, tm_u, tm_red, pooled,
                           static_cast<const unsigned char*>(wimg), b_fc1, b_fc2, b_rd, b_u, num_dets,
-                          has_a, has_b);
+                          has_a, has_b, tile_rows);
   if (e != cudaSuccess) {
     gn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e));
     return GN_ERR_CUDA;
